@@ -1,0 +1,64 @@
+"""CPU tests that PIN the oracle: both oracle back-ends must reproduce the golden vectors written by the
+unmodified reference (oracle/make_golden.py).  `ref` (the reference's own C extensions + our C FDTD) must be
+bit-exact; `port` (our C restatement, built without FMA contraction) must agree to 1e-13."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests.parity import check_state_against_golden
+
+
+def _load(g, k):
+    st = orc.OState.from_golden(g, f"t{k}")
+    st.set_reverse_x([int(g[f"t1/reverse_x/{s}"]) for s in range(st.nspec)])
+    return st
+
+
+@pytest.mark.parametrize("case", ["golden3d", "golden2d"])
+@pytest.mark.parametrize("k", [0, 1, 2])
+def test_port_single_step_matches_reference(case, k, request):
+    g = request.getfixturevalue(case)
+    st = _load(g, k)
+    orc.step(st, "port")
+    worst = check_state_against_golden(st, g, f"t{k + 1}", rtol=1e-13)
+    assert worst < 1e-13
+
+
+@pytest.mark.skipif(not orc.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("case", ["golden3d", "golden2d"])
+@pytest.mark.parametrize("k", [0, 1, 2])
+def test_ref_extensions_single_step_bit_exact(case, k, request):
+    g = request.getfixturevalue(case)
+    st = _load(g, k)
+    orc.step(st, "ref")
+    worst = check_state_against_golden(st, g, f"t{k + 1}", rtol=0.0)
+    assert worst == 0.0
+
+
+@pytest.mark.parametrize("case", ["golden3d", "golden2d"])
+def test_port_three_steps_from_t0(case, request):
+    g = request.getfixturevalue(case)
+    st = _load(g, 0)
+    for _ in range(3):
+        orc.step(st, "port")
+    check_state_against_golden(st, g, "t3", rtol=1e-12)
+
+
+def test_reverse_x_decision_matches_reference(golden3d):
+    st = orc.OState.from_golden(golden3d, "t0")
+    for s in range(st.nspec):
+        assert orc.decide_reverse_x(st, s) == bool(int(golden3d[f"t1/reverse_x/{s}"]))
+
+
+def test_charge_conservation_known_answer(golden3d):
+    """Known answer of the reference's own tests (tests/core/current/test_current_deposition.py:517-557):
+    sum(rho) = q * sum(w) / dV over alive particles."""
+    st = _load(golden3d, 0)
+    orc.reset_currents(st)
+    for s in range(st.nspec):
+        orc.push_deposit(st, s, "port")
+    dV = st.dx * st.dy * st.dz
+    total = sum(float(p.fields.rho.sum()) for p in st.patches)
+    expect = sum(st.q[s] * float(p.particles[s].w[~p.particles[s].is_dead].sum()) for p in st.patches for s in range(st.nspec)) / dV
+    scale = sum(abs(st.q[s]) * float(p.particles[s].w.sum()) for p in st.patches for s in range(st.nspec)) / dV
+    assert abs(total - expect) <= 1e-10 * scale
