@@ -1,0 +1,144 @@
+/*
+ * lpic_b200.h -- C-ABI of the B200-native lambdaPIC inner loop (liblpic_b200.so).
+ *
+ * Plain pointers and sizes only: no CUDA, torch or Python types cross this boundary.  Every entry point
+ * names the reference interface it replaces (paths relative to /root/reference/src/lambdapic/).  All
+ * functions return 0 on success or a negative status; lpic_last_error() then holds a message (no
+ * exceptions cross the boundary).  Kernels run on the context's own CUDA stream; calls that return
+ * values to the host (download, sort's nbuf, migrate_count) synchronise that stream, the others do not.
+ *
+ * Data model (reference: core/fields.py:71-170, core/particles.py:8-217):
+ *   fields    10 fp64 grids per patch  ex ey ez bx by bz jx jy jz rho, C-contiguous (NX,NY[,NZ]) with
+ *             N = n + 2*n_guard and the reference's WRAPPED guard layout (logical index -k lives at N-k).
+ *             Device arena = [attr][patch][NX*NY*NZ]; the host mirror handed to upload/download has the
+ *             same shape, so one copy moves one attribute of every patch.
+ *   particles SoA fp64 x y z w ux uy uz inv_gamma ex_part..bz_part _id + uint8 is_dead per
+ *             (species, patch).  Device arena per (species, attribute): patch p owns the slots
+ *             [off[p], off[p] + npart[p]) of a segment of physical size pcap[p] >= npart[p]; `npart`
+ *             is the reference's capacity (alive + dead slots).  The six *_part arrays are optional.
+ */
+#ifndef LPIC_B200_H
+#define LPIC_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lpic_ctx lpic_ctx;
+
+/* attribute ids: order of Fields.attrs (core/fields.py:71-75) and ParticlesBase.attrs (core/particles.py:63-67) */
+enum { LPIC_EX = 0, LPIC_EY, LPIC_EZ, LPIC_BX, LPIC_BY, LPIC_BZ, LPIC_JX, LPIC_JY, LPIC_JZ, LPIC_RHO, LPIC_NFIELD };
+enum { LPIC_P_X = 0, LPIC_P_Y, LPIC_P_Z, LPIC_P_W, LPIC_P_UX, LPIC_P_UY, LPIC_P_UZ, LPIC_P_INV_GAMMA,
+       LPIC_P_EX_PART, LPIC_P_EY_PART, LPIC_P_EZ_PART, LPIC_P_BX_PART, LPIC_P_BY_PART, LPIC_P_BZ_PART,
+       LPIC_P_ID, LPIC_NPATTR, LPIC_P_IS_DEAD = LPIC_NPATTR };
+/* sorter arrays (core/sort/particle_sort.py:20-160) */
+enum { LPIC_SORT_BUCKET_COUNT = 0, LPIC_SORT_BOUND_MIN, LPIC_SORT_BOUND_MAX, LPIC_SORT_PARTICLE_INDEX };
+/* flags of lpic_push_deposit */
+enum { LPIC_PUSH_WRITE_PART = 1 };
+
+const char *lpic_last_error(void);
+int lpic_device_count(void);
+/* version / build info: "lpic_b200 <ver> sm_100a" */
+const char *lpic_version(void);
+
+/* pinned host memory for the mirrors (falls back to malloc when no CUDA device is present) */
+void *lpic_host_alloc(int64_t bytes);
+void lpic_host_free(void *p);
+
+/* ---- context ------------------------------------------------------------------------------------
+ * Replaces the per-call pointer-table construction of every reference extension
+ * (core/utils/cutils.h:32-100, core/pusher/unified/unified_pusher_3d.c:234-276). */
+lpic_ctx *lpic_create(int dim, int64_t npatch, int64_t nx, int64_t ny, int64_t nz, int64_t n_guard,
+                      double dx, double dy, double dz, int nspec, int device);
+void lpic_destroy(lpic_ctx *ctx);
+/* x0,y0,z0: patch origins (core/patch/patch.py:272-273); neighbor_ipatch: (npatch, 8|26) int64 in the
+ * reference's Boundary2D/3D enum order (core/patch/patch.py:24-69), <0 = no local neighbour;
+ * box: (npatch, 6) particle boxes xmin,xmax,ymin,ymax,zmin,zmax ALREADY widened by half a cell
+ * (core/patch/sync_particles_3d.c:402-411); glob: global particle box (simulation/simulation.py:425-430);
+ * rank: MPI-style rank used in new particle ids (core/particles.py:91-116); patch_index: Patch.index. */
+int lpic_set_patch_geometry(lpic_ctx *ctx, const double *x0, const double *y0, const double *z0,
+                            const int64_t *neighbor_ipatch, const double *box, const double *glob,
+                            int64_t rank, const int64_t *patch_index);
+int lpic_sync(lpic_ctx *ctx); /* cudaStreamSynchronize on the context stream */
+
+/* ---- field mirrors ------------------------------------------------------------------------------ */
+int64_t lpic_field_cells(const lpic_ctx *ctx);                                    /* NX*NY*NZ per patch */
+/* host = base of a [LPIC_NFIELD][npatch][cells] fp64 arena; only attributes in attr_mask are copied */
+int lpic_upload_fields(lpic_ctx *ctx, uint32_t attr_mask, const double *host);
+int lpic_download_fields(lpic_ctx *ctx, uint32_t attr_mask, double *host);
+/* per-patch pointer variant for callers that keep the reference's separately allocated numpy arrays */
+int lpic_upload_field_ptrs(lpic_ctx *ctx, int attr, const double *const *host_ptrs);
+int lpic_download_field_ptrs(lpic_ctx *ctx, int attr, double *const *host_ptrs);
+
+/* ---- particle mirrors --------------------------------------------------------------------------- */
+/* (re)allocate species `ispec` with logical capacities npart[npatch]; physical segment size is
+ * max(npart*slack, npart+min_extra) rounded up to 32 slots.  with_part_fields!=0 also keeps ex_part..bz_part. */
+int lpic_species_alloc(lpic_ctx *ctx, int ispec, const int64_t *npart, double slack, int64_t min_extra,
+                       int with_part_fields);
+int lpic_species_layout(const lpic_ctx *ctx, int ispec, int64_t *off, int64_t *pcap, int64_t *npart, int64_t *total);
+/* host = base of an arena with the device's layout (total slots; fp64, or uint8 for LPIC_P_IS_DEAD) */
+int lpic_upload_particles(lpic_ctx *ctx, int ispec, int attr, const void *host);
+int lpic_download_particles(lpic_ctx *ctx, int ispec, int attr, void *host);
+int lpic_upload_particle_ptrs(lpic_ctx *ctx, int ispec, int attr, const void *const *host_ptrs);
+int lpic_download_particle_ptrs(lpic_ctx *ctx, int ispec, int attr, void *const *host_ptrs);
+/* ParticlesBase.extend (core/particles.py:141-168) for every patch at once: appends ext[p] dead slots
+ * (NaN attributes, w = 0, fresh ids starting at id_first[p]).  *relayout is set when a segment outgrew its
+ * physical size and the arena was re-laid-out (host arena offsets must be re-read). */
+int lpic_species_extend(lpic_ctx *ctx, int ispec, const int64_t *ext, const uint64_t *id_first, int *relayout);
+
+/* ---- Maxwell: core/maxwell/cpu.py:9-35 (2D), :83-112 (3D); facade core/maxwell/solver/solver.py:193-254 */
+int lpic_update_efield(lpic_ctx *ctx, double dt);
+int lpic_update_bfield(lpic_ctx *ctx, double dt);
+
+/* ---- guard cells: core/patch/sync_fields3d.c:350-620 / :84-348, sync_fields2d.c:150-255 / :43-148;
+ *      facade core/patch/patch.py:670-703.  attr_mask: bit a = field attribute a. */
+int lpic_sync_guard_fields(lpic_ctx *ctx, uint32_t attr_mask);
+int lpic_sync_currents(lpic_ctx *ctx);
+/* core/current/cpu3d.c:185-240 (reset_current_cpu_3d), cpu2d.c twin */
+int lpic_reset_currents(lpic_ctx *ctx);
+
+/* ---- particles ----------------------------------------------------------------------------------
+ * unified_boris_pusher_cpu_{2d,3d}(particles_list, fields_list, npatches, dt, q, m)
+ * (core/pusher/unified/unified_pusher_3d.c:219-436, unified_pusher_2d.c:157-365) */
+int lpic_push_deposit(lpic_ctx *ctx, int ispec, double dt, double q, double m, int flags);
+/* non-fused stages: interpolation_patches_* (core/interpolation/cpu3d.c:99-169), boris_push_patches and
+ * push_position_patches_2d (core/pusher/cpu.py:10-90), current_deposition_cpu_* (core/current/cpu3d.c:118-184) */
+int lpic_interpolate(lpic_ctx *ctx, int ispec);
+int lpic_push_momentum(lpic_ctx *ctx, int ispec, double dt, double q, double m);
+int lpic_push_position(lpic_ctx *ctx, int ispec, double dt);
+int lpic_deposit(lpic_ctx *ctx, int ispec, double dt, double q);
+
+/* ---- sort: sort_particles_patches_{2d,3d} (core/sort/cpu3d.c:214-299); x0s..: per-patch bucket origins
+ *      (core/sort/particle_sort.py:331-333).  *nbuf_total receives the reference's return value. */
+int lpic_sort(lpic_ctx *ctx, int ispec, int reverse_x, int64_t nxb, int64_t nyb, int64_t nzb,
+              double dxb, double dyb, double dzb, const double *x0s, const double *y0s, const double *z0s,
+              int64_t *nbuf_total);
+/* which = LPIC_SORT_*; out: bucket arrays (npatch, nbin) int64, particle_index: arena layout int64 */
+int lpic_sort_download(lpic_ctx *ctx, int ispec, int which, int64_t *out);
+/* sums for the mirrored-order decision (core/sort/particle_sort.py:64-89): out[0]=sum w, out[1]=sum w*ux (alive) */
+int lpic_weighted_drift(lpic_ctx *ctx, int ispec, double *out2);
+
+/* ---- intra-rank migration: get_npart_to_extend_* / fill_particles_from_boundary_*
+ *      (core/patch/sync_particles_3d.c:365-482 / :484-695; facade core/patch/patch.py:705-764) */
+int lpic_migrate_count(lpic_ctx *ctx, int ispec, int64_t *npart_to_extend, int64_t *npart_incoming,
+                       int64_t *npart_outgoing, int64_t *npart_alive);
+int lpic_migrate_fill(lpic_ctx *ctx, int ispec);
+
+/* ---- diagnostics (device-side reductions used by the bench and the energy-history test) ---------- */
+int lpic_count_alive(lpic_ctx *ctx, int ispec, int64_t *out);
+/* out[0] = sum w*(gamma-1) over alive particles of ispec (kinetic energy / (m c^2)) */
+int lpic_kinetic_sum(lpic_ctx *ctx, int ispec, double *out);
+/* out[0] = sum E^2, out[1] = sum B^2 over interior cells */
+int lpic_field_energy_sums(lpic_ctx *ctx, double *out2);
+
+/* ---- synthetic loader for the bench (uniform-in-cell positions as core/patch/cpu.py:66-99, thermal
+ *      momenta with per-component sigma `uth`); deterministic in (seed, patch, slot) */
+int lpic_species_init_uniform(lpic_ctx *ctx, int ispec, int64_t ppc, double weight, double uth, uint64_t seed);
+
+void *lpic_stream(lpic_ctx *ctx); /* cudaStream_t of the context (for event timing by the host) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,457 @@
+// Context, device arenas and host<->device mirrors of the C-ABI (include/lpic_b200.h).
+#include <stdarg.h>
+#include <stdlib.h>
+#include <algorithm>
+#include <vector>
+#include "lpic_common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void lpic_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *lpic_last_error(void) { return g_err; }
+extern "C" const char *lpic_version(void) { return "lpic_b200 0.1 sm_100a"; }
+
+extern "C" int lpic_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// pinned allocations are remembered so lpic_host_free knows how to release them
+static std::vector<void *> g_pinned;
+
+extern "C" void *lpic_host_alloc(int64_t bytes) {
+    if (bytes <= 0) bytes = 8;
+    void *p = nullptr;
+    if (lpic_device_count() > 0 && cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) == cudaSuccess) {
+        g_pinned.push_back(p);
+        return p;
+    }
+    cudaGetLastError();
+    return malloc((size_t)bytes);
+}
+
+extern "C" void lpic_host_free(void *p) {
+    if (!p) return;
+    auto it = std::find(g_pinned.begin(), g_pinned.end(), p);
+    if (it != g_pinned.end()) {
+        g_pinned.erase(it);
+        cudaFreeHost(p);
+    } else {
+        free(p);
+    }
+}
+
+extern "C" lpic_ctx *lpic_create(int dim, int64_t npatch, int64_t nx, int64_t ny, int64_t nz, int64_t ng, double dx,
+                                 double dy, double dz, int nspec, int device) {
+    if (!(dim == 2 || dim == 3) || npatch <= 0 || nx <= 0 || ny <= 0 || ng < 0 || nspec < 0 || (dim == 3 && nz <= 0)) {
+        lpic_set_error("lpic_create: bad arguments");
+        return nullptr;
+    }
+    if (lpic_device_count() <= device) {
+        lpic_set_error("lpic_create: CUDA device %d not available (this library has no CPU fallback)", device);
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) {
+        lpic_set_error("cudaSetDevice(%d) failed", device);
+        return nullptr;
+    }
+    lpic_ctx *c = new lpic_ctx();
+    Geom &g = c->g;
+    g.dim = dim; g.nb = dim == 3 ? 26 : 8;
+    g.nx = (int)nx; g.ny = (int)ny; g.nz = dim == 3 ? (int)nz : 1; g.ng = (int)ng; g.ngz = dim == 3 ? (int)ng : 0;
+    g.NX = g.nx + 2 * g.ng; g.NY = g.ny + 2 * g.ng; g.NZ = g.nz + 2 * g.ngz;
+    g.ncell = g.NX * g.NY * g.NZ;
+    g.npatch = (int)npatch;
+    g.dx = dx; g.dy = dy; g.dz = dim == 3 ? dz : 1.0;
+    c->device = device;
+    c->nspec = nspec;
+    c->spec = new Species[nspec > 0 ? nspec : 1];
+    bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+    const size_t fbytes = sizeof(double) * LPIC_NFIELD * (size_t)npatch * g.ncell;
+    ok = ok && cudaMalloc(&c->fields, fbytes) == cudaSuccess;
+    ok = ok && cudaMemset(c->fields, 0, fbytes) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_x0, sizeof(double) * npatch) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_y0, sizeof(double) * npatch) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_z0, sizeof(double) * npatch) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_nbr, sizeof(i64) * npatch * g.nb) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_box, sizeof(double) * npatch * 6) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_sort_org, sizeof(double) * npatch * 3) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_tmp64, sizeof(i64) * (64 + 16 * npatch)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_tmpf, sizeof(double) * 64) == cudaSuccess;
+    if (!ok) {
+        lpic_set_error("lpic_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        lpic_destroy(c);
+        return nullptr;
+    }
+    c->h_x0 = new double[npatch]; c->h_y0 = new double[npatch]; c->h_z0 = new double[npatch];
+    c->h_nbr = new i64[npatch * g.nb];
+    c->h_patch_index = new i64[npatch];
+    for (i64 p = 0; p < npatch; p++) c->h_patch_index[p] = p;
+    return c;
+}
+
+static void free_species(Species &sp) {
+    for (int a = 0; a < LPIC_NPATTR; a++) { cudaFree(sp.attr[a]); sp.attr[a] = nullptr; }
+    cudaFree(sp.dead); sp.dead = nullptr;
+    cudaFree(sp.d_off); cudaFree(sp.d_npart); sp.d_off = sp.d_npart = nullptr;
+    cudaFree(sp.sort.bucket_count); cudaFree(sp.sort.bound_min); cudaFree(sp.sort.bound_max); cudaFree(sp.sort.pidx);
+    sp.sort = SortState();
+    cudaFree(sp.d_out); cudaFree(sp.d_ndead); cudaFree(sp.d_incoming); cudaFree(sp.d_extend); cudaFree(sp.d_alive);
+    sp.d_out = sp.d_ndead = sp.d_incoming = sp.d_extend = sp.d_alive = nullptr;
+    delete[] sp.h_off; delete[] sp.h_pcap; delete[] sp.h_npart;
+    sp.h_off = sp.h_pcap = sp.h_npart = nullptr;
+    sp.allocated = false;
+}
+
+void lpic_free_peers(lpic_ctx *c);
+
+extern "C" void lpic_destroy(lpic_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int s = 0; s < c->nspec; s++) free_species(c->spec[s]);
+    delete[] c->spec;
+    lpic_free_peers(c);
+    cudaFree(c->fields); cudaFree(c->d_x0); cudaFree(c->d_y0); cudaFree(c->d_z0); cudaFree(c->d_nbr); cudaFree(c->d_box);
+    cudaFree(c->scr_a); cudaFree(c->scr_b); cudaFree(c->scr_buf); cudaFree(c->d_sort_org); cudaFree(c->d_tmp64); cudaFree(c->d_tmpf);
+    delete[] c->h_x0; delete[] c->h_y0; delete[] c->h_z0; delete[] c->h_nbr; delete[] c->h_patch_index;
+    delete[] c->h_nbr_rank; delete[] c->h_remote_ipatch;
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int lpic_set_patch_geometry(lpic_ctx *c, const double *x0, const double *y0, const double *z0,
+                                       const int64_t *nbr, const double *box, const double *glob, int64_t rank,
+                                       const int64_t *patch_index) {
+    const Geom &g = c->g;
+    const i64 n = g.npatch;
+    std::vector<double> zeros(n, 0.0);
+    if (!z0) z0 = zeros.data();
+    memcpy(c->h_x0, x0, sizeof(double) * n); memcpy(c->h_y0, y0, sizeof(double) * n); memcpy(c->h_z0, z0, sizeof(double) * n);
+    memcpy(c->h_nbr, nbr, sizeof(i64) * n * g.nb);
+    for (i64 i = 0; i < n * g.nb; i++) REQUIRE(nbr[i] < n, "neighbor_ipatch[%lld] = %lld out of range", (long long)i, (long long)nbr[i]);
+    memcpy(c->glob, glob, sizeof(double) * 6);
+    c->rank = rank;
+    if (patch_index) memcpy(c->h_patch_index, patch_index, sizeof(i64) * n);
+    CUDA_TRY(cudaMemcpyAsync(c->d_x0, c->h_x0, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->d_y0, c->h_y0, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->d_z0, c->h_z0, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->d_nbr, c->h_nbr, sizeof(i64) * n * g.nb, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->d_box, box, sizeof(double) * n * 6, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int lpic_sync(lpic_ctx *c) {
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+extern "C" void *lpic_stream(lpic_ctx *c) { return (void *)c->stream; }
+extern "C" int64_t lpic_field_cells(const lpic_ctx *c) { return c->g.ncell; }
+
+// ---- fields --------------------------------------------------------------------------------------------------
+static int copy_fields(lpic_ctx *c, uint32_t mask, double *host, bool up) {
+    const size_t n = (size_t)c->g.npatch * c->g.ncell;
+    int a = 0;
+    while (a < LPIC_NFIELD) {  // coalesce runs of consecutive attributes into one copy
+        if (!(mask & (1u << a))) { a++; continue; }
+        int b = a;
+        while (b + 1 < LPIC_NFIELD && (mask & (1u << (b + 1)))) b++;
+        const size_t bytes = sizeof(double) * n * (b - a + 1);
+        if (up) CUDA_TRY(cudaMemcpyAsync(field_ptr(c, a), host + n * a, bytes, cudaMemcpyHostToDevice, c->stream));
+        else CUDA_TRY(cudaMemcpyAsync(host + n * a, field_ptr(c, a), bytes, cudaMemcpyDeviceToHost, c->stream));
+        a = b + 1;
+    }
+    if (!up) CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+extern "C" int lpic_upload_fields(lpic_ctx *c, uint32_t mask, const double *host) { return copy_fields(c, mask, (double *)host, true); }
+extern "C" int lpic_download_fields(lpic_ctx *c, uint32_t mask, double *host) { return copy_fields(c, mask, host, false); }
+
+extern "C" int lpic_upload_field_ptrs(lpic_ctx *c, int attr, const double *const *ptrs) {
+    REQUIRE(attr >= 0 && attr < LPIC_NFIELD, "bad field attribute %d", attr);
+    for (int p = 0; p < c->g.npatch; p++)
+        CUDA_TRY(cudaMemcpyAsync(field_ptr(c, attr) + (size_t)p * c->g.ncell, ptrs[p], sizeof(double) * c->g.ncell,
+                                 cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+extern "C" int lpic_download_field_ptrs(lpic_ctx *c, int attr, double *const *ptrs) {
+    REQUIRE(attr >= 0 && attr < LPIC_NFIELD, "bad field attribute %d", attr);
+    for (int p = 0; p < c->g.npatch; p++)
+        CUDA_TRY(cudaMemcpyAsync(ptrs[p], field_ptr(c, attr) + (size_t)p * c->g.ncell, sizeof(double) * c->g.ncell,
+                                 cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- particles -----------------------------------------------------------------------------------------------
+static bool attr_resident(const Species &sp, int a) {
+    return a < LPIC_P_EX_PART || a > LPIC_P_BZ_PART || sp.with_part;
+}
+
+static i64 phys_cap(i64 npart, double slack, i64 min_extra) {
+    i64 c = std::max((i64)(npart * slack), npart + min_extra);
+    return ((c + 31) / 32) * 32;
+}
+
+static int upload_layout(lpic_ctx *c, Species &sp) {
+    const i64 n = c->g.npatch;
+    sp.max_npart = 0;
+    for (i64 p = 0; p < n; p++) sp.max_npart = std::max(sp.max_npart, sp.h_npart[p]);
+    CUDA_TRY(cudaMemcpyAsync(sp.d_off, sp.h_off, sizeof(i64) * n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(sp.d_npart, sp.h_npart, sizeof(i64) * n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));  // h_* may be rewritten by the caller right after
+    return 0;
+}
+
+extern "C" int lpic_species_alloc(lpic_ctx *c, int ispec, const int64_t *npart, double slack, int64_t min_extra,
+                                  int with_part) {
+    REQUIRE(ispec >= 0 && ispec < c->nspec, "bad species %d", ispec);
+    Species &sp = c->spec[ispec];
+    const i64 n = c->g.npatch;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    free_species(sp);
+    sp.with_part = with_part != 0;
+    sp.h_off = new i64[n]; sp.h_pcap = new i64[n]; sp.h_npart = new i64[n];
+    i64 total = 0;
+    for (i64 p = 0; p < n; p++) {
+        REQUIRE(npart[p] >= 0, "negative npart");
+        sp.h_npart[p] = npart[p];
+        sp.h_pcap[p] = phys_cap(npart[p], slack < 1.0 ? 1.0 : slack, min_extra < 0 ? 0 : min_extra);
+        sp.h_off[p] = total;
+        total += sp.h_pcap[p];
+    }
+    sp.total = total;
+    const size_t slots = (size_t)std::max<i64>(total, 1);
+    for (int a = 0; a < LPIC_NPATTR; a++)
+        if (attr_resident(sp, a)) CUDA_TRY(cudaMalloc(&sp.attr[a], sizeof(double) * slots));
+    CUDA_TRY(cudaMalloc(&sp.dead, slots));
+    CUDA_TRY(cudaMemsetAsync(sp.dead, 1, slots, c->stream));
+    CUDA_TRY(cudaMalloc(&sp.sort.pidx, sizeof(int) * slots));  // particle_index starts at -1 (particle_sort.py:120-131)
+    CUDA_TRY(cudaMemsetAsync(sp.sort.pidx, 0xff, sizeof(int) * slots, c->stream));
+    sp.sort.pidx_cap = (i64)slots;
+    CUDA_TRY(cudaMalloc(&sp.d_off, sizeof(i64) * n));
+    CUDA_TRY(cudaMalloc(&sp.d_npart, sizeof(i64) * n));
+    CUDA_TRY(cudaMalloc(&sp.d_out, sizeof(i64) * n * c->g.nb));
+    CUDA_TRY(cudaMalloc(&sp.d_ndead, sizeof(i64) * n));
+    CUDA_TRY(cudaMalloc(&sp.d_incoming, sizeof(i64) * n));
+    CUDA_TRY(cudaMalloc(&sp.d_extend, sizeof(i64) * n));
+    CUDA_TRY(cudaMalloc(&sp.d_alive, sizeof(i64) * n));
+    sp.allocated = true;
+    return upload_layout(c, sp);
+}
+
+extern "C" int lpic_species_layout(const lpic_ctx *c, int ispec, int64_t *off, int64_t *pcap, int64_t *npart, int64_t *total) {
+    REQUIRE(ispec >= 0 && ispec < c->nspec && c->spec[ispec].allocated, "species %d not allocated", ispec);
+    const Species &sp = c->spec[ispec];
+    const i64 n = c->g.npatch;
+    if (off) memcpy(off, sp.h_off, sizeof(i64) * n);
+    if (pcap) memcpy(pcap, sp.h_pcap, sizeof(i64) * n);
+    if (npart) memcpy(npart, sp.h_npart, sizeof(i64) * n);
+    if (total) *total = sp.total;
+    return 0;
+}
+
+static int particle_array(lpic_ctx *c, int ispec, int attr, void **dev, size_t *esz) {
+    REQUIRE(ispec >= 0 && ispec < c->nspec && c->spec[ispec].allocated, "species %d not allocated", ispec);
+    Species &sp = c->spec[ispec];
+    if (attr == LPIC_P_IS_DEAD) { *dev = sp.dead; *esz = 1; return 0; }
+    REQUIRE(attr >= 0 && attr < LPIC_NPATTR, "bad particle attribute %d", attr);
+    REQUIRE(attr_resident(sp, attr), "attribute %d is not resident (species allocated without *_part)", attr);
+    *dev = sp.attr[attr]; *esz = sizeof(double);
+    return 0;
+}
+
+extern "C" int lpic_upload_particles(lpic_ctx *c, int ispec, int attr, const void *host) {
+    void *dev; size_t esz;
+    if (int r = particle_array(c, ispec, attr, &dev, &esz)) return r;
+    CUDA_TRY(cudaMemcpyAsync(dev, host, esz * c->spec[ispec].total, cudaMemcpyHostToDevice, c->stream));
+    c->spec[ispec].sort.valid = false;
+    return 0;
+}
+extern "C" int lpic_download_particles(lpic_ctx *c, int ispec, int attr, void *host) {
+    void *dev; size_t esz;
+    if (int r = particle_array(c, ispec, attr, &dev, &esz)) return r;
+    CUDA_TRY(cudaMemcpyAsync(host, dev, esz * c->spec[ispec].total, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+extern "C" int lpic_upload_particle_ptrs(lpic_ctx *c, int ispec, int attr, const void *const *ptrs) {
+    void *dev; size_t esz;
+    if (int r = particle_array(c, ispec, attr, &dev, &esz)) return r;
+    Species &sp = c->spec[ispec];
+    for (int p = 0; p < c->g.npatch; p++)
+        if (sp.h_npart[p] > 0)
+            CUDA_TRY(cudaMemcpyAsync((char *)dev + esz * sp.h_off[p], ptrs[p], esz * sp.h_npart[p], cudaMemcpyHostToDevice, c->stream));
+    sp.sort.valid = false;
+    return 0;
+}
+extern "C" int lpic_download_particle_ptrs(lpic_ctx *c, int ispec, int attr, void *const *ptrs) {
+    void *dev; size_t esz;
+    if (int r = particle_array(c, ispec, attr, &dev, &esz)) return r;
+    Species &sp = c->spec[ispec];
+    for (int p = 0; p < c->g.npatch; p++)
+        if (sp.h_npart[p] > 0)
+            CUDA_TRY(cudaMemcpyAsync(ptrs[p], (char *)dev + esz * sp.h_off[p], esz * sp.h_npart[p], cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ParticlesBase.extend (core/particles.py:141-168): new slots are NaN, w = 0, dead, with fresh ids.
+__global__ void __launch_bounds__(256) k_extend_init(int npatch, const i64 *__restrict__ off, const i64 *__restrict__ old_npart,
+                                                     const i64 *__restrict__ ext, const u64 *__restrict__ id_first,
+                                                     double *const *attrs, int nattr, int ia_w, int ia_id, u8 *dead,
+                                                     int blocks_per_patch) {
+    const int p = blockIdx.x / blocks_per_patch;
+    const i64 t = (i64)(blockIdx.x - p * blocks_per_patch) * blockDim.x + threadIdx.x;
+    if (t >= ext[p]) return;
+    const i64 ip = off[p] + old_npart[p] + t;
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    for (int a = 0; a < nattr; a++) {
+        double v = nan;
+        if (a == ia_w) v = 0.0;
+        if (a == ia_id) v = __longlong_as_double((long long)(id_first[p] + (u64)t));
+        attrs[a][ip] = v;
+    }
+    dead[ip] = 1;
+}
+
+__global__ void __launch_bounds__(256) k_pidx_reset(const i64 *__restrict__ off, const i64 *__restrict__ old_npart,
+                                                    const i64 *__restrict__ ext, int *__restrict__ pidx, int blocks_per_patch) {
+    const int p = blockIdx.x / blocks_per_patch;
+    const i64 t = (i64)(blockIdx.x - p * blocks_per_patch) * blockDim.x + threadIdx.x;
+    if (ext[p] <= 0 || t >= old_npart[p] + ext[p]) return;
+    pidx[off[p] + t] = -1;
+}
+
+// move every patch segment from the old arena offsets to the new ones (one attribute at a time)
+template <typename T>
+__global__ void __launch_bounds__(256) k_relayout(const T *__restrict__ src, T *__restrict__ dst, const i64 *__restrict__ old_off,
+                                                  const i64 *__restrict__ new_off, const i64 *__restrict__ npart,
+                                                  int blocks_per_patch) {
+    const int p = blockIdx.x / blocks_per_patch;
+    const i64 t = (i64)(blockIdx.x - p * blocks_per_patch) * blockDim.x + threadIdx.x;
+    if (t >= npart[p]) return;
+    dst[new_off[p] + t] = src[old_off[p] + t];
+}
+
+extern "C" int lpic_species_extend(lpic_ctx *c, int ispec, const int64_t *ext, const uint64_t *id_first, int *relayout) {
+    REQUIRE(ispec >= 0 && ispec < c->nspec && c->spec[ispec].allocated, "species %d not allocated", ispec);
+    Species &sp = c->spec[ispec];
+    const i64 n = c->g.npatch;
+    if (relayout) *relayout = 0;
+    i64 max_ext = 0;
+    bool fits = true;
+    for (i64 p = 0; p < n; p++) {
+        REQUIRE(ext[p] >= 0, "negative extension");
+        max_ext = std::max(max_ext, (i64)ext[p]);
+        if (sp.h_npart[p] + ext[p] > sp.h_pcap[p]) fits = false;
+    }
+    if (max_ext == 0) return 0;
+    // small device tables: old npart is still in d_npart; ext / id_first go to scratch
+    i64 *d_ext = nullptr;
+    u64 *d_idf = nullptr;
+    CUDA_TRY(cudaMalloc(&d_ext, sizeof(i64) * n * 3));
+    d_idf = (u64 *)(d_ext + n);
+    i64 *d_newoff = d_ext + 2 * n;
+    CUDA_TRY(cudaMemcpyAsync(d_ext, ext, sizeof(i64) * n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_idf, id_first, sizeof(u64) * n, cudaMemcpyHostToDevice, c->stream));
+    if (!fits) {
+        // re-layout: every segment gets room for its new size plus the same relative slack as before
+        std::vector<i64> new_off(n), new_pcap(n);
+        i64 total = 0;
+        for (i64 p = 0; p < n; p++) {
+            const i64 want = sp.h_npart[p] + ext[p];
+            new_pcap[p] = std::max(sp.h_pcap[p], phys_cap(want, 1.25, 64));
+            new_off[p] = total;
+            total += new_pcap[p];
+        }
+        CUDA_TRY(cudaMemcpyAsync(d_newoff, new_off.data(), sizeof(i64) * n, cudaMemcpyHostToDevice, c->stream));
+        const int bpp = (int)div_up(std::max<i64>(sp.max_npart, 1), 256);
+        for (int a = 0; a < LPIC_NPATTR; a++) {
+            if (!attr_resident(sp, a)) continue;
+            double *fresh = nullptr;
+            CUDA_TRY(cudaMalloc(&fresh, sizeof(double) * total));
+            k_relayout<double><<<(unsigned)((i64)bpp * n), 256, 0, c->stream>>>(sp.attr[a], fresh, sp.d_off, d_newoff, sp.d_npart, bpp);
+            KERNEL_CHECK();
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            cudaFree(sp.attr[a]);
+            sp.attr[a] = fresh;
+        }
+        u8 *fresh_dead = nullptr;
+        CUDA_TRY(cudaMalloc(&fresh_dead, (size_t)total));
+        CUDA_TRY(cudaMemsetAsync(fresh_dead, 1, (size_t)total, c->stream));
+        k_relayout<u8><<<(unsigned)((i64)bpp * n), 256, 0, c->stream>>>(sp.dead, fresh_dead, sp.d_off, d_newoff, sp.d_npart, bpp);
+        KERNEL_CHECK();
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        cudaFree(sp.dead);
+        sp.dead = fresh_dead;
+        int *fresh_pidx = nullptr;
+        CUDA_TRY(cudaMalloc(&fresh_pidx, sizeof(int) * (size_t)total));
+        CUDA_TRY(cudaMemsetAsync(fresh_pidx, 0xff, sizeof(int) * (size_t)total, c->stream));
+        k_relayout<int><<<(unsigned)((i64)bpp * n), 256, 0, c->stream>>>(sp.sort.pidx, fresh_pidx, sp.d_off, d_newoff, sp.d_npart, bpp);
+        KERNEL_CHECK();
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        cudaFree(sp.sort.pidx);
+        sp.sort.pidx = fresh_pidx;
+        sp.sort.pidx_cap = total;
+        for (i64 p = 0; p < n; p++) { sp.h_off[p] = new_off[p]; sp.h_pcap[p] = new_pcap[p]; }
+        sp.total = total;
+        CUDA_TRY(cudaMemcpyAsync(sp.d_off, sp.h_off, sizeof(i64) * n, cudaMemcpyHostToDevice, c->stream));
+        if (relayout) *relayout = 1;
+    }
+    // initialise the appended slots
+    double *h_attrs[LPIC_NPATTR];
+    int na = 0, ia_w = -1, ia_id = -1;
+    for (int a = 0; a < LPIC_NPATTR; a++) {
+        if (!attr_resident(sp, a)) continue;
+        if (a == LPIC_P_W) ia_w = na;
+        if (a == LPIC_P_ID) ia_id = na;
+        h_attrs[na++] = sp.attr[a];
+    }
+    double **d_attrs = nullptr;
+    CUDA_TRY(cudaMalloc(&d_attrs, sizeof(double *) * na));
+    CUDA_TRY(cudaMemcpyAsync(d_attrs, h_attrs, sizeof(double *) * na, cudaMemcpyHostToDevice, c->stream));
+    const int bpp = (int)div_up(max_ext, 256);
+    k_extend_init<<<(unsigned)((i64)bpp * n), 256, 0, c->stream>>>((int)n, sp.d_off, sp.d_npart, d_ext, d_idf, d_attrs, na,
+                                                                 ia_w, ia_id, sp.dead, bpp);
+    KERNEL_CHECK();
+    for (i64 p = 0; p < n; p++) sp.h_npart[p] += ext[p];
+    {   // the reference re-creates the sorter's index arrays (-1) for every extended patch (simulation.py:781-824)
+        i64 m = 0;
+        for (i64 p = 0; p < n; p++) m = std::max(m, sp.h_npart[p]);
+        const int bpp2 = (int)div_up(std::max<i64>(m, 1), 256);
+        k_pidx_reset<<<(unsigned)((i64)bpp2 * n), 256, 0, c->stream>>>(sp.d_off, sp.d_npart, d_ext, sp.sort.pidx, bpp2);
+        KERNEL_CHECK();
+    }
+    int r = upload_layout(c, sp);  // synchronises the stream
+    cudaFree(d_ext);
+    cudaFree(d_attrs);
+    sp.sort.valid = false;
+    return r;
+}
+
+int lpic_ensure_scratch(lpic_ctx *c, i64 slots) {
+    if (slots <= c->scr_cap) return 0;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    cudaFree(c->scr_a); cudaFree(c->scr_b); cudaFree(c->scr_buf);
+    c->scr_a = c->scr_b = nullptr; c->scr_buf = nullptr; c->scr_cap = 0;
+    const i64 cap = slots + slots / 8 + 1024;
+    CUDA_TRY(cudaMalloc(&c->scr_a, sizeof(int) * cap));
+    CUDA_TRY(cudaMalloc(&c->scr_b, sizeof(int) * cap));
+    CUDA_TRY(cudaMalloc(&c->scr_buf, sizeof(double) * cap));
+    c->scr_cap = cap;
+    return 0;
+}
+
+void lpic_free_peers(lpic_ctx *) {}

@@ -1,0 +1,244 @@
+// Yee FDTD half-steps, guard-cell copy, guard->interior current reduce, J/rho reset.
+//
+// Reference behaviour restated (not copied): core/maxwell/cpu.py:9-35,83-112 (numba, no FMA contraction),
+// core/patch/sync_fields3d.c:84-620, sync_fields2d.c:43-255, core/current/cpu3d.c:185-240.
+// These kernels are bit-exact against the reference: every fp64 operation is an explicit round-to-nearest
+// intrinsic in the reference's association order, so nvcc cannot contract a*b+c into an FMA.
+//
+// HBM roofline note: all four kernels are pure streaming; one thread owns one (patch, cell).
+// Threads run along z (the contiguous axis) so a warp reads 128-256 B runs; neighbours in y/x come from L1/L2.
+#include "lpic_common.cuh"
+
+namespace {
+
+struct CellIdx {
+    int p, i, j, k;
+};
+
+__device__ __forceinline__ bool interior_cell(const Geom &g, i64 t, CellIdx &c) {
+    const int per = g.nx * g.ny * g.nz;
+    if (t >= (i64)per * g.npatch) return false;
+    c.p = (int)(t / per);
+    int r = (int)(t - (i64)c.p * per);
+    c.k = r % g.nz;
+    r /= g.nz;
+    c.j = r % g.ny;
+    c.i = r / g.ny;
+    return true;
+}
+
+__device__ __forceinline__ int sidx(const Geom &g, int i, int j, int k) {
+    return wrapneg(k, g.NZ) + g.NZ * (wrapneg(j, g.NY) + g.NY * wrapneg(i, g.NX));
+}
+
+// E += (dt c^2) curl B - (dt/eps0) J on interior cells; backward differences reach index -1 (low guard).
+template <int DIM>
+__global__ void __launch_bounds__(256) k_update_efield(Geom g, double *__restrict__ F, double bfactor, double jfactor) {
+    CellIdx c;
+    if (!interior_cell(g, (i64)blockIdx.x * blockDim.x + threadIdx.x, c)) return;
+    const size_t stride = (size_t)g.npatch * g.ncell;
+    double *base = F + (size_t)c.p * g.ncell;
+    double *ex = base + LPIC_EX * stride, *ey = base + LPIC_EY * stride, *ez = base + LPIC_EZ * stride;
+    const double *bx = base + LPIC_BX * stride, *by = base + LPIC_BY * stride, *bz = base + LPIC_BZ * stride;
+    const double *jx = base + LPIC_JX * stride, *jy = base + LPIC_JY * stride, *jz = base + LPIC_JZ * stride;
+    const int o = sidx(g, c.i, c.j, c.k), xm = sidx(g, c.i - 1, c.j, c.k), ym = sidx(g, c.i, c.j - 1, c.k);
+    const double bxc = bx[o], byc = by[o], bzc = bz[o];
+    if (DIM == 3) {
+        const int zm = sidx(g, c.i, c.j, c.k - 1);
+        // ex += bfactor*((bz[c]-bz[ym])/dy - (by[c]-by[zm])/dz) - jfactor*jx[c]       (cpu.py:92-97)
+        double cx = __dsub_rn(__ddiv_rn(__dsub_rn(bzc, bz[ym]), g.dy), __ddiv_rn(__dsub_rn(byc, by[zm]), g.dz));
+        double cy = __dsub_rn(__ddiv_rn(__dsub_rn(bxc, bx[zm]), g.dz), __ddiv_rn(__dsub_rn(bzc, bz[xm]), g.dx));
+        double cz = __dsub_rn(__ddiv_rn(__dsub_rn(byc, by[xm]), g.dx), __ddiv_rn(__dsub_rn(bxc, bx[ym]), g.dy));
+        ex[o] = __dadd_rn(ex[o], __dsub_rn(__dmul_rn(bfactor, cx), __dmul_rn(jfactor, jx[o])));
+        ey[o] = __dadd_rn(ey[o], __dsub_rn(__dmul_rn(bfactor, cy), __dmul_rn(jfactor, jy[o])));
+        ez[o] = __dadd_rn(ez[o], __dsub_rn(__dmul_rn(bfactor, cz), __dmul_rn(jfactor, jz[o])));
+    } else {
+        // 2D (cpu.py:22-24): ex += bfactor*((bz-bz[ym])/dy) ; ey += bfactor*(-(bz-bz[xm])/dx) ; ez as 3D
+        double cx = __ddiv_rn(__dsub_rn(bzc, bz[ym]), g.dy);
+        double cy = __ddiv_rn(-__dsub_rn(bzc, bz[xm]), g.dx);
+        double cz = __dsub_rn(__ddiv_rn(__dsub_rn(byc, by[xm]), g.dx), __ddiv_rn(__dsub_rn(bxc, bx[ym]), g.dy));
+        ex[o] = __dadd_rn(ex[o], __dsub_rn(__dmul_rn(bfactor, cx), __dmul_rn(jfactor, jx[o])));
+        ey[o] = __dadd_rn(ey[o], __dsub_rn(__dmul_rn(bfactor, cy), __dmul_rn(jfactor, jy[o])));
+        ez[o] = __dadd_rn(ez[o], __dsub_rn(__dmul_rn(bfactor, cz), __dmul_rn(jfactor, jz[o])));
+    }
+}
+
+// B -= dt curl E on interior cells; forward differences reach index n (high guard).
+template <int DIM>
+__global__ void __launch_bounds__(256) k_update_bfield(Geom g, double *__restrict__ F, double dt) {
+    CellIdx c;
+    if (!interior_cell(g, (i64)blockIdx.x * blockDim.x + threadIdx.x, c)) return;
+    const size_t stride = (size_t)g.npatch * g.ncell;
+    double *base = F + (size_t)c.p * g.ncell;
+    const double *ex = base + LPIC_EX * stride, *ey = base + LPIC_EY * stride, *ez = base + LPIC_EZ * stride;
+    double *bx = base + LPIC_BX * stride, *by = base + LPIC_BY * stride, *bz = base + LPIC_BZ * stride;
+    const int o = sidx(g, c.i, c.j, c.k), xp = sidx(g, c.i + 1, c.j, c.k), yp = sidx(g, c.i, c.j + 1, c.k);
+    const double exc = ex[o], eyc = ey[o], ezc = ez[o];
+    if (DIM == 3) {
+        const int zp = sidx(g, c.i, c.j, c.k + 1);
+        double cx = __dsub_rn(__ddiv_rn(__dsub_rn(ez[yp], ezc), g.dy), __ddiv_rn(__dsub_rn(ey[zp], eyc), g.dz));
+        double cy = __dsub_rn(__ddiv_rn(__dsub_rn(ex[zp], exc), g.dz), __ddiv_rn(__dsub_rn(ez[xp], ezc), g.dx));
+        double cz = __dsub_rn(__ddiv_rn(__dsub_rn(ey[xp], eyc), g.dx), __ddiv_rn(__dsub_rn(ex[yp], exc), g.dy));
+        bx[o] = __dsub_rn(bx[o], __dmul_rn(dt, cx));
+        by[o] = __dsub_rn(by[o], __dmul_rn(dt, cy));
+        bz[o] = __dsub_rn(bz[o], __dmul_rn(dt, cz));
+    } else {
+        double cx = __ddiv_rn(__dsub_rn(ez[yp], ezc), g.dy);
+        double cy = __ddiv_rn(-__dsub_rn(ez[xp], ezc), g.dx);
+        double cz = __dsub_rn(__ddiv_rn(__dsub_rn(ey[xp], eyc), g.dx), __ddiv_rn(__dsub_rn(ex[yp], exc), g.dy));
+        bx[o] = __dsub_rn(bx[o], __dmul_rn(dt, cx));
+        by[o] = __dsub_rn(by[o], __dmul_rn(dt, cy));
+        bz[o] = __dsub_rn(bz[o], __dmul_rn(dt, cz));
+    }
+}
+
+// storage index -> logical index along one axis
+__device__ __forceinline__ int logical(int s, int n, int ng) { return s < n + ng ? s : s - (n + 2 * ng); }
+
+// Guard copy: one thread per (attribute, patch, padded cell); guard cells pull from the neighbour's interior strip.
+// dst[-ng,0) <- src[n-ng,n), dst[n,n+ng) <- src[0,ng) per axis (sync_fields2d.c:191-196).  Every guard cell has
+// exactly one source, so the order of boundaries in the reference does not matter for a copy.
+struct AttrList {
+    int a[LPIC_NFIELD];
+};
+__global__ void __launch_bounds__(256) k_sync_guard(Geom g, double *__restrict__ F, const i64 *__restrict__ nbr,
+                                                    AttrList attrs) {
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (i64)g.npatch * g.ncell) return;
+    const int p = (int)(t / g.ncell);
+    int r = (int)(t - (i64)p * g.ncell);
+    const int sk = r % g.NZ;
+    r /= g.NZ;
+    const int sj = r % g.NY, si = r / g.NY;
+    const int li = logical(si, g.nx, g.ng), lj = logical(sj, g.ny, g.ng), lk = logical(sk, g.nz, g.ngz);
+    const int sx = li < 0 ? -1 : (li >= g.nx ? 1 : 0), sy = lj < 0 ? -1 : (lj >= g.ny ? 1 : 0),
+              sz = lk < 0 ? -1 : (lk >= g.nz ? 1 : 0);
+    if (sx == 0 && sy == 0 && sz == 0) return;
+    const int b = dir_lookup(g.dim, sx, sy, sz);
+    const i64 q = nbr[(i64)p * g.nb + b];
+    if (q < 0) return;
+    const int qi = li - sx * g.nx, qj = lj - sy * g.ny, qk = lk - sz * g.nz;  // interior of the neighbour
+    const int src = qk + g.NZ * (qj + g.NY * qi);
+    const int dst = sk + g.NZ * (sj + g.NY * si);
+    double *base = F + (size_t)attrs.a[blockIdx.y] * g.npatch * g.ncell;
+    base[(size_t)p * g.ncell + dst] = base[(size_t)q * g.ncell + src];
+}
+
+// Current reduce: one thread per (attribute, patch, interior cell).  The thread walks the boundaries in the
+// reference's enum order (faces, edges, vertices), adds the neighbour's guard value and zeroes it, exactly as
+// sync_currents_3d does cell by cell (sync_fields3d.c:117-128), which fixes the summation order at edge and
+// corner cells.  Each source guard cell has a single consumer, so zeroing it here is race-free.
+__global__ void __launch_bounds__(256) k_sync_currents(Geom g, double *__restrict__ F, const i64 *__restrict__ nbr) {
+    CellIdx c;
+    if (!interior_cell(g, (i64)blockIdx.x * blockDim.x + threadIdx.x, c)) return;
+    const bool lox = c.i < g.ng, hix = c.i >= g.nx - g.ng;
+    const bool loy = c.j < g.ng, hiy = c.j >= g.ny - g.ng;
+    const bool loz = g.dim == 3 && c.k < g.ng, hiz = g.dim == 3 && c.k >= g.nz - g.ng;
+    if (!(lox || hix || loy || hiy || loz || hiz)) return;
+    double *base = F + (size_t)(LPIC_JX + blockIdx.y) * g.npatch * g.ncell;
+    const int o = c.k + g.NZ * (c.j + g.NY * c.i);
+    double acc = base[(size_t)c.p * g.ncell + o];
+    bool touched = false;
+    for (int b = 0; b < g.nb; b++) {
+        const int sx = dir_component(g.dim, b, 0), sy = dir_component(g.dim, b, 1), sz = dir_component(g.dim, b, 2);
+        if ((sx < 0 && !lox) || (sx > 0 && !hix) || (sy < 0 && !loy) || (sy > 0 && !hiy) || (sz < 0 && !loz) ||
+            (sz > 0 && !hiz))
+            continue;
+        const i64 q = nbr[(i64)c.p * g.nb + b];
+        if (q < 0) continue;
+        // dst[0,ng) += src[n,n+ng) for a MIN side, dst[n-ng,n) += src[-ng,0) for a MAX side
+        const int qi = c.i - sx * g.nx, qj = c.j - sy * g.ny, qk = c.k - sz * g.nz;
+        const size_t s = (size_t)q * g.ncell + sidx(g, qi, qj, qk);
+        acc = __dadd_rn(acc, base[s]);
+        base[s] = 0.0;
+        touched = true;
+    }
+    if (touched) base[(size_t)c.p * g.ncell + o] = acc;
+}
+
+__global__ void __launch_bounds__(256) k_field_energy(Geom g, const double *__restrict__ F, double *__restrict__ out) {
+    CellIdx c;
+    double e2 = 0.0, b2 = 0.0;
+    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; interior_cell(g, t, c); t += (i64)gridDim.x * blockDim.x) {
+        const size_t stride = (size_t)g.npatch * g.ncell;
+        const double *base = F + (size_t)c.p * g.ncell + sidx(g, c.i, c.j, c.k);
+        double a;
+        a = base[LPIC_EX * stride]; e2 += a * a;
+        a = base[LPIC_EY * stride]; e2 += a * a;
+        a = base[LPIC_EZ * stride]; e2 += a * a;
+        a = base[LPIC_BX * stride]; b2 += a * a;
+        a = base[LPIC_BY * stride]; b2 += a * a;
+        a = base[LPIC_BZ * stride]; b2 += a * a;
+    }
+    for (int o = 16; o; o >>= 1) {
+        e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+        b2 += __shfl_xor_sync(0xffffffffu, b2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out, e2);
+        atomicAdd(out + 1, b2);
+    }
+}
+
+}  // namespace
+
+extern "C" int lpic_update_efield(lpic_ctx *c, double dt) {
+    const Geom &g = c->g;
+    const i64 n = (i64)g.npatch * g.nx * g.ny * g.nz;
+    // bfactor = dt*c**2, jfactor = dt/epsilon_0 (core/maxwell/cpu.py:90-91)
+    const double bfactor = dt * (LPIC_C_LIGHT * LPIC_C_LIGHT), jfactor = dt / LPIC_EPS0;
+    if (g.dim == 3)
+        k_update_efield<3><<<div_up(n, 256), 256, 0, c->stream>>>(g, c->fields, bfactor, jfactor);
+    else
+        k_update_efield<2><<<div_up(n, 256), 256, 0, c->stream>>>(g, c->fields, bfactor, jfactor);
+    KERNEL_CHECK();
+    return 0;
+}
+
+extern "C" int lpic_update_bfield(lpic_ctx *c, double dt) {
+    const Geom &g = c->g;
+    const i64 n = (i64)g.npatch * g.nx * g.ny * g.nz;
+    if (g.dim == 3)
+        k_update_bfield<3><<<div_up(n, 256), 256, 0, c->stream>>>(g, c->fields, dt);
+    else
+        k_update_bfield<2><<<div_up(n, 256), 256, 0, c->stream>>>(g, c->fields, dt);
+    KERNEL_CHECK();
+    return 0;
+}
+
+extern "C" int lpic_sync_guard_fields(lpic_ctx *c, uint32_t attr_mask) {
+    const Geom &g = c->g;
+    AttrList attrs;
+    int na = 0;
+    for (int a = 0; a < LPIC_NFIELD; a++)
+        if (attr_mask & (1u << a)) attrs.a[na++] = a;
+    if (!na) return 0;
+    dim3 grid(div_up((i64)g.npatch * g.ncell, 256), na);
+    k_sync_guard<<<grid, 256, 0, c->stream>>>(g, c->fields, c->d_nbr, attrs);
+    KERNEL_CHECK();
+    return 0;
+}
+
+extern "C" int lpic_sync_currents(lpic_ctx *c) {
+    const Geom &g = c->g;
+    dim3 grid(div_up((i64)g.npatch * g.nx * g.ny * g.nz, 256), 4);
+    k_sync_currents<<<grid, 256, 0, c->stream>>>(g, c->fields, c->d_nbr);
+    KERNEL_CHECK();
+    return 0;
+}
+
+extern "C" int lpic_reset_currents(lpic_ctx *c) {
+    const Geom &g = c->g;
+    CUDA_TRY(cudaMemsetAsync(field_ptr(c, LPIC_JX), 0, sizeof(double) * 4 * (size_t)g.npatch * g.ncell, c->stream));
+    return 0;
+}
+
+extern "C" int lpic_field_energy_sums(lpic_ctx *c, double *out2) {
+    const Geom &g = c->g;
+    CUDA_TRY(cudaMemsetAsync(c->d_tmpf, 0, 2 * sizeof(double), c->stream));
+    k_field_energy<<<148 * 4, 256, 0, c->stream>>>(g, c->fields, c->d_tmpf);
+    KERNEL_CHECK();
+    CUDA_TRY(cudaMemcpyAsync(out2, c->d_tmpf, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}

@@ -1,0 +1,146 @@
+// Shared definitions of the device library: context, geometry, index helpers.
+// Layout conventions follow the reference (core/fields.py:24-26, core/utils/cutils.h:19-26): a grid is
+// C-contiguous (NX,NY,NZ) with N = n + 2*ng and logical index i in [-ng, n+ng) stored at (i < 0 ? i + N : i).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/lpic_b200.h"
+
+typedef int64_t i64;
+typedef uint8_t u8;
+typedef uint64_t u64;
+
+#define LPIC_C_LIGHT 299792458.0           // core/utils/cutils.h:17
+#define LPIC_ONE_THIRD 0.3333333333333333  // core/utils/cutils.h:18
+#define LPIC_EPS0 8.8541878188e-12         // scipy.constants.epsilon_0 (CODATA 2022), core/maxwell/cpu.py:91
+
+struct Geom {
+    int dim, nb;         // 2|3, 8|26 boundaries
+    int nx, ny, nz, ng;  // interior cells per patch, guard width
+    int ngz;             // ng in 3D, 0 in 2D
+    int NX, NY, NZ;      // padded sizes (NZ = 1 in 2D)
+    int ncell;           // NX*NY*NZ
+    int npatch;
+    double dx, dy, dz;
+};
+
+struct SortState {
+    i64 nxb = 0, nyb = 0, nzb = 0, nbin = 0;
+    i64 *bucket_count = nullptr, *bound_min = nullptr, *bound_max = nullptr;  // (npatch, nbin) device
+    int *pidx = nullptr;                                                       // arena-sized, pre-sort bucket of every slot
+    i64 pidx_cap = 0;
+    bool valid = false;  // bound_min/max describe the current slot order (set by sort, cleared by extend/fill)
+};
+
+struct Species {
+    bool allocated = false;
+    bool with_part = false;
+    i64 total = 0;                  // physical slots in the arena
+    i64 *h_off = nullptr, *h_pcap = nullptr, *h_npart = nullptr;  // host copies (npatch)
+    i64 *d_off = nullptr, *d_npart = nullptr;                     // device copies
+    i64 max_npart = 0;
+    double *attr[LPIC_NPATTR] = {nullptr};
+    u8 *dead = nullptr;
+    SortState sort;
+    // migration bookkeeping (device): per (patch, boundary) leaver counts, per patch dead counts
+    i64 *d_out = nullptr, *d_ndead = nullptr, *d_incoming = nullptr, *d_extend = nullptr, *d_alive = nullptr;
+};
+
+struct lpic_ctx {
+    Geom g;
+    int device = 0;
+    int nspec = 0;
+    cudaStream_t stream = nullptr;
+    double *fields = nullptr;  // [LPIC_NFIELD][npatch][ncell]
+    double *d_x0 = nullptr, *d_y0 = nullptr, *d_z0 = nullptr;
+    double *h_x0 = nullptr, *h_y0 = nullptr, *h_z0 = nullptr;
+    i64 *d_nbr = nullptr, *h_nbr = nullptr;  // (npatch, nb)
+    double *d_box = nullptr;                 // (npatch, 6)
+    double glob[6] = {0, 0, 0, 0, 0, 0};
+    i64 rank = 0;
+    i64 *h_patch_index = nullptr;
+    Species *spec = nullptr;
+    // scratch shared by sort / migration of all species (arena-sized, grown on demand)
+    int *scr_a = nullptr, *scr_b = nullptr;  // int32 lists
+    double *scr_buf = nullptr;               // staging for the sort's value move
+    i64 scr_cap = 0;
+    double *d_sort_org = nullptr;            // (3, npatch) bucket origins
+    i64 *d_tmp64 = nullptr;                  // small reductions (>= 8 + npatch words)
+    double *d_tmpf = nullptr;
+    // inter-rank halo staging
+    i64 *h_nbr_rank = nullptr, *h_remote_ipatch = nullptr;
+    int nranks = 1;
+    struct PeerHalo *peers = nullptr;
+};
+
+inline double *field_ptr(const lpic_ctx *c, int attr) { return c->fields + (size_t)attr * c->g.npatch * c->g.ncell; }
+
+void lpic_set_error(const char *fmt, ...);
+#define CUDA_TRY(expr)                                                                            \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            lpic_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return -1;                                                                            \
+        }                                                                                         \
+    } while (0)
+#define KERNEL_CHECK() CUDA_TRY(cudaGetLastError())
+#define REQUIRE(cond, ...)               \
+    do {                                 \
+        if (!(cond)) {                   \
+            lpic_set_error(__VA_ARGS__); \
+            return -2;                   \
+        }                                \
+    } while (0)
+
+// boundary direction tables, enum order of core/patch/sync_fields3d.c:19-50 and sync_fields2d.c:18-28
+__constant__ const signed char kDir3[26][3] = {
+    {-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1},
+    {-1, -1, 0}, {-1, 1, 0}, {-1, 0, -1}, {-1, 0, 1}, {1, -1, 0}, {1, 1, 0}, {1, 0, -1}, {1, 0, 1},
+    {0, -1, -1}, {0, -1, 1}, {0, 1, -1}, {0, 1, 1},
+    {-1, -1, -1}, {-1, -1, 1}, {-1, 1, -1}, {-1, 1, 1}, {1, -1, -1}, {1, -1, 1}, {1, 1, -1}, {1, 1, 1}};
+__constant__ const signed char kDir2[8][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0},
+                                              {-1, -1, 0}, {1, -1, 0}, {-1, 1, 0}, {1, 1, 0}};
+// (sx+1) + 3*(sy+1) + 9*(sz+1) -> boundary id (-1 for the centre)
+__constant__ const signed char kLut3[27] = {18, 14, 22, 8, 4, 12, 20, 16, 24, 6, 2, 10, 0, -1, 1, 7, 3, 11,
+                                            19, 15, 23, 9, 5, 13, 21, 17, 25};
+__constant__ const signed char kLut2[9] = {4, 2, 5, 0, -1, 1, 6, 3, 7};
+
+static const signed char hDir3[26][3] = {
+    {-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1},
+    {-1, -1, 0}, {-1, 1, 0}, {-1, 0, -1}, {-1, 0, 1}, {1, -1, 0}, {1, 1, 0}, {1, 0, -1}, {1, 0, 1},
+    {0, -1, -1}, {0, -1, 1}, {0, 1, -1}, {0, 1, 1},
+    {-1, -1, -1}, {-1, -1, 1}, {-1, 1, -1}, {-1, 1, 1}, {1, -1, -1}, {1, -1, 1}, {1, 1, -1}, {1, 1, 1}};
+static const signed char hDir2[8][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0},
+                                        {-1, -1, 0}, {1, -1, 0}, {-1, 1, 0}, {1, 1, 0}};
+static const signed char hLut3[27] = {18, 14, 22, 8, 4, 12, 20, 16, 24, 6, 2, 10, 0, -1, 1, 7, 3, 11,
+                                      19, 15, 23, 9, 5, 13, 21, 17, 25};
+static const signed char hLut2[9] = {4, 2, 5, 0, -1, 1, 6, 3, 7};
+
+__host__ __device__ inline int dir_component(int dim, int b, int axis) {
+#ifdef __CUDA_ARCH__
+    return dim == 3 ? kDir3[b][axis] : kDir2[b][axis];
+#else
+    return dim == 3 ? hDir3[b][axis] : hDir2[b][axis];
+#endif
+}
+__host__ __device__ inline int dir_lookup(int dim, int sx, int sy, int sz) {
+#ifdef __CUDA_ARCH__
+    return dim == 3 ? kLut3[(sx + 1) + 3 * (sy + 1) + 9 * (sz + 1)] : kLut2[(sx + 1) + 3 * (sy + 1)];
+#else
+    return dim == 3 ? hLut3[(sx + 1) + 3 * (sy + 1) + 9 * (sz + 1)] : hLut2[(sx + 1) + 3 * (sy + 1)];
+#endif
+}
+__host__ __device__ inline int dir_opposite(int dim, int b) {
+    return dir_lookup(dim, -dir_component(dim, b, 0), -dir_component(dim, b, 1), -dir_component(dim, b, 2));
+}
+
+__host__ __device__ inline int wrapneg(int i, int N) { return i < 0 ? i + N : i; }
+
+// kernels' launch helpers
+static inline unsigned div_up(i64 a, i64 b) { return (unsigned)((a + b - 1) / b); }
+
+// entry points implemented per file
+int lpic_ensure_scratch(lpic_ctx *c, i64 slots);

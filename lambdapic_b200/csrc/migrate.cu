@@ -1,0 +1,284 @@
+// Intra-rank particle migration between patches, reproducing the reference's slot assignment bit-for-bit.
+//
+// Reference behaviour restated (not copied): core/patch/sync_particles_3d.c:79-193 (classification into the 26
+// directions), :365-482 (counts, growth rule), :204-323 (leaver lists and the AoS buffer order), :349-363
+// (periodic shift), :326-346 (kill + NaN), :484-695 (driver); 2D twin sync_particles_2d.c; facade patch.py:705-764.
+//   incoming stream of patch p = for b in enum order (neighbour q = nbr[p][b] >= 0):
+//                                    q's alive leavers towards opposite(b), ascending slot order
+//   k-th incoming particle -> k-th dead slot of p (ascending).
+// Device plan: (1) one CTA per patch counts leavers per direction and dead slots; (2) one thread per patch
+// derives incoming / alive / npart_to_extend; [host grows the arrays: lpic_species_extend]; (3) one CTA per
+// patch lists its leavers grouped by direction (stable) and its dead slots; (4) one thread per incoming
+// particle copies every attribute; (5) out-of-box particles are killed.
+#include <vector>
+#include "lpic_common.cuh"
+
+namespace {
+
+constexpr int T = 256;
+
+struct MigArgs {
+    int dim, nb, npatch, nattr;
+    const i64 *off, *npart, *nbr;
+    const double *box;  // (npatch, 6)
+    double *x, *y, *z;
+    u8 *dead;
+    i64 *out, *ndead, *incoming, *extend, *alive;  // per patch (out: per patch x boundary)
+    int *la, *lb;                                  // arena-sized int lists
+    int *dirstart;                                 // (npatch, nb)
+    double *attrs[LPIC_NPATTR];
+    int ia_x, ia_y, ia_z;
+    double glob[6], cell[3];
+};
+
+__device__ __forceinline__ int classify(const MigArgs &a, const double *bx, i64 ip) {
+    const double x = a.x[ip], y = a.y[ip];
+    const int sx = x < bx[0] ? -1 : (x > bx[1] ? 1 : 0);
+    const int sy = y < bx[2] ? -1 : (y > bx[3] ? 1 : 0);
+    int sz = 0;
+    if (a.dim == 3) {
+        const double z = a.z[ip];
+        sz = z < bx[4] ? -1 : (z > bx[5] ? 1 : 0);
+    }
+    return dir_lookup(a.dim, sx, sy, sz);  // -1 when inside
+}
+
+__device__ __forceinline__ int warp_incl_sum(int v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int n = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += n;
+    }
+    return v;
+}
+__device__ __forceinline__ int block_incl_sum(int v, int *sw, int &total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_incl_sum(v);
+    __syncthreads();
+    if (lane == 31) sw[w] = v;
+    __syncthreads();
+    int add = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < T / 32; i++) {
+        if (i < w) add += sw[i];
+        tot += sw[i];
+    }
+    total = tot;
+    return v + add;
+}
+
+__global__ void __launch_bounds__(T) k_count(MigArgs a) {
+    __shared__ int s_out[32];
+    __shared__ int s_dead;
+    const int p = blockIdx.x, tid = threadIdx.x;
+    if (tid < 32) s_out[tid] = 0;
+    if (tid == 0) s_dead = 0;
+    __syncthreads();
+    const i64 off = a.off[p];
+    const int np = (int)a.npart[p];
+    const double *bx = a.box + 6 * (size_t)p;
+    int mydead = 0;
+    for (int ip = tid; ip < np; ip += T) {
+        if (a.dead[off + ip]) { mydead++; continue; }
+        const int b = classify(a, bx, off + ip);
+        if (b >= 0) atomicAdd(&s_out[b], 1);
+    }
+    mydead = __reduce_add_sync(0xffffffffu, mydead);
+    if ((tid & 31) == 0 && mydead) atomicAdd(&s_dead, mydead);
+    __syncthreads();
+    if (tid < a.nb) a.out[(size_t)p * a.nb + tid] = s_out[tid];
+    if (tid == 0) a.ndead[p] = s_dead;
+}
+
+__global__ void k_plan(MigArgs a) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.npatch) return;
+    i64 incoming = 0;
+    for (int b = 0; b < a.nb; b++) {
+        const i64 q = a.nbr[(size_t)p * a.nb + b];
+        if (q >= 0) incoming += a.out[(size_t)q * a.nb + dir_opposite(a.dim, b)];
+    }
+    const i64 npart = a.npart[p], ndead = a.ndead[p];
+    a.incoming[p] = incoming;
+    a.alive[p] = npart - ndead + incoming;
+    // grow only when the dead slots cannot take the newcomers; a quarter of the capacity is added on top
+    a.extend[p] = incoming - ndead > 0 ? incoming - ndead + (i64)((double)npart * 0.25) : 0;
+}
+
+// leavers grouped by direction (stable, ascending slots) into lb[off ..]; dead slots ascending into la from the back
+__global__ void __launch_bounds__(T) k_lists(MigArgs a) {
+    __shared__ int sw[T / 32];
+    __shared__ int s_cur[32];
+    const int p = blockIdx.x, tid = threadIdx.x;
+    const i64 off = a.off[p];
+    const int np = (int)a.npart[p];
+    const double *bx = a.box + 6 * (size_t)p;
+    if (tid == 0) {
+        int run = 0;
+        for (int b = 0; b < a.nb; b++) {
+            s_cur[b] = run;
+            a.dirstart[(size_t)p * a.nb + b] = run;
+            run += (int)a.out[(size_t)p * a.nb + b];
+        }
+    }
+    __syncthreads();
+    int nl = 0, nd = 0;
+    for (int base = 0; base < np; base += T) {
+        const int ip = base + tid;
+        bool isdead = false, leaves = false;
+        if (ip < np) {
+            isdead = a.dead[off + ip] != 0;
+            if (!isdead) leaves = classify(a, bx, off + ip) >= 0;
+        }
+        int tot;
+        int incl = block_incl_sum(leaves ? 1 : 0, sw, tot);
+        if (leaves) a.la[off + nl + incl - 1] = ip;
+        nl += tot;
+        __syncthreads();
+        incl = block_incl_sum(isdead ? 1 : 0, sw, tot);
+        if (isdead) a.la[off + np - 1 - (nd + incl - 1)] = ip;
+        nd += tot;
+        __syncthreads();
+    }
+    if (tid == 0) a.ndead[p] = nd;  // dead slots after the host grew the arrays
+    // stable grouping by direction: warps take turns, lanes of one direction get consecutive places
+    for (int base = 0; base < nl; base += T) {
+        const int i = base + tid;
+        const bool act = i < nl;
+        int slot = 0, b = -2 - (tid & 31);
+        if (act) {
+            slot = a.la[off + i];
+            b = classify(a, bx, off + slot);
+        }
+        for (int w = 0; w < T / 32; w++) {
+            if ((tid >> 5) == w) {
+                const unsigned lane = tid & 31;
+                const unsigned peers = __match_any_sync(0xffffffffu, b);
+                const int leader = __ffs(peers) - 1;
+                int start = 0;
+                if (act && (int)lane == leader) { start = s_cur[b]; s_cur[b] = start + __popc(peers); }
+                start = __shfl_sync(0xffffffffu, start, leader);
+                if (act) a.lb[off + start + __popc(peers & ((1u << lane) - 1u))] = slot;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// one thread per incoming particle of patch p
+__global__ void __launch_bounds__(T) k_fill(MigArgs a, int blocks_per_patch) {
+    const int p = blockIdx.x / blocks_per_patch;
+    const i64 k = (i64)(blockIdx.x - p * blocks_per_patch) * blockDim.x + threadIdx.x;
+    if (k >= a.incoming[p] || k >= a.ndead[p]) return;
+    // which boundary does the k-th newcomer arrive through?  (fill_boundary_particles_to_buffer, :302-323)
+    i64 run = 0;
+    i64 q = -1;
+    int ob = 0;
+    i64 r = 0;
+    for (int b = 0; b < a.nb; b++) {
+        const i64 qq = a.nbr[(size_t)p * a.nb + b];
+        if (qq < 0) continue;
+        const int o = dir_opposite(a.dim, b);
+        const i64 cnt = a.out[(size_t)qq * a.nb + o];
+        if (k < run + cnt) { q = qq; ob = o; r = k - run; break; }
+        run += cnt;
+    }
+    if (q < 0) return;
+    const i64 src = a.off[q] + a.lb[a.off[q] + a.dirstart[(size_t)q * a.nb + ob] + r];
+    const i64 np = a.npart[p];
+    const i64 dst = a.off[p] + a.la[a.off[p] + np - 1 - k];
+    const double *bx = a.box + 6 * (size_t)p;
+    for (int t = 0; t < a.nattr; t++) {
+        double v = a.attrs[t][src];
+        const int d = t == a.ia_x ? 0 : (t == a.ia_y ? 1 : (t == a.ia_z ? 2 : -1));
+        if (d >= 0) {  // handle_periodic, :349-363
+            const double lo = a.glob[2 * d], hi = a.glob[2 * d + 1], L = hi - lo, c0 = v;
+            if (c0 > hi && fabs(bx[2 * d] - lo) < a.cell[d]) v -= L;
+            if (c0 < lo && fabs(bx[2 * d + 1] - hi) < a.cell[d]) v += L;
+        }
+        a.attrs[t][dst] = v;
+    }
+    a.dead[dst] = 0;
+}
+
+// mark_out_of_bound_as_dead (:326-346): alive outside the box -> dead with NaN position; in 3D every dead slot's
+// position is NaN'd, in 2D only the freshly killed ones (sync_particles_2d.c:185-202).
+__global__ void __launch_bounds__(T) k_mark(MigArgs a, int blocks_per_patch) {
+    const int p = blockIdx.x / blocks_per_patch;
+    const i64 t = (i64)(blockIdx.x - p * blocks_per_patch) * blockDim.x + threadIdx.x;
+    if (t >= a.npart[p]) return;
+    const i64 ip = a.off[p] + t;
+    bool out = false;
+    if (a.dead[ip]) {
+        if (a.dim != 3) return;
+        out = true;
+    } else if (classify(a, a.box + 6 * (size_t)p, ip) >= 0) {
+        out = true;
+        a.dead[ip] = 1;
+    }
+    if (out) {
+        const double nan = __longlong_as_double(0x7ff8000000000000ll);
+        a.x[ip] = nan;
+        a.y[ip] = nan;
+        if (a.dim == 3) a.z[ip] = nan;
+    }
+}
+
+int make_args(lpic_ctx *c, int ispec, MigArgs &a) {
+    REQUIRE(ispec >= 0 && ispec < c->nspec && c->spec[ispec].allocated, "species %d not allocated", ispec);
+    Species &sp = c->spec[ispec];
+    const Geom &g = c->g;
+    if (int r = lpic_ensure_scratch(c, sp.total)) return r;
+    a.dim = g.dim; a.nb = g.nb; a.npatch = g.npatch;
+    a.off = sp.d_off; a.npart = sp.d_npart; a.nbr = c->d_nbr; a.box = c->d_box;
+    a.x = sp.attr[LPIC_P_X]; a.y = sp.attr[LPIC_P_Y]; a.z = sp.attr[LPIC_P_Z]; a.dead = sp.dead;
+    a.out = sp.d_out; a.ndead = sp.d_ndead; a.incoming = sp.d_incoming; a.extend = sp.d_extend; a.alive = sp.d_alive;
+    a.la = c->scr_a; a.lb = c->scr_b;
+    a.dirstart = (int *)(c->d_tmp64 + 64);  // npatch*nb ints <= 4*npatch i64 words (26 ints = 13 words): checked below
+    a.nattr = 0; a.ia_x = a.ia_y = a.ia_z = -1;
+    for (int t = 0; t < LPIC_NPATTR; t++) {
+        if (!sp.attr[t]) continue;
+        if (t == LPIC_P_X) a.ia_x = a.nattr;
+        if (t == LPIC_P_Y) a.ia_y = a.nattr;
+        if (t == LPIC_P_Z && g.dim == 3) a.ia_z = a.nattr;
+        a.attrs[a.nattr++] = sp.attr[t];
+    }
+    for (int i = 0; i < 6; i++) a.glob[i] = c->glob[i];
+    a.cell[0] = g.dx; a.cell[1] = g.dy; a.cell[2] = g.dz;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int lpic_migrate_count(lpic_ctx *c, int ispec, int64_t *to_extend, int64_t *incoming, int64_t *outgoing,
+                                  int64_t *alive) {
+    MigArgs a;
+    if (int r = make_args(c, ispec, a)) return r;
+    Species &sp = c->spec[ispec];
+    const i64 n = c->g.npatch;
+    k_count<<<(unsigned)n, T, 0, c->stream>>>(a);
+    k_plan<<<div_up(n, 128), 128, 0, c->stream>>>(a);
+    KERNEL_CHECK();
+    if (to_extend) CUDA_TRY(cudaMemcpyAsync(to_extend, sp.d_extend, sizeof(i64) * n, cudaMemcpyDeviceToHost, c->stream));
+    if (incoming) CUDA_TRY(cudaMemcpyAsync(incoming, sp.d_incoming, sizeof(i64) * n, cudaMemcpyDeviceToHost, c->stream));
+    if (outgoing) CUDA_TRY(cudaMemcpyAsync(outgoing, sp.d_out, sizeof(i64) * n * c->g.nb, cudaMemcpyDeviceToHost, c->stream));
+    if (alive) CUDA_TRY(cudaMemcpyAsync(alive, sp.d_alive, sizeof(i64) * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int lpic_migrate_fill(lpic_ctx *c, int ispec) {
+    MigArgs a;
+    if (int r = make_args(c, ispec, a)) return r;
+    Species &sp = c->spec[ispec];
+    const i64 n = c->g.npatch;
+    if (sp.max_npart == 0) return 0;
+    k_lists<<<(unsigned)n, T, 0, c->stream>>>(a);
+    const int bpp = (int)div_up(sp.max_npart, T);
+    k_fill<<<(unsigned)((i64)bpp * n), T, 0, c->stream>>>(a, bpp);
+    k_mark<<<(unsigned)((i64)bpp * n), T, 0, c->stream>>>(a, bpp);
+    KERNEL_CHECK();
+    sp.sort.valid = false;
+    return 0;
+}

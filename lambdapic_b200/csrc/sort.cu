@@ -1,0 +1,352 @@
+// Per-patch in-place bucket sort of the particle SoA, reproducing the reference's slot permutation bit-for-bit.
+//
+// Reference behaviour restated (not copied): core/sort/cpu3d.c:8-156 (calculate_cell_index, calculate_bucket_bound,
+// bucket_sort_3d), driver :214-299, 2D twin core/sort/cpu2d.c; facade core/sort/particle_sort.py.
+//   1. key[ip]  = bucket of slot ip; dead slots inherit the key of the previous slot (a running value that starts
+//                 at 0 for every patch); alive out-of-range particles go to the last bucket.
+//   2. count / exclusive prefix -> bucket_bound_min/max; owner[ip] = bucket whose range contains slot ip.
+//   3. the misplaced slots (key != owner), listed ascending, are permuted among themselves: the values are laid
+//      out stably by key, then written back in list order.  Equivalent closed form used here:
+//         new[T_i] = old[T_j]  with  dest(j) = start[key_j] + #{j' < j : key_j' = key_j} = i.
+// One CTA owns one patch (all scans are block scans with a running carry), then two grid-wide kernels per
+// attribute move the values through a staging buffer.  Integer results are identical to the reference by construction.
+#include <limits.h>
+#include <algorithm>
+#include <vector>
+#include "lpic_common.cuh"
+
+namespace {
+
+constexpr int T = 256;         // threads per sort CTA
+constexpr int SMEM_BINS = 2048;  // histograms up to this many buckets live in shared memory
+
+__device__ __forceinline__ int warp_incl_sum(int v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int n = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += n;
+    }
+    return v;
+}
+__device__ __forceinline__ int warp_incl_max(int v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int n = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v = max(v, n);
+    }
+    return v;
+}
+// inclusive block scans over T threads; `total` receives the block aggregate. sw: int[T/32] scratch.
+__device__ __forceinline__ int block_incl_sum(int v, int *sw, int &total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_incl_sum(v);
+    __syncthreads();
+    if (lane == 31) sw[w] = v;
+    __syncthreads();
+    int add = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < T / 32; i++) {
+        if (i < w) add += sw[i];
+        tot += sw[i];
+    }
+    total = tot;
+    return v + add;
+}
+__device__ __forceinline__ int block_incl_max(int v, int *sw) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_incl_max(v);
+    __syncthreads();
+    if (lane == 31) sw[w] = v;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < T / 32; i++)
+        if (i < w) v = max(v, sw[i]);
+    return v;
+}
+
+// warp-aggregated counter increment: lanes with equal key elect a leader that adds the group size.
+// Returns the value of the counter before this warp's group was added plus the lane's rank inside the group.
+__device__ __forceinline__ int grouped_fetch_add(int *ctr, int key, bool active) {
+    const unsigned lane = threadIdx.x & 31;
+    const int k = active ? key : -2 - (int)lane;
+    const unsigned peers = __match_any_sync(0xffffffffu, k);
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (active && (int)lane == leader) base = atomicAdd(ctr + key, __popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + __popc(peers & ((1u << lane) - 1u));
+}
+
+struct SortArgs {
+    const double *x, *y, *z;
+    const u8 *dead;
+    const i64 *off, *npart;
+    const double *org;  // (3, npatch) bucket origins
+    int npatch, nxb, nyb, nzb, nbin, reverse_x, dim;
+    double dxb, dyb, dzb;
+    int *pidx;                              // arena
+    i64 *bucket_count, *bound_min, *bound_max;  // (npatch, nbin)
+    int *g_hist, *g_cur;                    // (npatch, nbin) global fallbacks when nbin > SMEM_BINS
+    int *tgt, *src_of;                      // arena-sized lists (local slot numbers)
+    i64 *nbuf;                              // (npatch)
+};
+
+__device__ __forceinline__ long long cell_of(double v) {
+    const double f = floor(v);
+    // C's (npy_intp)floor(NaN/inf) yields INT64_MIN on x86-64; keep such particles out of range
+    if (!(f >= -9.0e18 && f <= 9.0e18)) return LLONG_MIN / 2;
+    return (long long)f;
+}
+
+__global__ void __launch_bounds__(T) k_sort_index(SortArgs a) {
+    __shared__ int skey[T];
+    __shared__ int sw[T / 32];
+    __shared__ int s_hist[SMEM_BINS];
+    __shared__ int s_carry;
+    const int p = blockIdx.x, tid = threadIdx.x;
+    const i64 off = a.off[p];
+    const int np = (int)a.npart[p];
+    const int nbin = a.nbin;
+    const bool use_smem = nbin <= SMEM_BINS;
+    int *hist = use_smem ? s_hist : a.g_hist + (size_t)p * nbin;
+    int *cur = use_smem ? s_hist : a.g_cur + (size_t)p * nbin;
+    if (use_smem)
+        for (int b = tid; b < nbin; b += T) s_hist[b] = 0;
+    if (tid == 0) s_carry = 0;  // icell = 0 at the start of every patch (cpu3d.c:19)
+    __syncthreads();
+    const double x0 = a.org[p], y0 = a.org[a.npatch + p], z0 = a.org[2 * a.npatch + p];
+
+    // ---- 1. keys with inheritance, histogram ------------------------------------------------------------
+    for (int base = 0; base < np; base += T) {
+        const int ip = base + tid;
+        bool valid = false;
+        int key = 0;
+        if (ip < np && !a.dead[off + ip]) {
+            valid = true;
+            long long ix = cell_of((a.x[off + ip] - x0) / a.dxb);
+            long long iy = cell_of((a.y[off + ip] - y0) / a.dyb);
+            long long iz = a.dim == 3 ? cell_of((a.z[off + ip] - z0) / a.dzb) : 0;
+            if (a.reverse_x) {
+                ix = ix < 0 ? 0 : (ix >= a.nxb ? a.nxb - 1 : ix);
+                iy = iy < 0 ? 0 : (iy >= a.nyb ? a.nyb - 1 : iy);
+                iz = iz < 0 ? 0 : (iz >= a.nzb ? a.nzb - 1 : iz);
+                key = (int)(iz + iy * a.nzb + (a.nxb - 1 - ix) * a.nyb * a.nzb);
+            } else if (ix >= 0 && ix < a.nxb && iy >= 0 && iy < a.nyb && iz >= 0 && iz < a.nzb) {
+                key = (int)(iz + iy * a.nzb + ix * a.nyb * a.nzb);
+            } else {
+                key = nbin - 1;
+            }
+        }
+        skey[tid] = key;
+        const int carry = s_carry;
+        const int last = block_incl_max(valid ? tid : -1, sw);  // syncs inside make skey visible
+        key = last >= 0 ? skey[last] : carry;
+        if (ip < np) a.pidx[off + ip] = key;
+        grouped_fetch_add(hist, key, ip < np);
+        __syncthreads();
+        if (tid == T - 1) s_carry = key;
+        __syncthreads();
+    }
+
+    // ---- 2. bucket bounds (exclusive prefix of the counts) ----------------------------------------------
+    {
+        int run = 0;
+        for (int base = 0; base < nbin; base += T) {
+            const int b = base + tid;
+            const int cnt = b < nbin ? hist[b] : 0;
+            int tot;
+            const int incl = block_incl_sum(cnt, sw, tot);
+            if (b < nbin) {
+                a.bucket_count[(size_t)p * nbin + b] = cnt;
+                a.bound_min[(size_t)p * nbin + b] = run + incl - cnt;
+                a.bound_max[(size_t)p * nbin + b] = run + incl;
+            }
+            run += tot;
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    if (use_smem) {
+        for (int b = tid; b < nbin; b += T) s_hist[b] = 0;
+    } else {
+        for (int b = tid; b < nbin; b += T) cur[b] = 0;
+    }
+    __threadfence_block();
+    __syncthreads();
+
+    // ---- 3. misplaced slots, ascending; per-bucket counts of them ------------------------------------------
+    const i64 *bmax = a.bound_max + (size_t)p * nbin;
+    int nbuf = 0;
+    for (int base = 0; base < np; base += T) {
+        const int ip = base + tid;
+        bool miss = false;
+        int key = 0;
+        if (ip < np) {
+            key = a.pidx[off + ip];
+            int lo = 0, hi = nbin - 1;  // owner = first bucket with bound_max > ip
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (bmax[mid] > ip) hi = mid; else lo = mid + 1;
+            }
+            miss = key != lo;
+        }
+        int tot;
+        const int incl = block_incl_sum(miss ? 1 : 0, sw, tot);
+        if (miss) a.tgt[off + nbuf + incl - 1] = ip;
+        grouped_fetch_add(cur, key, miss);  // counts by key == counts by owner (see header comment)
+        nbuf += tot;
+        __syncthreads();
+    }
+    if (tid == 0) a.nbuf[p] = nbuf;
+    if (nbuf == 0) return;
+    __syncthreads();
+
+    // ---- 4. start[b] = exclusive prefix of the misplaced counts (in place) -----------------------------------
+    {
+        int run = 0;
+        for (int base = 0; base < nbin; base += T) {
+            const int b = base + tid;
+            const int cnt = b < nbin ? cur[b] : 0;
+            int tot;
+            const int incl = block_incl_sum(cnt, sw, tot);
+            __syncthreads();
+            if (b < nbin) cur[b] = run + incl - cnt;
+            run += tot;
+            __syncthreads();
+        }
+    }
+    __threadfence_block();
+    __syncthreads();
+
+    // ---- 5. stable placement: warps take turns so that counters advance in list order ------------------------
+    for (int base = 0; base < nbuf; base += T) {
+        const int i = base + tid;
+        const bool act = i < nbuf;
+        int slot = 0, key = 0;
+        if (act) {
+            slot = a.tgt[off + i];
+            key = a.pidx[off + slot];
+        }
+        for (int w = 0; w < T / 32; w++) {
+            if ((tid >> 5) == w) {
+                const int dest = grouped_fetch_add(cur, key, act);
+                if (act) a.src_of[off + dest] = slot;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <typename V>
+__global__ void __launch_bounds__(256) k_sort_gather(const V *__restrict__ attr, V *__restrict__ buf, const int *__restrict__ src_of,
+                                                     const i64 *__restrict__ off, const i64 *__restrict__ nbuf, int blocks_per_patch) {
+    const int p = blockIdx.x / blocks_per_patch;
+    const i64 i = (i64)(blockIdx.x - p * blocks_per_patch) * blockDim.x + threadIdx.x;
+    if (i >= nbuf[p]) return;
+    buf[off[p] + i] = attr[off[p] + src_of[off[p] + i]];
+}
+template <typename V>
+__global__ void __launch_bounds__(256) k_sort_scatter(V *__restrict__ attr, const V *__restrict__ buf, const int *__restrict__ tgt,
+                                                      const i64 *__restrict__ off, const i64 *__restrict__ nbuf, int blocks_per_patch) {
+    const int p = blockIdx.x / blocks_per_patch;
+    const i64 i = (i64)(blockIdx.x - p * blocks_per_patch) * blockDim.x + threadIdx.x;
+    if (i >= nbuf[p]) return;
+    attr[off[p] + tgt[off[p] + i]] = buf[off[p] + i];
+}
+
+__global__ void k_widen(const int *__restrict__ src, i64 *__restrict__ dst, i64 n) {
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) dst[t] = src[t];
+}
+
+}  // namespace
+
+extern "C" int lpic_sort(lpic_ctx *c, int ispec, int reverse_x, int64_t nxb, int64_t nyb, int64_t nzb, double dxb,
+                         double dyb, double dzb, const double *x0s, const double *y0s, const double *z0s,
+                         int64_t *nbuf_total) {
+    REQUIRE(ispec >= 0 && ispec < c->nspec && c->spec[ispec].allocated, "species %d not allocated", ispec);
+    Species &sp = c->spec[ispec];
+    const Geom &g = c->g;
+    const i64 n = g.npatch;
+    if (g.dim == 2) { nzb = 1; dzb = 1.0; }
+    const i64 nbin = nxb * nyb * nzb;
+    REQUIRE(nbin > 0 && nbin < (1ll << 30), "bad bucket grid");
+    REQUIRE(sp.max_npart < (1ll << 31), "patch too large for 32-bit slot numbers");
+    SortState &st = sp.sort;
+    if (st.nbin != nbin) {
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        cudaFree(st.bucket_count); cudaFree(st.bound_min); cudaFree(st.bound_max);
+        CUDA_TRY(cudaMalloc(&st.bucket_count, sizeof(i64) * n * nbin));
+        CUDA_TRY(cudaMalloc(&st.bound_min, sizeof(i64) * n * nbin));
+        CUDA_TRY(cudaMalloc(&st.bound_max, sizeof(i64) * n * nbin));
+        st.nbin = nbin;
+    }
+    st.nxb = nxb; st.nyb = nyb; st.nzb = nzb;
+    if (int r = lpic_ensure_scratch(c, sp.total)) return r;
+    // bucket origins
+    std::vector<double> org(3 * n, 0.0);
+    for (i64 p = 0; p < n; p++) { org[p] = x0s[p]; org[n + p] = y0s[p]; org[2 * n + p] = (g.dim == 3 && z0s) ? z0s[p] : 0.0; }
+    CUDA_TRY(cudaMemcpyAsync(c->d_sort_org, org.data(), sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    int *g_hist = nullptr, *g_cur = nullptr;
+    if (nbin > SMEM_BINS) {
+        CUDA_TRY(cudaMalloc(&g_hist, sizeof(int) * n * nbin * 2));
+        g_cur = g_hist + n * nbin;
+        CUDA_TRY(cudaMemsetAsync(g_hist, 0, sizeof(int) * n * nbin * 2, c->stream));
+    }
+    i64 *d_nbuf = c->d_tmp64 + 64;
+    SortArgs a;
+    a.x = sp.attr[LPIC_P_X]; a.y = sp.attr[LPIC_P_Y]; a.z = sp.attr[LPIC_P_Z]; a.dead = sp.dead;
+    a.off = sp.d_off; a.npart = sp.d_npart; a.org = c->d_sort_org;
+    a.npatch = (int)n; a.nxb = (int)nxb; a.nyb = (int)nyb; a.nzb = (int)nzb; a.nbin = (int)nbin;
+    a.reverse_x = reverse_x; a.dim = g.dim; a.dxb = dxb; a.dyb = dyb; a.dzb = dzb;
+    a.pidx = st.pidx; a.bucket_count = st.bucket_count; a.bound_min = st.bound_min; a.bound_max = st.bound_max;
+    a.g_hist = g_hist; a.g_cur = g_cur; a.tgt = c->scr_a; a.src_of = c->scr_b; a.nbuf = d_nbuf;
+    k_sort_index<<<(unsigned)n, T, 0, c->stream>>>(a);
+    KERNEL_CHECK();
+    std::vector<i64> h_nbuf(n);
+    CUDA_TRY(cudaMemcpyAsync(h_nbuf.data(), d_nbuf, sizeof(i64) * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (g_hist) cudaFree(g_hist);
+    i64 total = 0, mx = 0;
+    for (i64 p = 0; p < n; p++) { total += h_nbuf[p]; mx = std::max(mx, h_nbuf[p]); }
+    if (nbuf_total) *nbuf_total = total;
+    if (total > 0) {
+        const int bpp = (int)div_up(mx, 256);
+        const unsigned grid = (unsigned)((i64)bpp * n);
+        for (int at = 0; at < LPIC_NPATTR; at++) {
+            if (!sp.attr[at]) continue;
+            k_sort_gather<double><<<grid, 256, 0, c->stream>>>(sp.attr[at], c->scr_buf, c->scr_b, sp.d_off, d_nbuf, bpp);
+            k_sort_scatter<double><<<grid, 256, 0, c->stream>>>(sp.attr[at], c->scr_buf, c->scr_a, sp.d_off, d_nbuf, bpp);
+        }
+        k_sort_gather<u8><<<grid, 256, 0, c->stream>>>(sp.dead, (u8 *)c->scr_buf, c->scr_b, sp.d_off, d_nbuf, bpp);
+        k_sort_scatter<u8><<<grid, 256, 0, c->stream>>>(sp.dead, (const u8 *)c->scr_buf, c->scr_a, sp.d_off, d_nbuf, bpp);
+        KERNEL_CHECK();
+    }
+    st.valid = true;
+    return 0;
+}
+
+extern "C" int lpic_sort_download(lpic_ctx *c, int ispec, int which, int64_t *out) {
+    REQUIRE(ispec >= 0 && ispec < c->nspec && c->spec[ispec].allocated, "species %d not allocated", ispec);
+    Species &sp = c->spec[ispec];
+    SortState &st = sp.sort;
+    const i64 n = c->g.npatch;
+    if (which == LPIC_SORT_PARTICLE_INDEX) {
+        i64 *tmp = nullptr;
+        CUDA_TRY(cudaMalloc(&tmp, sizeof(i64) * std::max<i64>(sp.total, 1)));
+        k_widen<<<div_up(std::max<i64>(sp.total, 1), 256), 256, 0, c->stream>>>(st.pidx, tmp, sp.total);
+        CUDA_TRY(cudaMemcpyAsync(out, tmp, sizeof(i64) * sp.total, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        cudaFree(tmp);
+        return 0;
+    }
+    REQUIRE(st.nbin > 0, "sorter of species %d has not run yet", ispec);
+    const i64 *src = which == LPIC_SORT_BUCKET_COUNT ? st.bucket_count : which == LPIC_SORT_BOUND_MIN ? st.bound_min
+                     : which == LPIC_SORT_BOUND_MAX ? st.bound_max : nullptr;
+    REQUIRE(src != nullptr, "bad sorter array id %d", which);
+    CUDA_TRY(cudaMemcpyAsync(out, src, sizeof(i64) * n * st.nbin, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}

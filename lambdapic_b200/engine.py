@@ -1,0 +1,323 @@
+"""DeviceEngine: owns one lpic_ctx (one GPU) plus the pinned host mirrors of its fields and particles.
+
+The host mirrors have exactly the device layout (include/lpic_b200.h), so an upload/download of one attribute
+of every patch is a single copy.  The numpy arrays handed to user code (``p.fields.ex``,
+``p.particles[i].x`` ...) are views into these mirrors.  The device is authoritative between
+:meth:`upload_all` and :meth:`download_all`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import FIELD_ATTRS, PART_ATTRS, P_IS_DEAD, check
+
+ALL_FIELDS = (1 << len(FIELD_ATTRS)) - 1
+E_MASK, B_MASK, J_MASK = 0b111, 0b111000, 0b1111000000
+RESIDENT_ATTRS = ["x", "y", "z", "w", "ux", "uy", "uz", "inv_gamma", "_id"]
+PART_FIELD_ATTRS = PART_ATTRS[8:14]
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else None
+
+
+class HostBuffer:
+    """numpy view over memory from lpic_host_alloc (pinned when a GPU is present)."""
+
+    def __init__(self, nbytes: int):
+        self.nbytes = max(int(nbytes), 8)
+        self.ptr = _lib.lib().lpic_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise MemoryError(f"lpic_host_alloc({self.nbytes}) failed")
+        self._raw = (C.c_char * self.nbytes).from_address(self.ptr)
+
+    def array(self, dtype, count, offset=0):
+        return np.frombuffer(self._raw, dtype=dtype, count=count, offset=offset)
+
+    def free(self):
+        if self.ptr:
+            self._raw = None
+            _lib.lib().lpic_host_free(self.ptr)
+            self.ptr = None
+
+
+class SpeciesMirror:
+    """Host arenas of one species, same slot layout as the device arenas."""
+
+    def __init__(self, eng: "DeviceEngine", ispec: int, with_part: bool):
+        self.eng, self.ispec, self.with_part = eng, ispec, with_part
+        self.attrs = list(PART_ATTRS) if with_part else list(RESIDENT_ATTRS)
+        self.buffers = {}
+        self.host = {}
+        self.off = self.pcap = self.npart = None
+        self.total = 0
+        self.refresh_layout(copy_old=False)
+
+    def refresh_layout(self, copy_old: bool):
+        n = self.eng.npatch
+        off, pcap, npart = (np.zeros(n, dtype=np.int64) for _ in range(3))
+        total = C.c_int64(0)
+        check(self.eng.L.lpic_species_layout(self.eng.ctx, self.ispec, _ptr(off), _ptr(pcap), _ptr(npart), C.byref(total)))
+        old = (self.off, self.npart, self.host) if copy_old and self.off is not None else None
+        same = self.off is not None and total.value == self.total and np.array_equal(off, self.off)
+        self.off, self.pcap, self.npart, self.total = off, pcap, npart, int(total.value)
+        if same:
+            return
+        new_host, new_buf = {}, {}
+        for a in self.attrs + ["is_dead"]:
+            isz = 1 if a == "is_dead" else 8
+            buf = HostBuffer(self.total * isz)
+            arr = buf.array(np.uint8 if a == "is_dead" else np.float64, self.total)
+            if a == "is_dead":
+                arr[:] = 1
+            if old is not None:
+                o_off, o_np, o_host = old
+                for p in range(n):
+                    arr[off[p]:off[p] + o_np[p]] = o_host[a][o_off[p]:o_off[p] + o_np[p]]
+            new_host[a], new_buf[a] = arr, buf
+        for b in self.buffers.values():
+            b.free()
+        self.host, self.buffers = new_host, new_buf
+
+    def view(self, attr: str, p: int):
+        a = self.host[attr][self.off[p]:self.off[p] + self.npart[p]]
+        return a.view(np.bool_) if attr == "is_dead" else a
+
+    def free(self):
+        for b in self.buffers.values():
+            b.free()
+        self.buffers, self.host = {}, {}
+
+
+class DeviceEngine:
+    def __init__(self, dim, npatch, nx, ny, nz, n_guard, dx, dy, dz, nspec, device=0):
+        self.L = _lib.lib()
+        self.dim, self.npatch, self.nspec = int(dim), int(npatch), int(nspec)
+        self.nx, self.ny, self.nz, self.ng = int(nx), int(ny), int(nz if dim == 3 else 1), int(n_guard)
+        self.dx, self.dy, self.dz = float(dx), float(dy), float(dz if dim == 3 else 1.0)
+        self.nb = 26 if dim == 3 else 8
+        self.ctx = self.L.lpic_create(dim, npatch, nx, ny, self.nz, n_guard, dx, dy, self.dz, nspec, device)
+        if not self.ctx:
+            raise _lib.LpicError(self.L.lpic_last_error().decode())
+        self.shape = (nx + 2 * n_guard, ny + 2 * n_guard) + ((self.nz + 2 * n_guard,) if dim == 3 else ())
+        self.ncell = int(self.L.lpic_field_cells(self.ctx))
+        assert self.ncell == int(np.prod(self.shape))
+        self._fbuf = HostBuffer(8 * len(FIELD_ATTRS) * npatch * self.ncell)
+        self.fields_host = self._fbuf.array(np.float64, len(FIELD_ATTRS) * npatch * self.ncell).reshape(
+            (len(FIELD_ATTRS), npatch) + self.shape)
+        self.fields_host[...] = 0.0
+        self.species = [None] * nspec
+        self.sort_cfg = [None] * nspec
+        self.npart_created = [None] * nspec
+        self.rank = 0
+        self.patch_index = np.arange(npatch, dtype=np.int64)
+        self.x0 = self.y0 = self.z0 = None
+
+    # ---- lifetime --------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.L.lpic_destroy(self.ctx)
+            self.ctx = None
+            for s in self.species:
+                if s is not None:
+                    s.free()
+            self._fbuf.free()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        check(self.L.lpic_sync(self.ctx))
+
+    # ---- geometry --------------------------------------------------------------------------------------------
+    def set_geometry(self, x0, y0, z0, neighbor_ipatch, box, glob, rank=0, patch_index=None):
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
+        self.x0, self.y0 = f(x0), f(y0)
+        self.z0 = f(z0) if z0 is not None else np.zeros(self.npatch)
+        self.nbr = np.ascontiguousarray(neighbor_ipatch, dtype=np.int64).reshape(self.npatch, self.nb)
+        self.box = f(box).reshape(self.npatch, 6)
+        self.glob = f(glob).reshape(6)
+        self.rank = int(rank)
+        if patch_index is not None:
+            self.patch_index = np.ascontiguousarray(patch_index, dtype=np.int64)
+        check(self.L.lpic_set_patch_geometry(self.ctx, _ptr(self.x0), _ptr(self.y0), _ptr(self.z0), _ptr(self.nbr),
+                                             _ptr(self.box), _ptr(self.glob), self.rank, _ptr(self.patch_index)))
+
+    # ---- fields ----------------------------------------------------------------------------------------------
+    def field_view(self, attr: str, p: int):
+        return self.fields_host[FIELD_ATTRS.index(attr), p]
+
+    def upload_fields(self, mask=ALL_FIELDS):
+        check(self.L.lpic_upload_fields(self.ctx, mask, _ptr(self.fields_host)))
+
+    def download_fields(self, mask=ALL_FIELDS):
+        check(self.L.lpic_download_fields(self.ctx, mask, _ptr(self.fields_host)))
+
+    # ---- particles -------------------------------------------------------------------------------------------
+    def alloc_species(self, ispec, npart, slack=1.5, min_extra=64, with_part=False, npart_created=None):
+        npart = np.ascontiguousarray(npart, dtype=np.int64)
+        check(self.L.lpic_species_alloc(self.ctx, ispec, _ptr(npart), float(slack), int(min_extra), int(with_part)))
+        if self.species[ispec] is not None:
+            self.species[ispec].free()
+        self.species[ispec] = SpeciesMirror(self, ispec, bool(with_part))
+        self.npart_created[ispec] = (np.array(npart_created, dtype=np.int64) if npart_created is not None else npart.copy())
+        return self.species[ispec]
+
+    def upload_particles(self, ispec, attrs=None):
+        m = self.species[ispec]
+        for a in (attrs or m.attrs + ["is_dead"]):
+            aid = P_IS_DEAD if a == "is_dead" else PART_ATTRS.index(a)
+            check(self.L.lpic_upload_particles(self.ctx, ispec, aid, _ptr(m.host[a])))
+
+    def download_particles(self, ispec, attrs=None):
+        m = self.species[ispec]
+        for a in (attrs or m.attrs + ["is_dead"]):
+            aid = P_IS_DEAD if a == "is_dead" else PART_ATTRS.index(a)
+            check(self.L.lpic_download_particles(self.ctx, ispec, aid, _ptr(m.host[a])))
+
+    def upload_all(self):
+        self.upload_fields()
+        for s in range(self.nspec):
+            if self.species[s] is not None:
+                self.upload_particles(s)
+        self.sync()
+
+    def download_all(self):
+        self.download_fields()
+        for s in range(self.nspec):
+            if self.species[s] is not None:
+                self.download_particles(s)
+
+    def extend(self, ispec, ext):
+        """ParticlesBase.extend for every patch (core/particles.py:141-168); returns True if the arena moved."""
+        ext = np.ascontiguousarray(ext, dtype=np.int64)
+        if not ext.any():
+            return False
+        created = self.npart_created[ispec]
+        ids = ((np.uint64(self.rank) << np.uint64(50)) | (self.patch_index.astype(np.uint64) << np.uint64(32))
+               | created.astype(np.uint64))  # core/particles.py:91-116
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        moved = C.c_int(0)
+        check(self.L.lpic_species_extend(self.ctx, ispec, _ptr(ext), _ptr(ids), C.byref(moved)))
+        created += ext
+        self.species[ispec].refresh_layout(copy_old=False)
+        return bool(moved.value)
+
+    # ---- operators (one call each; names follow the reference facades) ------------------------------------------
+    def update_efield(self, dt):
+        check(self.L.lpic_update_efield(self.ctx, float(dt)))
+
+    def update_bfield(self, dt):
+        check(self.L.lpic_update_bfield(self.ctx, float(dt)))
+
+    def sync_guard_fields(self, mask):
+        check(self.L.lpic_sync_guard_fields(self.ctx, int(mask)))
+
+    def sync_currents(self):
+        check(self.L.lpic_sync_currents(self.ctx))
+
+    def reset_currents(self):
+        check(self.L.lpic_reset_currents(self.ctx))
+
+    def push_deposit(self, ispec, dt, q, m, write_part=False):
+        check(self.L.lpic_push_deposit(self.ctx, ispec, float(dt), float(q), float(m), _lib.PUSH_WRITE_PART if write_part else 0))
+
+    def interpolate(self, ispec):
+        check(self.L.lpic_interpolate(self.ctx, ispec))
+
+    def push_momentum(self, ispec, dt, q, m):
+        check(self.L.lpic_push_momentum(self.ctx, ispec, float(dt), float(q), float(m)))
+
+    def push_position(self, ispec, dt):
+        check(self.L.lpic_push_position(self.ctx, ispec, float(dt)))
+
+    def deposit(self, ispec, dt, q):
+        check(self.L.lpic_deposit(self.ctx, ispec, float(dt), float(q)))
+
+    def weighted_drift(self, ispec):
+        out = np.zeros(2)
+        check(self.L.lpic_weighted_drift(self.ctx, ispec, _ptr(out)))
+        return float(out[0]), float(out[1])
+
+    def configure_sort(self, ispec, nxb, nyb, nzb, dxb, dyb, dzb, x0s, y0s, z0s):
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
+        self.sort_cfg[ispec] = dict(nxb=int(nxb), nyb=int(nyb), nzb=int(nzb), dxb=float(dxb), dyb=float(dyb),
+                                    dzb=float(dzb), x0s=f(x0s), y0s=f(y0s), z0s=f(z0s) if z0s is not None else np.zeros(self.npatch))
+
+    def sort(self, ispec, reverse_x) -> int:
+        c = self.sort_cfg[ispec]
+        nbuf = C.c_int64(0)
+        check(self.L.lpic_sort(self.ctx, ispec, int(bool(reverse_x)), c["nxb"], c["nyb"], c["nzb"], c["dxb"], c["dyb"], c["dzb"],
+                               _ptr(c["x0s"]), _ptr(c["y0s"]), _ptr(c["z0s"]), C.byref(nbuf)))
+        return int(nbuf.value)
+
+    def sort_arrays(self, ispec):
+        """bucket_count / bound_min / bound_max as (npatch, nbin) int64 and particle_index per patch."""
+        c = self.sort_cfg[ispec]
+        nbin = c["nxb"] * c["nyb"] * c["nzb"]
+        out = {}
+        for name, which in (("bucket_count", _lib.SORT_BUCKET_COUNT), ("bound_min", _lib.SORT_BOUND_MIN),
+                            ("bound_max", _lib.SORT_BOUND_MAX)):
+            a = np.zeros((self.npatch, nbin), dtype=np.int64)
+            check(self.L.lpic_sort_download(self.ctx, ispec, which, _ptr(a)))
+            out[name] = a
+        m = self.species[ispec]
+        arena = np.zeros(max(m.total, 1), dtype=np.int64)
+        check(self.L.lpic_sort_download(self.ctx, ispec, _lib.SORT_PARTICLE_INDEX, _ptr(arena)))
+        out["particle_index"] = [arena[m.off[p]:m.off[p] + m.npart[p]].copy() for p in range(self.npatch)]
+        return out
+
+    def migrate_count(self, ispec):
+        n = self.npatch
+        ext, inc, alive = (np.zeros(n, dtype=np.int64) for _ in range(3))
+        out = np.zeros(n * self.nb, dtype=np.int64)
+        check(self.L.lpic_migrate_count(self.ctx, ispec, _ptr(ext), _ptr(inc), _ptr(out), _ptr(alive)))
+        return dict(to_extend=ext, incoming=inc, outgoing=out, alive=alive)
+
+    def migrate_fill(self, ispec):
+        check(self.L.lpic_migrate_fill(self.ctx, ispec))
+
+    def sync_particles(self, ispec):
+        """Patches.sync_particles for one species (core/patch/patch.py:705-764): count -> extend -> fill."""
+        rec = self.migrate_count(ispec)
+        rec["moved"] = self.extend(ispec, rec["to_extend"])
+        self.migrate_fill(ispec)
+        return rec
+
+    def count_alive(self, ispec) -> int:
+        out = C.c_int64(0)
+        check(self.L.lpic_count_alive(self.ctx, ispec, C.byref(out)))
+        return int(out.value)
+
+    def kinetic_sum(self, ispec) -> float:
+        out = C.c_double(0)
+        check(self.L.lpic_kinetic_sum(self.ctx, ispec, C.byref(out)))
+        return float(out.value)
+
+    def field_energy_sums(self):
+        out = np.zeros(2)
+        check(self.L.lpic_field_energy_sums(self.ctx, _ptr(out)))
+        return float(out[0]), float(out[1])
+
+    def init_uniform(self, ispec, ppc, weight, uth, seed):
+        check(self.L.lpic_species_init_uniform(self.ctx, ispec, int(ppc), float(weight), float(uth), int(seed)))
+
+    # ---- one full step, periodic / unified-pusher case (simulation/simulation.py:937-1130) ---------------------
+    def step(self, dt, q, m, reverse_x, write_part=False):
+        self.update_efield(0.5 * dt); self.sync_guard_fields(E_MASK)
+        self.update_bfield(0.5 * dt); self.sync_guard_fields(B_MASK)
+        nbuf = [self.sort(s, reverse_x[s]) for s in range(self.nspec)]
+        self.reset_currents()
+        for s in range(self.nspec):
+            self.push_deposit(s, dt, q[s], m[s], write_part)
+        self.sync_currents()
+        mig = [self.sync_particles(s) for s in range(self.nspec)]
+        self.update_bfield(0.5 * dt); self.sync_guard_fields(B_MASK)
+        self.update_efield(0.5 * dt); self.sync_guard_fields(E_MASK)
+        return nbuf, mig
