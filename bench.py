@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- particle-updates/s of the full PIC step (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path on the host cores
+
+Workload (config.workload): BASELINE.json configs[4], "3D uniform thermal plasma weak scaling": periodic
+electron-proton plasma, n = n_c(0.8 um), d = lambda/20, 1 keV, 16+16 particles per cell, 16^3-cell patches,
+256^3 cells PER GPU (N = 8 is the full 512^3 box).  configs[1..3] need CPML + laser (SURVEY.md 8(f), next tier)
+and configs[0] is the reference's own CPU-sized test, used by the parity tests.
+
+One "step" = everything simulation/simulation.py:937-1130 does between stage `start` and stage `end` for the
+periodic unified-pusher case: 4 FDTD half steps, 4 guard syncs, per-species sort, J/rho reset, fused
+gather+Boris+Esirkepov per species, current reduce, per-species migration.
+
+Prints ONE JSON line (see DESIGN.md "Measurement" for every key).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle-updates/sec (full PIC step)"
+UNIT = "particle-updates/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells", type=int, nargs=3, default=None, help="cells per GPU (default 256 256 256)")
+    ap.add_argument("--ppc", type=int, nargs=2, default=[16, 16])
+    ap.add_argument("--patch", type=int, default=16)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-cells", type=int, default=64, help="edge of the CPU sample box (cells)")
+    return ap.parse_args()
+
+
+def workload(args, nranks):
+    from lambdapic_b200.workloads import ThermalPlasma
+    per_gpu = tuple(args.cells) if args.cells else (256, 256, 256)
+    # weak scaling: the global box doubles along z, then y, then x as ranks double (8 ranks: 2x2x2 blocks)
+    mult = [1, 1, 1]
+    r, ax = nranks, 2
+    while r > 1:
+        mult[ax] *= 2
+        ax = (ax - 1) % 3
+        r //= 2
+    cells = tuple(c * m for c, m in zip(per_gpu, mult))
+    return ThermalPlasma(dim=3, cells=cells, patch=(args.patch,) * 3, ppc=tuple(args.ppc))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU baseline: the reference's own C extensions (oracle/_ref) or the oracle port, on the host cores
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_state(wl_small):
+    """Host-side OState with the same distribution as the device loader (uniform in cell, thermal momenta)."""
+    from oracle import oracle as orc
+    pg = wl_small.grid()
+    st = orc.OState(3, pg.nx, pg.ny, pg.nz, pg.n_guard, pg.dx, pg.dy, pg.dz, wl_small.dt, wl_small.q, wl_small.m,
+                    pg.x0, pg.y0, pg.z0, pg.neighbor_ipatch, pg.glob)
+    rng = np.random.default_rng(wl_small.seed)
+    ii, jj, kk = np.meshgrid(np.arange(pg.nx), np.arange(pg.ny), np.arange(pg.nz), indexing="ij")
+    for ip, p in enumerate(st.patches):
+        for s, ppc in enumerate(wl_small.ppc):
+            n = pg.nx * pg.ny * pg.nz * ppc
+            pt = p.particles[s]
+            pt.x = pg.x0[ip] + (np.repeat(ii.ravel(), ppc) + rng.random(n) - 0.5) * pg.dx
+            pt.y = pg.y0[ip] + (np.repeat(jj.ravel(), ppc) + rng.random(n) - 0.5) * pg.dy
+            pt.z = pg.z0[ip] + (np.repeat(kk.ravel(), ppc) + rng.random(n) - 0.5) * pg.dz
+            pt.ux, pt.uy, pt.uz = (rng.normal(0.0, wl_small.uth[s], n) for _ in range(3))
+            pt.inv_gamma = 1.0 / np.sqrt(1 + pt.ux**2 + pt.uy**2 + pt.uz**2)
+            pt.w = np.full(n, wl_small.weights[s])
+            for a in orc.PART_ATTRS[8:14]:
+                setattr(pt, a, np.zeros(n))
+            pt.npart = n
+            pt._id = pt._ids(0, n)
+            pt._npart_created = n
+            pt.is_dead = np.zeros(n, dtype=bool)
+    st.sorters = [orc.OSorter(st, s) for s in range(st.nspec)]
+    return st
+
+
+def cpu_reference_run(args, steps, warmup):
+    """Times `steps` full PIC steps of the reference's CPU path on a bounded sample of the workload."""
+    from lambdapic_b200.workloads import ThermalPlasma
+    from oracle import oracle as orc
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    orc.lib()
+    kind = "reference" if orc.have_ref() else "port"
+    backend = "ref" if kind == "reference" else "port"
+    e = args.cpu_cells
+    wl_small = ThermalPlasma(dim=3, cells=(e, e, e), patch=(args.patch,) * 3, ppc=tuple(args.ppc))
+    st = cpu_state(wl_small)
+    for _ in range(max(warmup, 1)):
+        orc.step(st, backend)
+    t0 = time.perf_counter()
+    n_upd = 0
+    for _ in range(steps):
+        n_upd += st.n_alive()
+        orc.step(st, backend)
+    dt = time.perf_counter() - t0
+    sample = (f"{e}^3 cells, {args.ppc[0]}+{args.ppc[1]} ppc, {args.patch}^3 patches ({wl_small.n_particles()} particles), "
+              f"{steps} steps after {max(warmup, 1)} warm-up; pusher/sort/sync = the reference's C extensions "
+              f"(OpenMP, {cores} threads), FDTD = C restatement (serial)" if kind == "reference" else
+              f"{e}^3 cells, oracle C port, serial")
+    return {"value": n_upd / dt, "unit": UNIT, "cores": cores if kind == "reference" else 1, "kind": kind,
+            "sample": sample, "ms_per_step": 1e3 * dt / steps}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_reference_run(args, args.steps, args.warmup)
+    wl = workload(args, args.gpus)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args, wl, args.gpus), "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args, wl, nranks):
+    return {"workload": "BASELINE.json configs[4]: 3D uniform thermal e-/p+ plasma, periodic, weak scaling "
+                        f"({wl.cells[0]}x{wl.cells[1]}x{wl.cells[2]} cells on {nranks} GPU(s), "
+                        f"{args.ppc[0]}+{args.ppc[1]} ppc, {args.patch}^3-cell patches, 1 keV, fp64)",
+            "cells_global": list(wl.cells), "particles_global": wl.n_particles(), "patch_cells": args.patch,
+            "ppc": list(args.ppc), "n_guard": 3, "parallelism": f"patch blocks over {nranks} GPU(s)",
+            "l2_policy": "inputs larger than L2 (particle arenas are tens of GB; no flush needed)"}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from lambdapic_b200 import _lib
+    from lambdapic_b200.workloads import build_engine
+    wl = workload(args, world)
+    eng = build_engine(wl, device=local, rank=rank, nranks=world)
+    if world > 1:
+        from lambdapic_b200.multigpu import HaloExchanger
+        eng.halo = HaloExchanger(eng, eng.grid)
+    L = _lib.lib()
+    dt, q, m = wl.dt, wl.q, wl.m
+    rev = [False, False]  # thermal plasma has no net drift: the reference picks the normal x order
+
+    def barrier():
+        eng.sync()
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    def one_step(slot=None):
+        if world > 1:
+            return eng.halo.step(dt, q, m, rev, slot)
+        return eng.step(dt, q, m, rev, event_slot=slot)
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    barrier()
+    alive0 = sum(eng.count_alive(s) for s in range(eng.nspec))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.lpic_launch_count()
+    barrier()
+    L.lpic_event_record(eng.ctx, 0)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        one_step(slot=2 + 4 * k)  # events 2+4k .. 5+4k bracket the two push_deposit launches of step k
+    L.lpic_event_record(eng.ctx, 1)
+    ms = _lib.C.c_double(0)
+    _lib.check(L.lpic_event_elapsed_ms(eng.ctx, 0, 1, _lib.C.byref(ms)))
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = L.lpic_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    # per-launch time of the dominant kernel (fused gather+push+deposit), CUDA events on its own stream
+    push_ms = []
+    for k in range(args.steps):
+        for s in range(eng.nspec):
+            e = _lib.C.c_double(0)
+            _lib.check(L.lpic_event_elapsed_ms(eng.ctx, 2 + 4 * k + 2 * s, 3 + 4 * k + 2 * s, _lib.C.byref(e)))
+            push_ms.append(e.value)
+    alive1 = sum(eng.count_alive(s) for s in range(eng.nspec))
+    step_ms = ms.value / args.steps
+    if world > 1:
+        t = torch.tensor([step_ms, float(alive0), float(alive1), float(launches)], dtype=torch.float64, device="cuda")
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        step_ms = float(tmax[0])
+        alive0, alive1, launches = int(t[1]), int(t[2]), int(t[3])
+    value = 0.5 * (alive0 + alive1) / (step_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    pg = eng.grid
+    n_local = 0.5 * (sum(eng.count_alive(s) for s in range(eng.nspec)) + alive0 / world) / eng.nspec  # per launch
+    # algorithmic bytes of ONE fused launch: 121 B per particle (8 attrs + is_dead read, 7 written)
+    # + per interior cell 6x8 B gather read + 4x16 B J/rho read-modify-write
+    cells_local = pg.npatch * pg.nx * pg.ny * pg.nz
+    bytes_launch = 121.0 * n_local + (48.0 + 64.0) * cells_local
+    avg_push_ms = float(np.mean(push_ms))
+    achieved = bytes_launch / (avg_push_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_particles<3,FUSED> (gather+Boris+Esirkepov)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6.65 TB/s",
+                "avg_launch_ms": avg_push_ms, "algorithmic_bytes_per_launch": bytes_launch,
+                "share_of_step": eng.nspec * avg_push_ms / (ms.value / args.steps)}
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        roofline["traffic"] = prof.get("k_particles_bytes_per_launch_at_bench_size")
+    except Exception:
+        pass
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args, wl, world),
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "wall_ms_per_step": 1e3 * wall / args.steps}
+
+    # ---- end to end through the public API with host buffers ---------------------------------------------------
+    if not args.no_e2e and world == 1:
+        line["e2e"] = e2e_run(args, eng, wl, rev)
+    elif world > 1:
+        line["e2e"] = {"value": None, "unit": UNIT, "note": "measured at N=1 only in this round"}
+    if not args.no_cpu_baseline and world == 1:
+        eng.close()
+        line["cpu_baseline"] = cpu_reference_run(args, steps=2, warmup=1)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def e2e_run(args, eng, wl, rev):
+    """Same metric with the state starting and ending in HOST memory: every timed step uploads the full particle
+    and field state from the pinned host mirrors, runs the step, and downloads it again (what a drop-in for the
+    reference's host-array operators pays when a callback touches the state every step)."""
+    from lambdapic_b200 import _lib
+    t_alloc = time.perf_counter()
+    eng.download_all()  # also allocates the pinned mirrors
+    t_alloc = time.perf_counter() - t_alloc
+    h2d = eng.fields_host.nbytes + sum(sum(a.nbytes for a in eng.species[s].host.values()) for s in range(eng.nspec))
+    steps = max(1, min(args.steps, 3))
+    n_upd = 0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        eng.upload_all()
+        n_upd += sum(eng.count_alive(s) for s in range(eng.nspec))
+        _, mig = eng.step(wl.dt, wl.q, wl.m, rev)
+        if any(r["moved"] for r in mig):
+            pass  # arena re-laid out: mirrors are re-created by download_all below
+        eng.download_all()
+    dt = time.perf_counter() - t0
+    d2h = eng.fields_host.nbytes + sum(sum(a.nbytes for a in eng.species[s].host.values()) for s in range(eng.nspec))
+    return {"value": n_upd / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "steps": steps, "ms_per_step": 1e3 * dt / steps, "pinned_alloc_s": t_alloc,
+            "mode": "per step: H2D of all fields+particles from pinned host mirrors, full PIC step, D2H of all state"}
+
+
+if __name__ == "__main__":
+    main()

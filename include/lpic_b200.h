@@ -136,6 +136,12 @@ int lpic_field_energy_sums(lpic_ctx *ctx, double *out2);
  *      momenta with per-component sigma `uth`); deterministic in (seed, patch, slot) */
 int lpic_species_init_uniform(lpic_ctx *ctx, int ispec, int64_t ppc, double weight, double uth, uint64_t seed);
 
+/* ---- measurement helpers: CUDA events on the context stream (bench.py), and the number of kernels this
+ *      library has launched so far in the process */
+int lpic_event_record(lpic_ctx *ctx, int slot);                              /* slot in [0, 4096) */
+int lpic_event_elapsed_ms(lpic_ctx *ctx, int slot_a, int slot_b, double *ms); /* synchronises on slot_b */
+int64_t lpic_launch_count(void);
+
 void *lpic_stream(lpic_ctx *ctx); /* cudaStream_t of the context (for event timing by the host) */
 
 #ifdef __cplusplus

@@ -64,6 +64,9 @@ SIGNATURES = {
     "lpic_kinetic_sum": (_int, [_vp, _int, _vp]),
     "lpic_field_energy_sums": (_int, [_vp, _vp]),
     "lpic_species_init_uniform": (_int, [_vp, _int, _i64, _dbl, _dbl, _u64]),
+    "lpic_event_record": (_int, [_vp, _int]),
+    "lpic_event_elapsed_ms": (_int, [_vp, _int, _int, _vp]),
+    "lpic_launch_count": (_i64, []),
     "lpic_stream": (_vp, [_vp]),
 }
 

@@ -6,6 +6,7 @@
 #include "lpic_common.cuh"
 
 static thread_local char g_err[1024] = "";
+long long g_lpic_launches = 0;
 
 void lpic_set_error(const char *fmt, ...) {
     va_list ap;
@@ -126,6 +127,11 @@ extern "C" void lpic_destroy(lpic_ctx *c) {
     cudaFree(c->scr_a); cudaFree(c->scr_b); cudaFree(c->scr_buf); cudaFree(c->d_sort_org); cudaFree(c->d_tmp64); cudaFree(c->d_tmpf);
     delete[] c->h_x0; delete[] c->h_y0; delete[] c->h_z0; delete[] c->h_nbr; delete[] c->h_patch_index;
     delete[] c->h_nbr_rank; delete[] c->h_remote_ipatch;
+    if (c->events) {
+        for (int i = 0; i < 4096; i++)
+            if (c->events[i]) cudaEventDestroy(c->events[i]);
+        delete[] c->events;
+    }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -383,6 +389,7 @@ extern "C" int lpic_species_extend(lpic_ctx *c, int ispec, const int64_t *ext, c
             double *fresh = nullptr;
             CUDA_TRY(cudaMalloc(&fresh, sizeof(double) * total));
             k_relayout<double><<<(unsigned)((i64)bpp * n), 256, 0, c->stream>>>(sp.attr[a], fresh, sp.d_off, d_newoff, sp.d_npart, bpp);
+            LAUNCHED(1);
             KERNEL_CHECK();
             CUDA_TRY(cudaStreamSynchronize(c->stream));
             cudaFree(sp.attr[a]);
@@ -392,6 +399,7 @@ extern "C" int lpic_species_extend(lpic_ctx *c, int ispec, const int64_t *ext, c
         CUDA_TRY(cudaMalloc(&fresh_dead, (size_t)total));
         CUDA_TRY(cudaMemsetAsync(fresh_dead, 1, (size_t)total, c->stream));
         k_relayout<u8><<<(unsigned)((i64)bpp * n), 256, 0, c->stream>>>(sp.dead, fresh_dead, sp.d_off, d_newoff, sp.d_npart, bpp);
+        LAUNCHED(1);
         KERNEL_CHECK();
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         cudaFree(sp.dead);
@@ -400,6 +408,7 @@ extern "C" int lpic_species_extend(lpic_ctx *c, int ispec, const int64_t *ext, c
         CUDA_TRY(cudaMalloc(&fresh_pidx, sizeof(int) * (size_t)total));
         CUDA_TRY(cudaMemsetAsync(fresh_pidx, 0xff, sizeof(int) * (size_t)total, c->stream));
         k_relayout<int><<<(unsigned)((i64)bpp * n), 256, 0, c->stream>>>(sp.sort.pidx, fresh_pidx, sp.d_off, d_newoff, sp.d_npart, bpp);
+        LAUNCHED(1);
         KERNEL_CHECK();
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         cudaFree(sp.sort.pidx);
@@ -425,6 +434,7 @@ extern "C" int lpic_species_extend(lpic_ctx *c, int ispec, const int64_t *ext, c
     const int bpp = (int)div_up(max_ext, 256);
     k_extend_init<<<(unsigned)((i64)bpp * n), 256, 0, c->stream>>>((int)n, sp.d_off, sp.d_npart, d_ext, d_idf, d_attrs, na,
                                                                  ia_w, ia_id, sp.dead, bpp);
+    LAUNCHED(1);
     KERNEL_CHECK();
     for (i64 p = 0; p < n; p++) sp.h_npart[p] += ext[p];
     {   // the reference re-creates the sorter's index arrays (-1) for every extended patch (simulation.py:781-824)
@@ -432,6 +442,7 @@ extern "C" int lpic_species_extend(lpic_ctx *c, int ispec, const int64_t *ext, c
         for (i64 p = 0; p < n; p++) m = std::max(m, sp.h_npart[p]);
         const int bpp2 = (int)div_up(std::max<i64>(m, 1), 256);
         k_pidx_reset<<<(unsigned)((i64)bpp2 * n), 256, 0, c->stream>>>(sp.d_off, sp.d_npart, d_ext, sp.sort.pidx, bpp2);
+        LAUNCHED(1);
         KERNEL_CHECK();
     }
     int r = upload_layout(c, sp);  // synchronises the stream
@@ -455,3 +466,21 @@ int lpic_ensure_scratch(lpic_ctx *c, i64 slots) {
 }
 
 void lpic_free_peers(lpic_ctx *) {}
+
+static const int kEventSlots = 4096;
+extern "C" int lpic_event_record(lpic_ctx *c, int slot) {
+    REQUIRE(slot >= 0 && slot < kEventSlots, "event slot %d out of range", slot);
+    if (!c->events) c->events = new cudaEvent_t[kEventSlots]();
+    if (!c->events[slot]) CUDA_TRY(cudaEventCreate(&c->events[slot]));
+    CUDA_TRY(cudaEventRecord(c->events[slot], c->stream));
+    return 0;
+}
+extern "C" int lpic_event_elapsed_ms(lpic_ctx *c, int a, int b, double *ms) {
+    REQUIRE(c->events && a >= 0 && b >= 0 && a < kEventSlots && b < kEventSlots && c->events[a] && c->events[b], "events not recorded");
+    CUDA_TRY(cudaEventSynchronize(c->events[b]));
+    float f = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&f, c->events[a], c->events[b]));
+    *ms = f;
+    return 0;
+}
+extern "C" int64_t lpic_launch_count(void) { return g_lpic_launches; }

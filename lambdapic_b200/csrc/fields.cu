@@ -191,6 +191,7 @@ extern "C" int lpic_update_efield(lpic_ctx *c, double dt) {
         k_update_efield<3><<<div_up(n, 256), 256, 0, c->stream>>>(g, c->fields, bfactor, jfactor);
     else
         k_update_efield<2><<<div_up(n, 256), 256, 0, c->stream>>>(g, c->fields, bfactor, jfactor);
+    LAUNCHED(1);
     KERNEL_CHECK();
     return 0;
 }
@@ -202,6 +203,7 @@ extern "C" int lpic_update_bfield(lpic_ctx *c, double dt) {
         k_update_bfield<3><<<div_up(n, 256), 256, 0, c->stream>>>(g, c->fields, dt);
     else
         k_update_bfield<2><<<div_up(n, 256), 256, 0, c->stream>>>(g, c->fields, dt);
+    LAUNCHED(1);
     KERNEL_CHECK();
     return 0;
 }
@@ -215,6 +217,7 @@ extern "C" int lpic_sync_guard_fields(lpic_ctx *c, uint32_t attr_mask) {
     if (!na) return 0;
     dim3 grid(div_up((i64)g.npatch * g.ncell, 256), na);
     k_sync_guard<<<grid, 256, 0, c->stream>>>(g, c->fields, c->d_nbr, attrs);
+    LAUNCHED(1);
     KERNEL_CHECK();
     return 0;
 }
@@ -223,6 +226,7 @@ extern "C" int lpic_sync_currents(lpic_ctx *c) {
     const Geom &g = c->g;
     dim3 grid(div_up((i64)g.npatch * g.nx * g.ny * g.nz, 256), 4);
     k_sync_currents<<<grid, 256, 0, c->stream>>>(g, c->fields, c->d_nbr);
+    LAUNCHED(1);
     KERNEL_CHECK();
     return 0;
 }
@@ -237,6 +241,7 @@ extern "C" int lpic_field_energy_sums(lpic_ctx *c, double *out2) {
     const Geom &g = c->g;
     CUDA_TRY(cudaMemsetAsync(c->d_tmpf, 0, 2 * sizeof(double), c->stream));
     k_field_energy<<<148 * 4, 256, 0, c->stream>>>(g, c->fields, c->d_tmpf);
+    LAUNCHED(1);
     KERNEL_CHECK();
     CUDA_TRY(cudaMemcpyAsync(out2, c->d_tmpf, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));

@@ -73,6 +73,7 @@ struct lpic_ctx {
     i64 *h_nbr_rank = nullptr, *h_remote_ipatch = nullptr;
     int nranks = 1;
     struct PeerHalo *peers = nullptr;
+    cudaEvent_t *events = nullptr;  // lazily created, 4096 slots
 };
 
 inline double *field_ptr(const lpic_ctx *c, int attr) { return c->fields + (size_t)attr * c->g.npatch * c->g.ncell; }
@@ -141,6 +142,9 @@ __host__ __device__ inline int wrapneg(int i, int N) { return i < 0 ? i + N : i;
 
 // kernels' launch helpers
 static inline unsigned div_up(i64 a, i64 b) { return (unsigned)((a + b - 1) / b); }
+
+extern long long g_lpic_launches;  // kernels launched by this library (bench.py's gpu_launches)
+#define LAUNCHED(n) (g_lpic_launches += (n))
 
 // entry points implemented per file
 int lpic_ensure_scratch(lpic_ctx *c, i64 slots);

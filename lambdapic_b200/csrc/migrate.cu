@@ -258,7 +258,9 @@ extern "C" int lpic_migrate_count(lpic_ctx *c, int ispec, int64_t *to_extend, in
     Species &sp = c->spec[ispec];
     const i64 n = c->g.npatch;
     k_count<<<(unsigned)n, T, 0, c->stream>>>(a);
+    LAUNCHED(1);
     k_plan<<<div_up(n, 128), 128, 0, c->stream>>>(a);
+    LAUNCHED(1);
     KERNEL_CHECK();
     if (to_extend) CUDA_TRY(cudaMemcpyAsync(to_extend, sp.d_extend, sizeof(i64) * n, cudaMemcpyDeviceToHost, c->stream));
     if (incoming) CUDA_TRY(cudaMemcpyAsync(incoming, sp.d_incoming, sizeof(i64) * n, cudaMemcpyDeviceToHost, c->stream));
@@ -275,9 +277,12 @@ extern "C" int lpic_migrate_fill(lpic_ctx *c, int ispec) {
     const i64 n = c->g.npatch;
     if (sp.max_npart == 0) return 0;
     k_lists<<<(unsigned)n, T, 0, c->stream>>>(a);
+    LAUNCHED(1);
     const int bpp = (int)div_up(sp.max_npart, T);
     k_fill<<<(unsigned)((i64)bpp * n), T, 0, c->stream>>>(a, bpp);
+    LAUNCHED(1);
     k_mark<<<(unsigned)((i64)bpp * n), T, 0, c->stream>>>(a, bpp);
+    LAUNCHED(1);
     KERNEL_CHECK();
     sp.sort.valid = false;
     return 0;

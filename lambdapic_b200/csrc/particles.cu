@@ -429,6 +429,7 @@ int launch_particles(lpic_ctx *c, int ispec, double dt, double q, double m, bool
     if (g.dim == 3) { if (write_part) LAUNCH(3, true); else LAUNCH(3, false); }
     else { if (write_part) LAUNCH(2, true); else LAUNCH(2, false); }
 #undef LAUNCH
+    LAUNCHED(1);
     KERNEL_CHECK();
     return 0;
 }
@@ -458,6 +459,7 @@ static int reduce_species(lpic_ctx *c, int ispec, int which, double *outf, int n
         const int bpp = (int)div_up(sp.max_npart, 256);
         k_reduce<<<(unsigned)((i64)bpp * c->g.npatch), 256, 0, c->stream>>>(make_slots(sp), bpp, which, c->d_tmpf,
                                                                            (unsigned long long *)c->d_tmp64);
+        LAUNCHED(1);
         KERNEL_CHECK();
     }
     if (outf) CUDA_TRY(cudaMemcpyAsync(outf, c->d_tmpf, nf * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -481,6 +483,7 @@ extern "C" int lpic_species_init_uniform(lpic_ctx *c, int ispec, int64_t ppc, do
     k_init_uniform<<<(unsigned)((i64)bpp * g.npatch), 256, 0, c->stream>>>(g, c->d_x0, c->d_y0, c->d_z0, make_slots(sp), sp.dead,
                                                                          sp.attr[LPIC_P_ID], bpp, ppc, weight, uth, seed,
                                                                          (u64)c->rank, d_pidx);
+    LAUNCHED(1);
     KERNEL_CHECK();
     sp.sort.valid = false;
     return 0;

@@ -304,6 +304,7 @@ extern "C" int lpic_sort(lpic_ctx *c, int ispec, int reverse_x, int64_t nxb, int
     a.pidx = st.pidx; a.bucket_count = st.bucket_count; a.bound_min = st.bound_min; a.bound_max = st.bound_max;
     a.g_hist = g_hist; a.g_cur = g_cur; a.tgt = c->scr_a; a.src_of = c->scr_b; a.nbuf = d_nbuf;
     k_sort_index<<<(unsigned)n, T, 0, c->stream>>>(a);
+    LAUNCHED(1);
     KERNEL_CHECK();
     std::vector<i64> h_nbuf(n);
     CUDA_TRY(cudaMemcpyAsync(h_nbuf.data(), d_nbuf, sizeof(i64) * n, cudaMemcpyDeviceToHost, c->stream));
@@ -318,10 +319,14 @@ extern "C" int lpic_sort(lpic_ctx *c, int ispec, int reverse_x, int64_t nxb, int
         for (int at = 0; at < LPIC_NPATTR; at++) {
             if (!sp.attr[at]) continue;
             k_sort_gather<double><<<grid, 256, 0, c->stream>>>(sp.attr[at], c->scr_buf, c->scr_b, sp.d_off, d_nbuf, bpp);
+            LAUNCHED(1);
             k_sort_scatter<double><<<grid, 256, 0, c->stream>>>(sp.attr[at], c->scr_buf, c->scr_a, sp.d_off, d_nbuf, bpp);
+            LAUNCHED(1);
         }
         k_sort_gather<u8><<<grid, 256, 0, c->stream>>>(sp.dead, (u8 *)c->scr_buf, c->scr_b, sp.d_off, d_nbuf, bpp);
+        LAUNCHED(1);
         k_sort_scatter<u8><<<grid, 256, 0, c->stream>>>(sp.dead, (const u8 *)c->scr_buf, c->scr_a, sp.d_off, d_nbuf, bpp);
+        LAUNCHED(1);
         KERNEL_CHECK();
     }
     st.valid = true;
@@ -337,6 +342,7 @@ extern "C" int lpic_sort_download(lpic_ctx *c, int ispec, int which, int64_t *ou
         i64 *tmp = nullptr;
         CUDA_TRY(cudaMalloc(&tmp, sizeof(i64) * std::max<i64>(sp.total, 1)));
         k_widen<<<div_up(std::max<i64>(sp.total, 1), 256), 256, 0, c->stream>>>(st.pidx, tmp, sp.total);
+        LAUNCHED(1);
         CUDA_TRY(cudaMemcpyAsync(out, tmp, sizeof(i64) * sp.total, cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         cudaFree(tmp);

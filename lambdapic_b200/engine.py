@@ -51,36 +51,33 @@ class SpeciesMirror:
         self.eng, self.ispec, self.with_part = eng, ispec, with_part
         self.attrs = list(PART_ATTRS) if with_part else list(RESIDENT_ATTRS)
         self.buffers = {}
-        self.host = {}
+        self._host = None  # pinned arenas are allocated on first use (the bench's device-resident leg never needs them)
         self.off = self.pcap = self.npart = None
         self.total = 0
-        self.refresh_layout(copy_old=False)
+        self.refresh_layout()
 
-    def refresh_layout(self, copy_old: bool):
+    @property
+    def host(self):
+        if self._host is None:
+            self._host = {}
+            for a in self.attrs + ["is_dead"]:
+                buf = HostBuffer(self.total * (1 if a == "is_dead" else 8))
+                arr = buf.array(np.uint8 if a == "is_dead" else np.float64, self.total)
+                if a == "is_dead":
+                    arr[:] = 1
+                self._host[a], self.buffers[a] = arr, buf
+        return self._host
+
+    def refresh_layout(self):
+        """Re-read the device layout; the host arenas are dropped if the arena moved (the device is authoritative)."""
         n = self.eng.npatch
         off, pcap, npart = (np.zeros(n, dtype=np.int64) for _ in range(3))
         total = C.c_int64(0)
         check(self.eng.L.lpic_species_layout(self.eng.ctx, self.ispec, _ptr(off), _ptr(pcap), _ptr(npart), C.byref(total)))
-        old = (self.off, self.npart, self.host) if copy_old and self.off is not None else None
         same = self.off is not None and total.value == self.total and np.array_equal(off, self.off)
         self.off, self.pcap, self.npart, self.total = off, pcap, npart, int(total.value)
-        if same:
-            return
-        new_host, new_buf = {}, {}
-        for a in self.attrs + ["is_dead"]:
-            isz = 1 if a == "is_dead" else 8
-            buf = HostBuffer(self.total * isz)
-            arr = buf.array(np.uint8 if a == "is_dead" else np.float64, self.total)
-            if a == "is_dead":
-                arr[:] = 1
-            if old is not None:
-                o_off, o_np, o_host = old
-                for p in range(n):
-                    arr[off[p]:off[p] + o_np[p]] = o_host[a][o_off[p]:o_off[p] + o_np[p]]
-            new_host[a], new_buf[a] = arr, buf
-        for b in self.buffers.values():
-            b.free()
-        self.host, self.buffers = new_host, new_buf
+        if not same:
+            self.free()
 
     def view(self, attr: str, p: int):
         a = self.host[attr][self.off[p]:self.off[p] + self.npart[p]]
@@ -89,7 +86,7 @@ class SpeciesMirror:
     def free(self):
         for b in self.buffers.values():
             b.free()
-        self.buffers, self.host = {}, {}
+        self.buffers, self._host = {}, None
 
 
 class DeviceEngine:
@@ -206,7 +203,7 @@ class DeviceEngine:
         moved = C.c_int(0)
         check(self.L.lpic_species_extend(self.ctx, ispec, _ptr(ext), _ptr(ids), C.byref(moved)))
         created += ext
-        self.species[ispec].refresh_layout(copy_old=False)
+        self.species[ispec].refresh_layout()
         return bool(moved.value)
 
     # ---- operators (one call each; names follow the reference facades) ------------------------------------------
@@ -309,13 +306,20 @@ class DeviceEngine:
         check(self.L.lpic_species_init_uniform(self.ctx, ispec, int(ppc), float(weight), float(uth), int(seed)))
 
     # ---- one full step, periodic / unified-pusher case (simulation/simulation.py:937-1130) ---------------------
-    def step(self, dt, q, m, reverse_x, write_part=False):
+    def record_event(self, slot):
+        check(self.L.lpic_event_record(self.ctx, int(slot)))
+
+    def step(self, dt, q, m, reverse_x, write_part=False, event_slot=None):
         self.update_efield(0.5 * dt); self.sync_guard_fields(E_MASK)
         self.update_bfield(0.5 * dt); self.sync_guard_fields(B_MASK)
         nbuf = [self.sort(s, reverse_x[s]) for s in range(self.nspec)]
         self.reset_currents()
         for s in range(self.nspec):
+            if event_slot is not None:
+                self.record_event(event_slot + 2 * s)
             self.push_deposit(s, dt, q[s], m[s], write_part)
+            if event_slot is not None:
+                self.record_event(event_slot + 2 * s + 1)
         self.sync_currents()
         mig = [self.sync_particles(s) for s in range(self.nspec)]
         self.update_bfield(0.5 * dt); self.sync_guard_fields(B_MASK)
