@@ -1,0 +1,11 @@
+"""lambdapic_b200: the lambdaPIC per-step inner loop on B200, behind the reference's Simulation / Species /
+callback-stage API.  ``import lambdapic_b200 as lambdapic`` is the intended drop-in for periodic-domain scripts."""
+from .callback import Callback, callback
+from .simulation import Simulation, Simulation2D, Simulation3D
+from .species import Electron, Positron, Proton, Species
+
+c, e, epsilon_0, m_e, m_p, mu_0, pi = (299792458.0, 1.602176634e-19, 8.8541878188e-12, 9.1093837139e-31,
+                                       1.67262192595e-27, 1.25663706127e-06, 3.141592653589793)
+
+__all__ = ["Simulation", "Simulation2D", "Simulation3D", "Species", "Electron", "Proton", "Positron",
+           "callback", "Callback", "c", "e", "epsilon_0", "m_e", "m_p", "mu_0", "pi"]

@@ -1,0 +1,181 @@
+"""DeviceBridge: keeps the host objects of a Simulation (Patches / Fields / ParticlesBase) and the GPU state coherent.
+
+Protocol (SURVEY.md 8b "stage <-> mirror contract"):
+  * the device is authoritative while ``resident`` is True (inside ``Simulation.run``'s loop);
+  * before callbacks of a stage run, everything is downloaded into the host mirrors; after them everything is
+    uploaded again (callbacks may write anything);
+  * operator facades called while not resident (user code outside ``run``) upload, run, and download, so they
+    behave like the reference's host-array operators.
+"""
+from __future__ import annotations
+
+from contextlib import contextmanager
+
+import numpy as np
+
+from ._lib import FIELD_ATTRS, PART_ATTRS
+from .engine import ALL_FIELDS, DeviceEngine
+from .fields import Fields2D, Fields3D
+
+
+class DeviceBridge:
+    def __init__(self, patches, n_guard, device=0, with_part=True, slack=1.5, nspec=0):
+        self.patches = patches
+        dim = patches.dimension
+        p0 = patches[0]
+        self.engine = DeviceEngine(dim, patches.npatches, p0.nx, p0.ny, getattr(p0, "nz", 1), n_guard,
+                                   p0.dx, p0.dy, getattr(p0, "dz", 0.0), nspec, device)
+        self.dim = dim
+        self.with_part, self.slack, self.device = with_part, slack, device
+        self.resident = False
+        self.stats = dict(uploads=0, downloads=0, h2d_bytes=0, d2h_bytes=0)
+        self._set_geometry()
+        F = Fields3D if dim == 3 else Fields2D
+        for ip, p in enumerate(patches):
+            p.set_fields(F(self.engine, ip, dim, p.x0, p.y0, getattr(p, "z0", 0.0)))
+        patches._bridge = self
+
+    def _set_geometry(self):
+        ps, dim = self.patches, self.dim
+        x0 = np.array([p.x0 for p in ps]); y0 = np.array([p.y0 for p in ps])
+        z0 = np.array([getattr(p, "z0", 0.0) for p in ps])
+        nbr = np.stack([p.neighbor_ipatch for p in ps]).astype(np.int64)
+        box = np.zeros((ps.npatches, 6))
+        for i, p in enumerate(ps):  # widened by half a cell, core/patch/sync_particles_3d.c:402-411
+            box[i, 0:4] = [p.xmin - p.dx / 2, p.xmax + p.dx / 2, p.ymin - p.dy / 2, p.ymax + p.dy / 2]
+            if dim == 3:
+                box[i, 4:6] = [p.zmin - p.dz / 2, p.zmax + p.dz / 2]
+        glob = np.array([ps.xmin_global, ps.xmax_global, ps.ymin_global, ps.ymax_global,
+                         ps.zmin_global or 0.0, ps.zmax_global or 0.0], dtype=float)
+        rank = ps[0].rank or 0
+        self.engine.set_geometry(x0, y0, z0, nbr, box, glob, rank, np.array([p.index for p in ps], dtype=np.int64))
+
+    # ---- species -----------------------------------------------------------------------------------------------
+    def _recreate_engine_species(self):
+        """(Re)allocate the device arenas from the host particle objects (all species)."""
+        ps, eng = self.patches, self.engine
+        nspec = len(ps.species)
+        if eng.nspec != nspec:  # species are added before initialize() finishes: rebuild the context once
+            fields = eng.fields_host.copy()
+            p0 = ps[0]
+            eng.close()
+            self.engine = eng = DeviceEngine(self.dim, ps.npatches, p0.nx, p0.ny, getattr(p0, "nz", 1), p0.fields.n_guard,
+                                             p0.dx, p0.dy, getattr(p0, "dz", 0.0), nspec, self.device)
+            self._set_geometry()
+            eng.fields_host[...] = fields
+            for ip, p in enumerate(ps):
+                for a in FIELD_ATTRS:
+                    setattr(p.fields, a, eng.field_view(a, ip))
+        for s in range(nspec):
+            self._alloc_species_from_host(s)
+
+    def _alloc_species_from_host(self, s):
+        ps, eng = self.patches, self.engine
+        parts = [p.particles[s] for p in ps]
+        npart = np.array([pt.npart for pt in parts], dtype=np.int64)
+        created = np.array([pt._npart_created for pt in parts], dtype=np.int64)
+        old = [{a: np.array(getattr(pt, a)) for a in PART_ATTRS} | {"is_dead": np.array(pt.is_dead, dtype=bool)} for pt in parts]
+        m = eng.alloc_species(s, npart, slack=self.slack, min_extra=64, with_part=self.with_part, npart_created=created)
+        for ip, pt in enumerate(parts):
+            self._seat(pt, m, ip)
+            for a in m.attrs:
+                getattr(pt, a)[...] = old[ip][a]
+            pt.is_dead[...] = old[ip]["is_dead"]
+            if not self.with_part:
+                for a in PART_ATTRS[8:14]:
+                    setattr(pt, a, old[ip][a])
+
+    def _seat(self, pt, m, ip):
+        for a in m.attrs:
+            setattr(pt, a, m.view(a, ip))
+        pt.is_dead = m.view("is_dead", ip)
+        pt.npart = int(m.npart[ip])
+        pt._detached = False
+
+    def _layout_changed_on_host(self, s):
+        m = self.engine.species[s] if s < len(self.engine.species) else None
+        if m is None:
+            return True
+        for ip, p in enumerate(self.patches):
+            pt = p.particles[s]
+            if pt._detached or pt.npart != int(m.npart[ip]):
+                return True
+        return False
+
+    # ---- coherency ---------------------------------------------------------------------------------------------
+    def upload(self):
+        ps, eng = self.patches, self.engine
+        nspec = len(ps.species)
+        if eng.nspec != nspec:
+            self._recreate_engine_species()
+        else:
+            for s in range(nspec):
+                if self._layout_changed_on_host(s):
+                    self._alloc_species_from_host(s)
+        eng.upload_all()
+        self.stats["uploads"] += 1
+        self.stats["h2d_bytes"] += self.state_bytes()
+
+    def download(self):
+        eng = self.engine
+        for s in range(eng.nspec):
+            m = eng.species[s]
+            reseat = m._host is None
+            eng.download_particles(s)
+            for ip, p in enumerate(self.patches):
+                pt = p.particles[s]
+                if reseat or pt.npart != int(m.npart[ip]) or pt.x.size != int(m.npart[ip]):
+                    if pt.npart != int(m.npart[ip]) or pt.x.size != int(m.npart[ip]):
+                        pt.extended = True
+                    self._seat(pt, m, ip)
+                    if not self.with_part:
+                        for a in PART_ATTRS[8:14]:
+                            setattr(pt, a, np.zeros(pt.npart))
+                pt._npart_created = int(eng.npart_created[s][ip])
+        eng.download_fields(ALL_FIELDS)
+        self.stats["downloads"] += 1
+        self.stats["d2h_bytes"] += self.state_bytes()
+
+    def state_bytes(self):
+        eng = self.engine
+        n = eng.fields_host.nbytes
+        for s in range(eng.nspec):
+            m = eng.species[s]
+            n += m.total * (8 * len(m.attrs) + 1)
+        return int(n)
+
+    @contextmanager
+    def coherent(self):
+        """Run a device operator on host-authoritative data (facade called outside the resident loop)."""
+        if self.resident:
+            yield
+            return
+        self.upload()
+        yield
+        self.download()
+
+    # ---- operators used by the facades -------------------------------------------------------------------------
+    def sync_guard_fields(self, attrs):
+        mask = 0
+        for a in attrs:
+            mask |= 1 << FIELD_ATTRS.index(a)
+        with self.coherent():
+            self.engine.sync_guard_fields(mask)
+
+    def sync_currents(self):
+        with self.coherent():
+            self.engine.sync_currents()
+
+    def sync_particles(self):
+        total = np.zeros(self.patches.npatches, dtype=np.int64)
+        with self.coherent():
+            for s in range(self.engine.nspec):
+                rec = self.engine.sync_particles(s)
+                total += rec["to_extend"]
+                for ip, p in enumerate(self.patches):
+                    if rec["to_extend"][ip] > 0:
+                        p.particles[s].extended = True
+        return total
+
+    def close(self):
+        self.engine.close()

@@ -1,0 +1,235 @@
+"""Patch containers with the reference's names (core/patch/patch.py:24-764).  Geometry and neighbour tables live
+on the host; fields and particles are views into the device mirrors owned by :class:`lambdapic_b200.device.DeviceBridge`."""
+from __future__ import annotations
+
+from enum import IntEnum, auto
+
+import numpy as np
+
+from .particles import ParticlesBase
+from .species import Species
+
+
+class Boundary2D(IntEnum):  # core/patch/patch.py:24-34
+    XMIN = 0
+    XMAX = auto()
+    YMIN = auto()
+    YMAX = auto()
+    XMINYMIN = auto()
+    XMAXYMIN = auto()
+    XMINYMAX = auto()
+    XMAXYMAX = auto()
+
+
+class Boundary3D(IntEnum):  # core/patch/patch.py:37-69
+    XMIN = 0
+    XMAX = auto()
+    YMIN = auto()
+    YMAX = auto()
+    ZMIN = auto()
+    ZMAX = auto()
+    XMINYMIN = auto()
+    XMINYMAX = auto()
+    XMINZMIN = auto()
+    XMINZMAX = auto()
+    XMAXYMIN = auto()
+    XMAXYMAX = auto()
+    XMAXZMIN = auto()
+    XMAXZMAX = auto()
+    YMINZMIN = auto()
+    YMINZMAX = auto()
+    YMAXZMIN = auto()
+    YMAXZMAX = auto()
+    XMINYMINZMIN = auto()
+    XMINYMINZMAX = auto()
+    XMINYMAXZMIN = auto()
+    XMINYMAXZMAX = auto()
+    XMAXYMINZMIN = auto()
+    XMAXYMINZMAX = auto()
+    XMAXYMAXZMIN = auto()
+    XMAXYMAXZMAX = auto()
+
+
+class Patch:
+    def __init__(self):
+        self.particles: list[ParticlesBase] = []
+        self.pml_boundary = []
+        self.fields = None
+
+    # particle box of the patch (core/patch/patch.py:105-148; no PML shrink on the periodic path)
+    xmin = property(lambda s: s.x0)
+    xmax = property(lambda s: s.x0 + (s.nx - 1) * s.dx)
+    ymin = property(lambda s: s.y0)
+    ymax = property(lambda s: s.y0 + (s.ny - 1) * s.dy)
+    zmin = property(lambda s: s.z0)
+    zmax = property(lambda s: s.z0 + (s.nz - 1) * s.dz)
+
+    def add_particles(self, particles: ParticlesBase) -> None:
+        self.particles.append(particles)
+
+    def set_fields(self, fields) -> None:
+        self.fields = fields
+
+
+class Patch2D(Patch):
+    def __init__(self, rank, index, ipatch_x, ipatch_y, x0, y0, nx, ny, dx, dy):
+        super().__init__()
+        self.rank, self.index, self.ipatch_x, self.ipatch_y = rank, index, ipatch_x, ipatch_y
+        self.x0, self.y0, self.nx, self.ny, self.dx, self.dy = x0, y0, nx, ny, dx, dy
+        self.xaxis = np.arange(nx) * dx + x0
+        self.yaxis = np.arange(ny) * dy + y0
+        n = len(Boundary2D)
+        self.neighbor_index = np.full(n, -1, dtype=int)
+        self.neighbor_rank = np.full(n, -1, dtype=int)
+        self.neighbor_ipatch = np.full(n, -1, dtype=int)
+
+
+class Patch3D(Patch):
+    def __init__(self, rank, index, ipatch_x, ipatch_y, ipatch_z, x0, y0, z0, nx, ny, nz, dx, dy, dz):
+        super().__init__()
+        self.rank, self.index = rank, index
+        self.ipatch_x, self.ipatch_y, self.ipatch_z = ipatch_x, ipatch_y, ipatch_z
+        self.x0, self.y0, self.z0 = x0, y0, z0
+        self.nx, self.ny, self.nz, self.dx, self.dy, self.dz = nx, ny, nz, dx, dy, dz
+        self.xaxis = np.arange(nx) * dx + x0
+        self.yaxis = np.arange(ny) * dy + y0
+        self.zaxis = np.arange(nz) * dz + z0
+        n = len(Boundary3D)
+        self.neighbor_index = np.full(n, -1, dtype=int)
+        self.neighbor_rank = np.full(n, -1, dtype=int)
+        self.neighbor_ipatch = np.full(n, -1, dtype=int)
+
+
+class Patches:
+    """Container of this rank's patches; the ``sync_*`` methods are the drop-in boundary of
+    core/patch/patch.py:670-764 and run on the GPU through the attached DeviceBridge."""
+
+    def __init__(self, dimension: int) -> None:
+        self.dimension = dimension
+        self.patches: list[Patch] = []
+        self.species: list[Species] = []
+        self.npatches = 0
+        self.xmin_global = self.xmax_global = self.ymin_global = self.ymax_global = None
+        self.zmin_global = self.zmax_global = None
+        self._bridge = None
+        self._comm = None
+
+    def __getitem__(self, i):
+        return self.patches[i]
+
+    def __len__(self):
+        return self.npatches
+
+    def __iter__(self):
+        return iter(self.patches)
+
+    def append(self, patch: Patch):
+        self.patches.append(patch)
+        self.npatches += 1
+
+    nx = property(lambda s: s.patches[0].nx)
+    ny = property(lambda s: s.patches[0].ny)
+    nz = property(lambda s: s.patches[0].nz)
+    dx = property(lambda s: s.patches[0].dx)
+    dy = property(lambda s: s.patches[0].dy)
+    dz = property(lambda s: s.patches[0].dz)
+    n_guard = property(lambda s: s.patches[0].fields.n_guard)
+
+    def update_lists(self):
+        pass
+
+    def _need_bridge(self):
+        if self._bridge is None:
+            raise RuntimeError("patches are not attached to a device (Simulation.initialize() does that); "
+                               "lambdapic_b200 has no CPU path")
+        return self._bridge
+
+    def sync_guard_fields(self, attrs=("ex", "ey", "ez", "bx", "by", "bz")):
+        self._need_bridge().sync_guard_fields(list(attrs))
+
+    def sync_currents(self):
+        self._need_bridge().sync_currents()
+
+    def sync_particles(self):
+        """Returns npart_to_extend summed over species, per patch (int64), like the reference."""
+        return self._need_bridge().sync_particles()
+
+    # ---- particle loading (host side so that seeds reproduce the reference's positions) ---------------------
+    def calculate_npart(self, species: Species):
+        """core/patch/patch.py:796-844 + core/patch/cpu.py:6-19,46-63: sum of int(ppc) over nodes with density > min."""
+        dim = self.dimension
+        out = np.zeros(self.npatches, dtype=np.int64)
+        if species.density is None:
+            return out
+        species.density_jit = Species.compile_profile(species.density, dim)
+        species.ppc_jit = Species.compile_profile(species.ppc, dim)
+        for ip, p in enumerate(self.patches):
+            _, ppc = _node_profiles(species, p, dim)
+            out[ip] = int(ppc.sum())
+        return out
+
+    def add_species(self, species: Species, aux_attrs=None) -> int:
+        npart = self.calculate_npart(species)
+        for ip, p in enumerate(self.patches):
+            part = ParticlesBase(ipatch=p.index, rank=p.rank)
+            part.attrs += list(aux_attrs or [])
+            part.initialize(int(npart[ip]))
+            p.add_particles(part)
+        self.species.append(species)
+        return int(npart.sum())
+
+    def fill_particles(self, rand_gen: np.random.Generator):
+        """core/patch/patch.py:864-907 + core/patch/cpu.py:22-43,66-99: per patch generator, node by node
+        x, y(, z) = uniform(-d/2, d/2, ppc) + node, w = density*dV/ppc -- drawn in that order so that the
+        random stream matches the reference's numba loop exactly."""
+        gens = rand_gen.spawn(self.npatches)
+        dim = self.dimension
+        for ispec, s in enumerate(self.species):
+            if s.density is None:
+                continue
+            for ip, p in enumerate(self.patches):
+                dens, ppc = _node_profiles(s, p, dim)
+                part = p.particles[ispec]
+                n = int(ppc.sum())
+                if n == 0:
+                    continue
+                d = (p.dx, p.dy) + ((p.dz,) if dim == 3 else ())
+                grids = np.meshgrid(*((p.xaxis, p.yaxis) + ((p.zaxis,) if dim == 3 else ())), indexing="ij")
+                ppc_f, dens_f = ppc.ravel(), dens.ravel()
+                nodes = [g.ravel() for g in grids]
+                u = gens[ip].random(dim * n)
+                # stream layout: node-major, then axis, then the ppc draws of that axis
+                first = np.concatenate([[0], np.cumsum(ppc_f)[:-1]])            # first particle of each node
+                node_of = np.repeat(np.arange(ppc_f.size), ppc_f)               # node of each particle
+                k = np.arange(n) - first[node_of]                               # index inside the node
+                for a, name in enumerate(("x", "y", "z")[:dim]):
+                    pos = dim * first[node_of] + a * ppc_f[node_of] + k
+                    low, rng = -d[a] / 2, d[a] / 2 - (-d[a] / 2)
+                    getattr(part, name)[:n] = (low + rng * u[pos]) + nodes[a][node_of]
+                wnode = dens_f.copy()
+                for da in d:  # dens*dx*dy*dz / ppc in the reference's association (core/patch/cpu.py:43,99)
+                    wnode = wnode * da
+                part.w[:n] = wnode[node_of] / ppc_f[node_of]
+
+
+def _node_profiles(species: Species, p: Patch, dim: int):
+    """density and int(ppc) on the nodes of patch p (0 where density <= density_min)."""
+    axes = (p.xaxis, p.yaxis) + ((p.zaxis,) if dim == 3 else ())
+    shape = tuple(len(a) for a in axes)
+    dfun, pfun = species.density_jit, species.ppc_jit
+    grids = np.meshgrid(*axes, indexing="ij")
+
+    def evaluate(fun):
+        try:
+            v = np.asarray(fun(*grids), dtype=float)
+            if v.shape == shape:
+                return v
+            if v.shape == ():
+                return np.full(shape, float(v))
+        except Exception:
+            pass
+        return np.vectorize(fun, otypes=[float])(*grids)
+    dens = evaluate(dfun)
+    ppc = evaluate(pfun).astype(np.int64)
+    ppc = np.where(dens > species.density_min, ppc, 0)
+    return dens, ppc

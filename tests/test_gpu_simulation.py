@@ -1,0 +1,112 @@
+"""GPU parity through the PUBLIC API: the same user script (Simulation / Species / callbacks) that produced the
+golden vectors with the unmodified reference is run on ``lambdapic_b200`` and compared step by step.
+
+  * seed-for-seed: positions come from the host loader (bit-exact vs the reference), momenta and seed fields from
+    the same ``init`` callback as oracle/make_golden.py;
+  * per step: integer state bit-exact, floats <= 1e-12 (single step from t0) / 1e-11 (accumulated);
+  * 1000 steps of BASELINE.json configs[0]: total-energy history within 1e-6 of the reference's.
+"""
+import types
+
+import numpy as np
+import pytest
+
+from tests.parity import check_state_against_golden
+from tests.test_host_api import make_sim
+
+pytestmark = pytest.mark.gpu
+
+
+def _golden_callbacks(first):
+    from lambdapic_b200 import callback
+
+    @callback("init")
+    def set_momenta(sim):  # same statements as oracle/make_golden.py:set_momenta
+        rng = np.random.default_rng(99)
+        for p in sim.patches:
+            for isp, part in enumerate(p.particles):
+                n = part.npart
+                sig = 0.6 if isp == 0 else 0.05
+                part.ux[:] = rng.normal(0.2 if isp == 0 else -0.02, sig, n)
+                part.uy[:] = rng.normal(0.0, sig, n)
+                part.uz[:] = rng.normal(0.0, sig, n)
+                part.inv_gamma[:] = 1.0 / np.sqrt(1 + part.ux**2 + part.uy**2 + part.uz**2)
+            f = p.fields
+            for a, amp in (("ex", 3e11), ("ey", -2e11), ("ez", 1e11), ("bx", 500.0), ("by", -800.0), ("bz", 300.0)):
+                arr = getattr(f, a)
+                arr[...] = amp * rng.standard_normal(arr.shape)
+    return set_momenta
+
+
+def _view(sim):
+    srt = [types.SimpleNamespace(bucket_count=s.bucket_count_list, bound_min=s.bucket_bound_min_list,
+                                 bound_max=s.bucket_bound_max_list, pidx=s.particle_index_list, nbuf_last=s.nbuf_last)
+           for s in sim.sorter]
+    return types.SimpleNamespace(patches=sim.patches, sorters=srt)
+
+
+@pytest.mark.parametrize("dim,case", [(3, "golden3d"), (2, "golden2d")])
+def test_public_api_run_matches_reference_step_by_step(dim, case, request):
+    g = request.getfixturevalue(case)
+    sim = make_sim(dim)
+    seen = {}
+
+    from lambdapic_b200 import callback
+
+    @callback("start")
+    def at_start(sim):
+        if "t0" not in seen:
+            seen["t0"] = check_state_against_golden(types.SimpleNamespace(patches=sim.patches, sorters=None), g, "t0", rtol=0.0,
+                                                    check_sorter=False)
+    init_cb = _golden_callbacks(True)
+    for it in range(3):
+        sim.run(nsteps=1, callbacks=[init_cb, at_start] if it == 0 else [at_start])
+        for s in range(2):
+            assert sim.sorter[s].reverse_x == bool(int(g[f"t1/reverse_x/{s}"]))
+        worst = check_state_against_golden(_view(sim), g, f"t{it + 1}", rtol=1e-12 if it == 0 else 1e-11)
+        assert worst <= 1e-11
+    assert seen["t0"] == 0.0  # the state handed to the first step is bit-identical to the reference's
+    assert sim.itime == 3
+    sim.bridge.close()
+
+
+def test_nonunified_path_with_pusher_stage_callback_2d(golden2d):
+    """A callback at a pusher stage forces the non-fused operator sequence (simulation.py:896-911,993-1038); the
+    result must equal the fused path to rounding, and the callback must see *_part on the host."""
+    from lambdapic_b200 import callback
+    g = golden2d
+    sim = make_sim(2)
+    seen = []
+
+    @callback("_interpolator")
+    def peek(sim):
+        seen.append(float(np.abs(sim.patches[0].particles[sim.ispec].ex_part).max()))
+    sim.run(nsteps=1, callbacks=[_golden_callbacks(True), peek])
+    assert len(seen) == 2 and min(seen) > 0.0
+    check_state_against_golden(_view(sim), g, "t1", rtol=1e-12)
+    sim.bridge.close()
+
+
+def test_energy_history_1000_steps_config0():
+    """BASELINE.json configs[0] (2D periodic thermal e-/p+ plasma, 64x64, 4x4 patches, 32+32 ppc): energy history
+    of 1000 steps within 1e-6 (relative to the total) of the unmodified reference's (tests/golden/energy_history_2d.npz)."""
+    import os
+    from lambdapic_b200 import Electron, Proton, Simulation, callback
+    from oracle.make_golden import energy_setup
+    ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "energy_history_2d.npz"))
+    d, n0 = 0.8e-6 / 20, 1.742e27
+    sim = Simulation(nx=64, ny=64, dx=d, dy=d, npatch_x=4, npatch_y=4, dt_cfl=0.95,
+                     boundary_conditions={k: "periodic" for k in ("xmin", "xmax", "ymin", "ymax")}, random_seed=77)
+    sim.add_species([Electron(density=lambda x, y: n0, ppc=32), Proton(density=lambda x, y: n0, ppc=32)])
+    set_momenta, energy, hist = energy_setup(sim, callback, np)
+    energy.interval = 50  # host diagnostics every 50 steps; the state stays on the device in between
+    sim.run(nsteps=int(ref["nsteps"]), callbacks=[set_momenta, energy])
+    got = np.array(hist)
+    want = ref["history"][49::50]
+    assert got.shape == want.shape
+    total = want.sum(axis=1)
+    err = np.abs(got - want).max(axis=1) / total
+    assert err.max() <= 1e-6, err.max()
+    drift = abs(got.sum(axis=1)[-1] - got.sum(axis=1)[0]) / got.sum(axis=1)[0]
+    assert drift < 0.01  # the reference's own bar (tests/test_numerical_heating.py:103-133)
+    sim.bridge.close()

@@ -1,0 +1,130 @@
+"""CPU tests of the host-side mirror of the reference API (no GPU compute): configuration validation, patch
+decomposition and neighbour tables, the host particle loader (bit-exact against the reference's numba loader on the
+same seed), callback trigger rules, and the comm shim over a world_size-2 gloo group."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from lambdapic_b200 import Electron, Proton, Simulation, Simulation3D, callback
+from lambdapic_b200.callback import _interval_triggered
+from lambdapic_b200.simulation import SimulationCallbacks
+from lambdapic_b200.workloads import block_rank_map, make_patch_grid
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+N0, D = 1.742e27, 0.8e-6 / 20
+
+
+def make_sim(dim):
+    if dim == 3:
+        sim = Simulation3D(nx=10, ny=8, nz=12, dx=D, dy=D * 1.25, dz=D * 0.8, npatch_x=2, npatch_y=2, npatch_z=2, dt_cfl=0.95,
+                           boundary_conditions={k: "periodic" for k in ("xmin", "xmax", "ymin", "ymax", "zmin", "zmax")}, random_seed=1234)
+        dens = lambda x, y, z: N0  # noqa: E731
+    else:
+        sim = Simulation(nx=16, ny=12, dx=D, dy=D * 1.25, npatch_x=2, npatch_y=3, dt_cfl=0.95,
+                         boundary_conditions={k: "periodic" for k in ("xmin", "xmax", "ymin", "ymax")}, random_seed=4321)
+        dens = lambda x, y: N0  # noqa: E731
+    sim.add_species([Electron(density=dens, ppc=3), Proton(density=dens, ppc=2)])
+    return sim
+
+
+@pytest.mark.parametrize("dim,case", [(3, "golden3d"), (2, "golden2d")])
+def test_loader_matches_reference_seed_for_seed(dim, case, request):
+    """Same seed => bit-identical x, y, z, w, _id per patch as the reference (tests/test_random_seed.py there)."""
+    g = request.getfixturevalue(case)
+    sim = make_sim(dim)
+    assert sim.dt == float(g["meta/dt"])
+    patches = sim.create_patches(sim._grid(0, 1))
+    for s in sim.species:
+        patches.add_species(s)
+    patches.fill_particles(np.random.default_rng(sim.random_seed).spawn(1)[0])
+    assert np.array_equal(np.stack([p.neighbor_ipatch for p in patches]), g["meta/neighbor_ipatch"])
+    for ip, p in enumerate(patches):
+        for s in range(2):
+            for a in ("x", "y", "z", "w", "_id"):
+                if dim == 2 and a == "z":
+                    continue
+                assert np.array_equal(getattr(p.particles[s], a).view(np.uint64), g[f"t0/p/{ip}/{s}/{a}"].view(np.uint64)), (ip, s, a)
+
+
+def test_config_validation():
+    per = {k: "periodic" for k in ("xmin", "xmax", "ymin", "ymax")}
+    with pytest.raises(ValueError):
+        Simulation(nx=10, ny=8, dx=D, dy=D, npatch_x=3, npatch_y=2, boundary_conditions=per)
+    with pytest.raises(ValueError):
+        Simulation(nx=16, ny=16, dx=D, dy=D, npatch_x=2, npatch_y=2, nsteps=1, sim_time=1e-15, boundary_conditions=per)
+    with pytest.raises(NotImplementedError):
+        Simulation(nx=16, ny=16, dx=D, dy=D, npatch_x=2, npatch_y=2)  # default boundaries are PML: next tier
+    sim = Simulation(nx=64, ny=32, dx=D, dy=D, boundary_conditions=per)
+    assert sim.npatch_x == 4 and sim.npatch_y == 2  # auto patching: 16-cell tiles
+    assert sim.STAGES[0] == "init" and sim.DEFAULT_STAGE == "end" and len(sim.STAGES) == 14
+    sim.add_species([Electron(density=lambda x, y: N0, ppc=1)])
+    with pytest.raises(ValueError):
+        sim.add_species([Electron(density=lambda x, y: N0, ppc=1)])
+    with pytest.raises(ValueError):
+        sim.add_species([Proton(density=lambda x, y, z: N0, ppc=1)])
+
+
+def test_callbacks_stage_and_interval_rules():
+    per = {k: "periodic" for k in ("xmin", "xmax", "ymin", "ymax")}
+    sim = Simulation(nx=32, ny=32, dx=D, dy=D, npatch_x=2, npatch_y=2, boundary_conditions=per)
+
+    @callback("maxwell_1", interval=3)
+    def a(sim):
+        pass
+
+    def plain(sim):
+        pass
+    cbs = SimulationCallbacks([a, plain], sim)
+    assert cbs.non_empty_stages() == ["maxwell_1", "end"]
+    sim.itime = 3
+    assert cbs.has_triggered_callbacks("maxwell_1")
+    sim.itime = 4
+    assert not cbs.has_triggered_callbacks("maxwell_1") and cbs.has_triggered_callbacks("end")
+    sim.time, sim.dt = 2.05e-15, 1e-16
+    assert _interval_triggered(sim, 1e-15) and not _interval_triggered(sim, 0.8e-15)
+    with pytest.raises(ValueError):
+        SimulationCallbacks([callback("nonsense")(plain)], sim)
+    with pytest.raises(ValueError):
+        callback("end", interval=0)(plain)
+
+
+def test_block_partition_and_remote_tables():
+    rk = block_rank_map(4, 4, 4, 8)
+    assert sorted(np.bincount(rk)) == [8] * 8
+    grids = [make_patch_grid(3, 4, 4, 4, 8, 8, 8, 1.0, 1.0, 1.0, rank=r, nranks=8) for r in range(8)]
+    seen = np.concatenate([g.index for g in grids])
+    assert sorted(seen) == list(range(64))
+    for g in grids:
+        local, remote = g.neighbor_ipatch >= 0, g.neighbor_rank >= 0
+        assert not (local & remote).any() and (local | remote).all()  # periodic: every neighbour exists somewhere
+        # the remote position really addresses that patch on its owner
+        for k in range(g.npatch):
+            for b in np.nonzero(remote[k])[0]:
+                owner = grids[g.neighbor_rank[k, b]]
+                assert owner.index[g.remote_ipatch[k, b]] == g.neighbor_index[k, b]
+
+
+def test_comm_shim_world_size_2_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(
+        "import os, sys\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import torch.distributed as dist\n"
+        "from lambdapic_b200.comm import default_comm\n"
+        "dist.init_process_group('gloo')\n"
+        "c = default_comm(); r = c.Get_rank()\n"
+        "assert c.Get_size() == 2\n"
+        "assert c.bcast({'a': r}, root=0) == {'a': 0}\n"
+        "assert c.scatter([['p0'], ['p1']] if r == 0 else None, root=0) == [f'p{r}']\n"
+        "assert c.allgather(r) == [0, 1]\n"
+        "assert c.allreduce(r + 1) == 3\n"
+        "g = c.gather(r * 10, root=0); assert (g == [0, 10]) if r == 0 else g is None\n"
+        "c.Barrier(); dist.destroy_process_group(); print('ok', r)\n")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29517", str(script)], capture_output=True, text=True, env=env, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.count("ok") == 2
