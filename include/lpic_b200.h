@@ -136,6 +136,28 @@ int lpic_field_energy_sums(lpic_ctx *ctx, double *out2);
  *      momenta with per-component sigma `uth`); deterministic in (seed, patch, slot) */
 int lpic_species_init_uniform(lpic_ctx *ctx, int ispec, int64_t ppc, double weight, double uth, uint64_t seed);
 
+/* ---- inter-rank exchange (replaces core/mpi/sync_fields{2d,3d}.c and core/mpi/sync_particles_{2d,3d}.c).
+ *      The library packs ONE staging buffer per peer rank and unpacks what arrived; the transport is NCCL
+ *      send/recv issued by the host on those device buffers (lambdapic_b200/multigpu.py).
+ *      Plan: for each peer slot, nsend[slot] / nrecv[slot] entries (local patch, boundary) in the canonical order
+ *      (ascending global index of the receiving patch, then boundary id at the receiver). */
+int lpic_halo_plan(lpic_ctx *ctx, int npeers, const int64_t *nsend, const int64_t *send_patch, const int64_t *send_b,
+                   const int64_t *nrecv, const int64_t *recv_patch, const int64_t *recv_b);
+/* fp64 words per grid attribute exchanged with the peer (recv = 0: what we send, 1: what we receive) */
+int64_t lpic_halo_words(lpic_ctx *ctx, int peer_slot, int recv);
+/* reduce = 0: E/B guard copy, sends interior strips (core/mpi/sync_fields3d.c:883-996);
+ * reduce = 1: J/rho, sends guard strips and zeroes them (:713-866).  Buffer layout [attribute][words]. */
+int lpic_halo_pack(lpic_ctx *ctx, int peer_slot, uint32_t attr_mask, int reduce, double *dev_send);
+int lpic_halo_unpack(lpic_ctx *ctx, uint32_t attr_mask, int reduce, const double *const *dev_recv_per_peer);
+/* remote migration (core/mpi/sync_particles_3d.c:413-745): prepare counts the alive leavers of every send entry
+ * and the dead slots per patch; pack writes them AoS (record = resident attributes) and marks them dead; unpack
+ * fills the dead slots of each patch in ascending order with the arrivals ordered by (boundary, sender slot). */
+int lpic_particle_record_words(lpic_ctx *ctx, int ispec);
+int lpic_remote_migrate_prepare(lpic_ctx *ctx, int ispec, int64_t *send_counts, int64_t *ndead);
+int lpic_remote_migrate_relist(lpic_ctx *ctx, int ispec);
+int lpic_remote_migrate_pack(lpic_ctx *ctx, int ispec, int peer_slot, double *dev_send, int64_t *nparticles);
+int lpic_remote_migrate_unpack(lpic_ctx *ctx, int ispec, const int64_t *recv_counts, const double *const *dev_recv_per_peer);
+
 /* ---- measurement helpers: CUDA events on the context stream (bench.py), and the number of kernels this
  *      library has launched so far in the process */
 int lpic_event_record(lpic_ctx *ctx, int slot);                              /* slot in [0, 4096) */

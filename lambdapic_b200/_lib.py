@@ -64,6 +64,15 @@ SIGNATURES = {
     "lpic_kinetic_sum": (_int, [_vp, _int, _vp]),
     "lpic_field_energy_sums": (_int, [_vp, _vp]),
     "lpic_species_init_uniform": (_int, [_vp, _int, _i64, _dbl, _dbl, _u64]),
+    "lpic_halo_plan": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lpic_halo_words": (_i64, [_vp, _int, _int]),
+    "lpic_halo_pack": (_int, [_vp, _int, _u32, _int, _vp]),
+    "lpic_halo_unpack": (_int, [_vp, _u32, _int, _vp]),
+    "lpic_particle_record_words": (_int, [_vp, _int]),
+    "lpic_remote_migrate_prepare": (_int, [_vp, _int, _vp, _vp]),
+    "lpic_remote_migrate_relist": (_int, [_vp, _int]),
+    "lpic_remote_migrate_pack": (_int, [_vp, _int, _int, _vp, _vp]),
+    "lpic_remote_migrate_unpack": (_int, [_vp, _int, _vp, _vp]),
     "lpic_event_record": (_int, [_vp, _int]),
     "lpic_event_elapsed_ms": (_int, [_vp, _int, _int, _vp]),
     "lpic_launch_count": (_i64, []),

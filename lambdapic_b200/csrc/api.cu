@@ -126,7 +126,6 @@ extern "C" void lpic_destroy(lpic_ctx *c) {
     cudaFree(c->fields); cudaFree(c->d_x0); cudaFree(c->d_y0); cudaFree(c->d_z0); cudaFree(c->d_nbr); cudaFree(c->d_box);
     cudaFree(c->scr_a); cudaFree(c->scr_b); cudaFree(c->scr_buf); cudaFree(c->d_sort_org); cudaFree(c->d_tmp64); cudaFree(c->d_tmpf);
     delete[] c->h_x0; delete[] c->h_y0; delete[] c->h_z0; delete[] c->h_nbr; delete[] c->h_patch_index;
-    delete[] c->h_nbr_rank; delete[] c->h_remote_ipatch;
     if (c->events) {
         for (int i = 0; i < 4096; i++)
             if (c->events[i]) cudaEventDestroy(c->events[i]);
@@ -465,7 +464,6 @@ int lpic_ensure_scratch(lpic_ctx *c, i64 slots) {
     return 0;
 }
 
-void lpic_free_peers(lpic_ctx *) {}
 
 static const int kEventSlots = 4096;
 extern "C" int lpic_event_record(lpic_ctx *c, int slot) {

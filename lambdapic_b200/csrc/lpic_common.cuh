@@ -48,6 +48,25 @@ struct Species {
     i64 *d_out = nullptr, *d_ndead = nullptr, *d_incoming = nullptr, *d_extend = nullptr, *d_alive = nullptr;
 };
 
+#define LPIC_MAX_PEERS 32
+// Inter-rank exchange plan: entries are (local patch, boundary) pairs whose neighbour lives on another rank, grouped
+// by peer and ordered canonically (ascending global index of the RECEIVING patch, then boundary at the receiver) so
+// that the sender's and the receiver's lists line up without any negotiation.
+struct HaloPlan {
+    int npeers = 0;
+    i64 nsend_total = 0, nrecv_total = 0;
+    i64 send_first[LPIC_MAX_PEERS + 1] = {0}, recv_first[LPIC_MAX_PEERS + 1] = {0};  // entry ranges per peer
+    i64 send_words[LPIC_MAX_PEERS] = {0}, recv_words[LPIC_MAX_PEERS] = {0};          // fp64 words per grid attribute
+    int *h_send_patch = nullptr, *h_send_b = nullptr, *h_recv_patch = nullptr, *h_recv_b = nullptr;
+    int *d_send_patch = nullptr, *d_send_b = nullptr;
+    i64 *d_send_woff = nullptr;                        // word offset of each send entry inside its peer's buffer
+    int *d_recv_peer = nullptr;                        // (npatch, nb): peer slot the boundary receives from, or -1
+    i64 *d_recv_woff = nullptr;                        // (npatch, nb): word offset inside that peer's buffer
+    // particle migration (per call): send entry -> particle count / offset; (patch, boundary) -> count / offset
+    i64 *h_mig_send_cnt = nullptr, *d_mig_send_cnt = nullptr, *d_mig_send_poff = nullptr;
+    i64 *d_mig_recv_cnt = nullptr, *d_mig_recv_poff = nullptr, *d_mig_incoming = nullptr;
+};
+
 struct lpic_ctx {
     Geom g;
     int device = 0;
@@ -69,10 +88,7 @@ struct lpic_ctx {
     double *d_sort_org = nullptr;            // (3, npatch) bucket origins
     i64 *d_tmp64 = nullptr;                  // small reductions (>= 8 + npatch words)
     double *d_tmpf = nullptr;
-    // inter-rank halo staging
-    i64 *h_nbr_rank = nullptr, *h_remote_ipatch = nullptr;
-    int nranks = 1;
-    struct PeerHalo *peers = nullptr;
+    struct HaloPlan *halo = nullptr;  // inter-rank exchange plan (halo.cu), null on a single rank
     cudaEvent_t *events = nullptr;  // lazily created, 4096 slots
 };
 

@@ -249,7 +249,162 @@ int make_args(lpic_ctx *c, int ispec, MigArgs &a) {
     return 0;
 }
 
+// ---- inter-rank migration (core/mpi/sync_particles_3d.c:413-745 restated for packed per-peer buffers) -------------
+struct PeerRecs {
+    const double *p[LPIC_MAX_PEERS];
+};
+
+// grid: (chunks of the largest entry, entries of this peer).  Record layout AoS: buf[(poff + r) * nattr + t].
+__global__ void __launch_bounds__(T) k_remote_pack(MigArgs a, const int *__restrict__ ent_patch, const int *__restrict__ ent_b,
+                                                   const i64 *__restrict__ cnt, const i64 *__restrict__ poff, i64 first,
+                                                   double *__restrict__ buf) {
+    const i64 e = first + blockIdx.y;
+    const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= cnt[e]) return;
+    const int p = ent_patch[e], b = ent_b[e];
+    const i64 src = a.off[p] + a.lb[a.off[p] + a.dirstart[(size_t)p * a.nb + b] + r];
+    double *rec = buf + (size_t)(poff[e] + r) * a.nattr;
+    for (int t = 0; t < a.nattr; t++) rec[t] = a.attrs[t][src];
+    a.dead[src] = 1;  // the sender gives the slot up at once (core/mpi/sync_particles_3d.c:573-577)
+}
+
+// one thread per arriving particle of patch p: boundaries in enum order, then sender slot order; k-th arrival ->
+// k-th dead slot (ascending)
+__global__ void __launch_bounds__(T) k_remote_unpack(MigArgs a, const int *__restrict__ recv_peer, const i64 *__restrict__ rcnt,
+                                                     const i64 *__restrict__ rpoff, const i64 *__restrict__ incoming,
+                                                     PeerRecs bufs, int blocks_per_patch) {
+    const int p = blockIdx.x / blocks_per_patch;
+    const i64 k = (i64)(blockIdx.x - p * blocks_per_patch) * blockDim.x + threadIdx.x;
+    if (k >= incoming[p] || k >= a.ndead[p]) return;
+    i64 run = 0;
+    const double *rec = nullptr;
+    for (int b = 0; b < a.nb; b++) {
+        const size_t key = (size_t)p * a.nb + b;
+        if (recv_peer[key] < 0) continue;
+        const i64 c = rcnt[key];
+        if (k < run + c) { rec = bufs.p[recv_peer[key]] + (size_t)(rpoff[key] + (k - run)) * a.nattr; break; }
+        run += c;
+    }
+    if (!rec) return;
+    const i64 np = a.npart[p];
+    const i64 dst = a.off[p] + a.la[a.off[p] + np - 1 - k];
+    const double *bx = a.box + 6 * (size_t)p;
+    for (int t = 0; t < a.nattr; t++) {
+        double v = rec[t];
+        const int d = t == a.ia_x ? 0 : (t == a.ia_y ? 1 : (t == a.ia_z ? 2 : -1));
+        if (d >= 0) {
+            const double lo = a.glob[2 * d], hi = a.glob[2 * d + 1], L = hi - lo, c0 = v;
+            if (c0 > hi && fabs(bx[2 * d] - lo) < a.cell[d]) v -= L;
+            if (c0 < lo && fabs(bx[2 * d + 1] - hi) < a.cell[d]) v += L;
+        }
+        a.attrs[t][dst] = v;
+    }
+    a.dead[dst] = 0;
+}
+
 }  // namespace
+
+extern "C" int lpic_particle_record_words(lpic_ctx *c, int ispec) {
+    MigArgs a;
+    if (make_args(c, ispec, a)) return -1;
+    return a.nattr;
+}
+
+extern "C" int lpic_remote_migrate_prepare(lpic_ctx *c, int ispec, int64_t *send_counts, int64_t *ndead) {
+    HaloPlan *h = c->halo;
+    REQUIRE(h, "no exchange plan");
+    MigArgs a;
+    if (int r = make_args(c, ispec, a)) return r;
+    Species &sp = c->spec[ispec];
+    const i64 n = c->g.npatch;
+    const int nb = c->g.nb;
+    k_count<<<(unsigned)n, T, 0, c->stream>>>(a);
+    k_lists<<<(unsigned)n, T, 0, c->stream>>>(a);
+    LAUNCHED(2);
+    KERNEL_CHECK();
+    std::vector<i64> out(n * nb);
+    CUDA_TRY(cudaMemcpyAsync(out.data(), sp.d_out, sizeof(i64) * n * nb, cudaMemcpyDeviceToHost, c->stream));
+    if (ndead) CUDA_TRY(cudaMemcpyAsync(ndead, sp.d_ndead, sizeof(i64) * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    std::vector<i64> poff(h->nsend_total + 1, 0);
+    for (int s = 0; s < h->npeers; s++) {
+        i64 run = 0;
+        for (i64 e = h->send_first[s]; e < h->send_first[s + 1]; e++) {
+            const i64 cnt = out[(size_t)h->h_send_patch[e] * nb + h->h_send_b[e]];
+            h->h_mig_send_cnt[e] = cnt;
+            if (send_counts) send_counts[e] = cnt;
+            poff[e] = run;
+            run += cnt;
+        }
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->d_mig_send_cnt, h->h_mig_send_cnt, sizeof(i64) * h->nsend_total, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_mig_send_poff, poff.data(), sizeof(i64) * h->nsend_total, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int lpic_remote_migrate_relist(lpic_ctx *c, int ispec) {
+    MigArgs a;
+    if (int r = make_args(c, ispec, a)) return r;
+    k_lists<<<(unsigned)c->g.npatch, T, 0, c->stream>>>(a);
+    LAUNCHED(1);
+    KERNEL_CHECK();
+    return 0;
+}
+
+extern "C" int lpic_remote_migrate_pack(lpic_ctx *c, int ispec, int slot, double *dev_send, int64_t *nparticles) {
+    HaloPlan *h = c->halo;
+    REQUIRE(h && slot >= 0 && slot < h->npeers, "no exchange plan / bad peer slot");
+    MigArgs a;
+    if (int r = make_args(c, ispec, a)) return r;
+    i64 total = 0, mx = 0;
+    for (i64 e = h->send_first[slot]; e < h->send_first[slot + 1]; e++) { total += h->h_mig_send_cnt[e]; mx = std::max(mx, h->h_mig_send_cnt[e]); }
+    if (nparticles) *nparticles = total;
+    if (total == 0) return 0;
+    dim3 grid(div_up(mx, T), (unsigned)(h->send_first[slot + 1] - h->send_first[slot]));
+    k_remote_pack<<<grid, T, 0, c->stream>>>(a, h->d_send_patch, h->d_send_b, h->d_mig_send_cnt, h->d_mig_send_poff,
+                                             h->send_first[slot], dev_send);
+    LAUNCHED(1);
+    KERNEL_CHECK();
+    c->spec[ispec].sort.valid = false;
+    return 0;
+}
+
+extern "C" int lpic_remote_migrate_unpack(lpic_ctx *c, int ispec, const int64_t *recv_counts, const double *const *dev_recv) {
+    HaloPlan *h = c->halo;
+    REQUIRE(h, "no exchange plan");
+    MigArgs a;
+    if (int r = make_args(c, ispec, a)) return r;
+    const i64 n = c->g.npatch;
+    const int nb = c->g.nb;
+    std::vector<i64> rcnt(n * nb, 0), rpoff(n * nb, 0), incoming(n, 0);
+    i64 mx = 0;
+    for (int s = 0; s < h->npeers; s++) {
+        i64 run = 0;
+        for (i64 e = h->recv_first[s]; e < h->recv_first[s + 1]; e++) {
+            const size_t key = (size_t)h->h_recv_patch[e] * nb + h->h_recv_b[e];
+            rcnt[key] = recv_counts[e];
+            rpoff[key] = run;
+            run += recv_counts[e];
+            incoming[h->h_recv_patch[e]] += recv_counts[e];
+        }
+    }
+    for (i64 p = 0; p < n; p++) mx = std::max(mx, incoming[p]);
+    if (mx == 0) return 0;
+    CUDA_TRY(cudaMemcpyAsync(h->d_mig_recv_cnt, rcnt.data(), sizeof(i64) * n * nb, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_mig_recv_poff, rpoff.data(), sizeof(i64) * n * nb, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_mig_incoming, incoming.data(), sizeof(i64) * n, cudaMemcpyHostToDevice, c->stream));
+    PeerRecs bufs;
+    for (int s = 0; s < h->npeers; s++) bufs.p[s] = dev_recv[s];
+    const int bpp = (int)div_up(mx, T);
+    k_remote_unpack<<<(unsigned)((i64)bpp * n), T, 0, c->stream>>>(a, h->d_recv_peer, h->d_mig_recv_cnt, h->d_mig_recv_poff,
+                                                                 h->d_mig_incoming, bufs, bpp);
+    LAUNCHED(1);
+    KERNEL_CHECK();
+    CUDA_TRY(cudaStreamSynchronize(c->stream));  // the host vectors above must outlive the copies
+    c->spec[ispec].sort.valid = false;
+    return 0;
+}
 
 extern "C" int lpic_migrate_count(lpic_ctx *c, int ispec, int64_t *to_extend, int64_t *incoming, int64_t *outgoing,
                                   int64_t *alive) {

@@ -65,3 +65,69 @@ def host_view(eng, nbuf=None, with_sorter=True):
                                                     bound_max=arr["bound_max"], pidx=arr["particle_index"],
                                                     nbuf_last=nbuf[s] if nbuf is not None else 0))
     return st
+
+
+def split_engines_from_golden(g, tag, nranks, with_part=False):
+    """One DeviceEngine per emulated rank (all on cuda:0), each owning its block of the golden state's patches."""
+    from lambdapic_b200.workloads import make_patch_grid
+    dim = int(g["meta/dim"])
+    nx, ny, nz, ng = (int(g[f"meta/{k}"]) for k in ("nx", "ny", "nz", "n_guard"))
+    dx, dy, dz = (float(g[f"meta/{k}"]) for k in ("dx", "dy", "dz"))
+    npx, npy, npz = (int(g[f"meta/npatch_{a}"]) for a in "xyz")
+    nspec = int(g["meta/nspec"])
+    glob = g["meta/bounds_global"]
+    engines, grids = [], []
+    for r in range(nranks):
+        pg = make_patch_grid(dim, npx, npy, npz, nx, ny, nz, dx, dy, dz, ng, (True, True, True), r, nranks)
+        eng = DeviceEngine(dim, pg.npatch, nx, ny, nz, ng, dx, dy, dz, nspec)
+        eng.set_geometry(pg.x0, pg.y0, pg.z0, pg.neighbor_ipatch, pg.boxes, pg.glob, r, pg.index)
+        assert np.allclose(pg.glob, glob)
+        for k, gp in enumerate(pg.index):
+            for a in FIELD_ATTRS:
+                eng.field_view(a, k)[...] = g[f"{tag}/f/{gp}/{a}"]
+        for s in range(nspec):
+            npart = [g[f"{tag}/p/{gp}/{s}/x"].size for gp in pg.index]
+            m = eng.alloc_species(s, npart, slack=1.5, min_extra=64, with_part=with_part)
+            for k, gp in enumerate(pg.index):
+                for a in m.attrs:
+                    m.view(a, k)[...] = g[f"{tag}/p/{gp}/{s}/{a}"]
+                m.view("is_dead", k)[...] = g[f"{tag}/p/{gp}/{s}/is_dead"].astype(bool)
+            eng.configure_sort(s, nx, 1, 1, dx, glob[3] - glob[2], (glob[5] - glob[4]) if dim == 3 else 1.0,
+                               pg.x0 - dx / 2, pg.y0 - dy / 2, pg.z0 - dz / 2)
+        eng.upload_all()
+        engines.append(eng)
+        grids.append(pg)
+    meta = dict(dt=float(g["meta/dt"]), q=[float(v) for v in g["meta/q"]], m=[float(v) for v in g["meta/m"]], dim=dim)
+    return engines, grids, meta
+
+
+def compare_split_state_with_golden(engines, grids, g, tag, rtol):
+    """N-rank result vs the 1-rank reference on the same global patch grid: fields <= rtol; per global patch the SET
+    of alive particles (by _id) must be identical and their attributes agree to rtol (slot order may differ because
+    arrivals from other ranks are placed before local ones)."""
+    from tests.parity import rel_err
+    worst = 0.0
+    nspec = engines[0].nspec
+    dim = engines[0].dim
+    for eng, pg in zip(engines, grids):
+        eng.download_all()
+        for k, gp in enumerate(pg.index):
+            for a in FIELD_ATTRS:
+                e = rel_err(eng.field_view(a, k), g[f"{tag}/f/{gp}/{a}"])
+                worst = max(worst, e)
+                assert e <= rtol, f"field {a} global patch {gp}: {e:.3e}"
+            for s in range(nspec):
+                m = eng.species[s]
+                alive = ~m.view("is_dead", k)
+                ralive = ~g[f"{tag}/p/{gp}/{s}/is_dead"].astype(bool)
+                ids = m.view("_id", k).view(np.uint64)[alive]
+                rids = g[f"{tag}/p/{gp}/{s}/_id"].view(np.uint64)[ralive]
+                assert ids.size == rids.size and np.array_equal(np.sort(ids), np.sort(rids)), f"particle set of patch {gp} spec {s}"
+                o, ro = np.argsort(ids), np.argsort(rids)
+                for a in ("x", "y", "z", "w", "ux", "uy", "uz", "inv_gamma"):
+                    if dim == 2 and a == "z":
+                        continue
+                    e = rel_err(m.view(a, k)[alive][o], g[f"{tag}/p/{gp}/{s}/{a}"][ralive][ro])
+                    worst = max(worst, e)
+                    assert e <= rtol, f"particle {a} global patch {gp} spec {s}: {e:.3e}"
+    return worst
