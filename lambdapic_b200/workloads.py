@@ -78,8 +78,9 @@ def block_rank_map(npx, npy, npz, nranks):
     r = nranks
     while r > 1:
         assert r % 2 == 0, "rank count must be a power of two"
-        ax = max(range(3), key=lambda a: (dims[a] / splits[a], a))  # z first on ties (slowest-varying index)
-        assert dims[ax] % (splits[ax] * 2) == 0, "patch grid not divisible by the rank grid"
+        ok = [a for a in range(3) if dims[a] % (splits[a] * 2) == 0]
+        assert ok, "patch grid not divisible by the rank grid"
+        ax = max(ok, key=lambda a: (dims[a] / splits[a], a))  # longest divisible axis; z first on ties
         splits[ax] *= 2
         r //= 2
     bx, by, bz = npx // splits[0], npy // splits[1], npz // splits[2]
