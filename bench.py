@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--cells", type=int, nargs=3, default=None, help="cells per GPU (default 256 256 256)")
     ap.add_argument("--ppc", type=int, nargs=2, default=[16, 16])
     ap.add_argument("--patch", type=int, default=16)
+    ap.add_argument("--slot-order", action="store_true", help="use the v1 particle kernel (memory order)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-cells", type=int, default=64, help="edge of the CPU sample box (cells)")
@@ -200,6 +201,7 @@ def main():
     from lambdapic_b200.workloads import build_engine
     wl = workload(args, world)
     eng = build_engine(wl, device=local, rank=rank, nranks=world)
+    eng.slot_order = args.slot_order
     if world > 1:
         from lambdapic_b200.multigpu import HaloExchanger
         eng.halo = HaloExchanger(eng, eng.grid)

@@ -1,0 +1,283 @@
+// Cell-ordered, warp-cooperative version of the fused particle kernel (3D).
+//
+// Same arithmetic as k_particles<3,FUSED> (particles.cu; reference: core/pusher/unified/unified_pusher_3d.c:281-431,
+// core/current/current_deposit.h:275-440) but organised for the memory system of the B200:
+//   1. k_cell_perm   one CTA per patch builds, once per species and step, a permutation of the ALIVE slots ordered
+//                    by cell (z fastest): shared-memory histogram -> block scan -> scatter.  The slot order in memory
+//                    stays the reference's (x-column buckets, bit-exact sort/migration indices); only the ORDER OF
+//                    PROCESSING changes.  Dead slots never reach the particle kernel.
+//   2. k_push_sorted one thread per alive particle in cell order.  A warp now works on 1-3 neighbouring cells, so its
+//                    6x27 gather loads coalesce into a handful of L1-resident sectors, and the 27x4 stencil values
+//                    of the lanes that share a start cell are summed across the warp (segmented shuffle reduction)
+//                    before a single head lane issues the fp64 RED: ~10x fewer L2 atomics per particle.
+//                    Particles that cross a cell boundary during the step (a few %) are appended to a list ...
+//   3. k_deposit_list ... and deposited by the general 125-point routine, one thread each.
+// Shared-memory fp64 atomics are a CAS loop on sm_100a (ATOMS.CAST.SPIN.64), which is why the reduction happens in
+// registers and the accumulation uses native REDG.E.ADD.F64 in L2.
+#include <algorithm>
+#include "lpic_common.cuh"
+#include "particle_math.cuh"
+
+namespace {
+
+constexpr int PT = 256;          // threads of the permutation CTA
+constexpr int KEY_LIMIT = 24576;  // cells per patch that fit the shared-memory histogram (96 KB)
+
+__device__ __forceinline__ int warp_incl_sum(int v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int n = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += n;
+    }
+    return v;
+}
+
+struct PermArgs {
+    const double *x, *y, *z;
+    const u8 *dead;
+    const i64 *off, *npart;
+    const double *x0, *y0, *z0;
+    int nx, ny, nz, kx, ky, kz;  // kx,ky,kz: key grid (nz -> 1 etc. when a patch has more cells than KEY_LIMIT)
+    double dx, dy, dz;
+    int *perm;     // arena: local slot numbers of the alive particles in cell order
+    i64 *nalive;   // per patch
+};
+
+__device__ __forceinline__ int node_of(double x, double x0, double d, int n) {
+    const int i = (int)floor((x - x0) / d + 0.5);
+    return i < 0 ? 0 : (i >= n ? n - 1 : i);
+}
+
+__global__ void __launch_bounds__(PT) k_cell_perm(PermArgs a) {
+    extern __shared__ int hist[];
+    __shared__ int sw[PT / 32];
+    const int p = blockIdx.x, tid = threadIdx.x;
+    const i64 off = a.off[p];
+    const int np = (int)a.npart[p];
+    const int nkey = a.kx * a.ky * a.kz;
+    for (int b = tid; b < nkey; b += PT) hist[b] = 0;
+    __syncthreads();
+    const double x0 = a.x0[p], y0 = a.y0[p], z0 = a.z0[p];
+    auto key_of = [&](int ip) -> int {
+        if (a.dead[off + ip]) return -1;
+        const double x = a.x[off + ip], y = a.y[off + ip], z = a.z[off + ip];
+        if (isnan(x) || isnan(y) || isnan(z)) return -1;
+        const int ix = node_of(x, x0, a.dx, a.nx), iy = a.ky > 1 ? node_of(y, y0, a.dy, a.ny) : 0,
+                  iz = a.kz > 1 ? node_of(z, z0, a.dz, a.nz) : 0;
+        return iz + a.kz * (iy + a.ky * ix);
+    };
+    for (int ip = tid; ip < np; ip += PT) {
+        const int k = key_of(ip);
+        if (k >= 0) atomicAdd(&hist[k], 1);
+    }
+    __syncthreads();
+    // exclusive scan of the histogram in place
+    int run = 0;
+    for (int base = 0; base < nkey; base += PT) {
+        const int b = base + tid;
+        const int cnt = b < nkey ? hist[b] : 0;
+        int v = warp_incl_sum(cnt);
+        if ((tid & 31) == 31) sw[tid >> 5] = v;
+        __syncthreads();
+        int add = 0, tot = 0;
+#pragma unroll
+        for (int i = 0; i < PT / 32; i++) {
+            if (i < (tid >> 5)) add += sw[i];
+            tot += sw[i];
+        }
+        if (b < nkey) hist[b] = run + v + add - cnt;
+        run += tot;
+        __syncthreads();
+    }
+    if (tid == 0) a.nalive[p] = run;
+    for (int ip = tid; ip < np; ip += PT) {
+        const int k = key_of(ip);
+        if (k >= 0) a.perm[off + atomicAdd(&hist[k], 1)] = ip;
+    }
+}
+
+// sum over the lanes [lane, seg_end] of a contiguous segment; the segment head (lowest lane) ends up with the total
+__device__ __forceinline__ double seg_reduce(double v, int lane, int seg_end) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double o = __shfl_down_sync(0xffffffffu, v, d);
+        if (lane + d <= seg_end) v += o;
+    }
+    return v;
+}
+
+__device__ __forceinline__ void shape3(double delta, double *S) {  // calculate_S0 restricted to its 3 non-zeros
+    const double d2 = delta * delta;
+    S[0] = 0.5 * (d2 + delta + 0.25);
+    S[1] = 0.75 - d2;
+    S[2] = 0.5 * (d2 - delta + 0.25);
+}
+
+template <bool WRITE_PART>
+__global__ void __launch_bounds__(128) k_push_sorted(Geom g, double *__restrict__ F, const double *__restrict__ px0,
+                                                     const double *__restrict__ py0, const double *__restrict__ pz0, Slots s,
+                                                     const int *__restrict__ perm, const i64 *__restrict__ nalive,
+                                                     int *__restrict__ cross, int *__restrict__ ncross, int blocks_per_patch,
+                                                     double dt, double q, double m) {
+    const int p = blockIdx.x / blocks_per_patch;
+    const i64 t = (i64)(blockIdx.x - p * blocks_per_patch) * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const i64 n = nalive[p];
+    if (t - lane >= n) return;  // whole warp beyond the alive particles of this patch
+    const bool active = t < n;
+    const i64 off = s.off[p];
+    const PatchView v = patch_view(g, F, px0, py0, pz0, p);
+    const double cdt = LPIC_C_LIGHT * 0.5 * dt;
+    double x = 0, y = 0, z = 0, ux = 0, uy = 0, uz = 0, ig = 1, w = 0;
+    i64 ip = 0;
+    int local = 0;
+    if (active) {
+        local = perm[off + t];
+        ip = off + local;
+        x = s.x[ip]; y = s.y[ip]; z = s.z[ip];
+        ux = s.ux[ip]; uy = s.uy[ip]; uz = s.uz[ip]; ig = s.ig[ip];
+        w = s.w[ip];
+        x += cdt * ig * ux; y += cdt * ig * uy; z += cdt * ig * uz;
+        double eb[6];
+        gather_eb<3>(g, v, x, y, z, eb);
+        if (WRITE_PART) {
+#pragma unroll
+            for (int a = 0; a < 6; a++) s.part[a][ip] = eb[a];
+        }
+        const double efactor = q * dt / (2 * m * LPIC_C_LIGHT), bfactor = q * dt / (2 * m);
+        boris_kick(ux, uy, uz, ig, eb, efactor, bfactor);
+        s.ux[ip] = ux; s.uy[ip] = uy; s.uz[ip] = uz; s.ig[ip] = ig;
+        x += cdt * ig * ux; y += cdt * ig * uy; z += cdt * ig * uz;
+        s.x[ip] = x; s.y[ip] = y; s.z[ip] = z;
+    }
+    // ---- deposit set-up (current_deposit.h:341-373) ------------------------------------------------------------
+    const double vx = ux * LPIC_C_LIGHT * ig, vy = uy * LPIC_C_LIGHT * ig, vz = uz * LPIC_C_LIGHT * ig;
+    const double X0 = (x - vx * 0.5 * dt - v.x0) / g.dx, X1 = (x + vx * 0.5 * dt - v.x0) / g.dx;
+    const double Y0 = (y - vy * 0.5 * dt - v.y0) / g.dy, Y1 = (y + vy * 0.5 * dt - v.y0) / g.dy;
+    const double Z0 = (z - vz * 0.5 * dt - v.z0) / g.dz, Z1 = (z + vz * 0.5 * dt - v.z0) / g.dz;
+    const int ix0 = (int)floor(X0 + 0.5), iy0 = (int)floor(Y0 + 0.5), iz0 = (int)floor(Z0 + 0.5);
+    const int ix1 = (int)floor(X1 + 0.5), iy1 = (int)floor(Y1 + 0.5), iz1 = (int)floor(Z1 + 0.5);
+    const bool fast = active && ix1 == ix0 && iy1 == iy0 && iz1 == iz0;
+    if (active && !fast) cross[off + atomicAdd(&ncross[p], 1)] = local;  // general routine, second kernel
+    // segments = runs of consecutive lanes that start in the same cell
+    const int bx0 = wrap_base(ix0, g.NX), by0 = wrap_base(iy0, g.NY), bz0 = wrap_base(iz0, g.NZ);
+    const int key = fast ? bz0 + g.NZ * (by0 + g.NY * bx0) : -1 - lane;
+    const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
+    const unsigned above = lane == 31 ? 0u : (heads >> (lane + 1));
+    const int seg_end = above ? lane + __ffs(above) - 1 : 31;
+    const bool head = (heads >> lane) & 1u;
+    if (!__any_sync(0xffffffffu, fast)) return;
+    double S0x[3], S0y[3], S0z[3], DSx[3], DSy[3], DSz[3];
+    shape3(ix0 - X0, S0x); shape3(iy0 - Y0, S0y); shape3(iz0 - Z0, S0z);
+    shape3(ix1 - X1, DSx); shape3(iy1 - Y1, DSy); shape3(iz1 - Z1, DSz);  // S1 (no cell crossing: same support)
+    double S1x[3], S1y[3], S1z[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        S1x[i] = DSx[i]; S1y[i] = DSy[i]; S1z[i] = DSz[i];
+        DSx[i] -= S0x[i]; DSy[i] -= S0y[i]; DSz[i] -= S0z[i];
+    }
+    const double wq = fast ? w : 0.0;  // lanes outside the fast path add zeros
+    const double cd = q / (g.dx * g.dy * g.dz) * wq, fdx = q / (g.dy * g.dz * dt) * wq, fdy = q / (g.dx * g.dz * dt) * wq,
+                 fdz = q / (g.dx * g.dy * dt) * wq;
+    double jxb[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) jxb[a][b] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int ox = wrap_once(bx0 + i - 1, g.NX) * g.NY * g.NZ;
+        const double ax = S0x[i] + 0.5 * DSx[i], cx = 0.5 * S0x[i] + LPIC_ONE_THIRD * DSx[i], fx = fdx * DSx[i];
+        double jyb[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const int oy = ox + wrap_once(by0 + j - 1, g.NY) * g.NZ;
+            const double ay = S0y[j] + 0.5 * DSy[j], cy = 0.5 * S0y[j] + LPIC_ONE_THIRD * DSy[j], fy = fdy * DSy[j];
+            const double tz = ax * S0y[j] + cx * DSy[j];
+            const double rxy = cd * S1x[i] * S1y[j];
+            double jzb = 0.0;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                jxb[k][j] -= fx * (ay * S0z[k] + cy * DSz[k]);
+                jyb[k] -= fy * (ax * S0z[k] + cx * DSz[k]);
+                jzb -= fdz * DSz[k] * tz;
+                const double r0 = seg_reduce(jxb[k][j], lane, seg_end);
+                const double r1 = seg_reduce(jyb[k], lane, seg_end);
+                const double r2 = seg_reduce(jzb, lane, seg_end);
+                const double r3 = seg_reduce(rxy * S1z[k], lane, seg_end);
+                if (head && fast) {
+                    const int id = oy + wrap_once(bz0 + k - 1, g.NZ);
+                    atomicAdd(v.jx + id, r0);
+                    atomicAdd(v.jy + id, r1);
+                    atomicAdd(v.jz + id, r2);
+                    atomicAdd(v.rho + id, r3);
+                }
+            }
+        }
+    }
+}
+
+// general deposit for the particles that changed cell during the step
+__global__ void __launch_bounds__(128) k_deposit_list(Geom g, double *__restrict__ F, const double *__restrict__ px0,
+                                                      const double *__restrict__ py0, const double *__restrict__ pz0, Slots s,
+                                                      const int *__restrict__ cross, const int *__restrict__ ncross,
+                                                      int blocks_per_patch, double dt, double q) {
+    const int p = blockIdx.x / blocks_per_patch;
+    const i64 t = (i64)(blockIdx.x - p * blocks_per_patch) * blockDim.x + threadIdx.x;
+    if (t >= ncross[p]) return;
+    const i64 ip = s.off[p] + cross[s.off[p] + t];
+    const PatchView v = patch_view(g, F, px0, py0, pz0, p);
+    DepositCoef3 k;
+    k.q_dV = q / (g.dx * g.dy * g.dz); k.q_dydzdt = q / (g.dy * g.dz * dt);
+    k.q_dxdzdt = q / (g.dx * g.dz * dt); k.q_dxdydt = q / (g.dx * g.dy * dt); k.dt = dt;
+    deposit3(g, v, k, s.x[ip], s.y[ip], s.z[ip], s.ux[ip], s.uy[ip], s.uz[ip], s.ig[ip], s.w[ip]);
+}
+
+}  // namespace
+
+// 3D fused push + deposit in cell order; returns 1 if this path does not apply (caller falls back to k_particles)
+int lpic_push_deposit_sorted(lpic_ctx *c, int ispec, double dt, double q, double m, bool write_part) {
+    const Geom &g = c->g;
+    Species &sp = c->spec[ispec];
+    if (g.dim != 3) return 1;
+    if (sp.max_npart == 0) return 0;
+    if (int r = lpic_ensure_scratch(c, sp.total)) return r;
+    PermArgs a;
+    a.x = sp.attr[LPIC_P_X]; a.y = sp.attr[LPIC_P_Y]; a.z = sp.attr[LPIC_P_Z]; a.dead = sp.dead;
+    a.off = sp.d_off; a.npart = sp.d_npart; a.x0 = c->d_x0; a.y0 = c->d_y0; a.z0 = c->d_z0;
+    a.nx = g.nx; a.ny = g.ny; a.nz = g.nz; a.kx = g.nx; a.ky = g.ny; a.kz = g.nz;
+    if ((i64)a.kx * a.ky * a.kz > KEY_LIMIT) a.kz = 1;
+    if ((i64)a.kx * a.ky * a.kz > KEY_LIMIT) a.ky = 1;
+    if ((i64)a.kx * a.ky * a.kz > KEY_LIMIT) return 1;
+    a.dx = g.dx; a.dy = g.dy; a.dz = g.dz;
+    a.perm = c->scr_b;
+    i64 *d_nalive = c->d_tmp64 + 64;
+    int *d_ncross = (int *)(c->d_tmp64 + 64 + g.npatch);
+    a.nalive = d_nalive;
+    const size_t smem = sizeof(int) * (size_t)a.kx * a.ky * a.kz;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(k_cell_perm, cudaFuncAttributeMaxDynamicSharedMemorySize, KEY_LIMIT * (int)sizeof(int)));
+        attr_set = true;
+    }
+    CUDA_TRY(cudaMemsetAsync(d_ncross, 0, sizeof(int) * g.npatch, c->stream));
+    k_cell_perm<<<g.npatch, PT, smem, c->stream>>>(a);
+    LAUNCHED(1);
+    const int B = 128;
+    const int bpp = (int)div_up(sp.max_npart, B);
+    const unsigned grid = (unsigned)((i64)bpp * g.npatch);
+    Slots s = make_slots(sp);
+    if (write_part)
+        k_push_sorted<true><<<grid, B, 0, c->stream>>>(g, c->fields, c->d_x0, c->d_y0, c->d_z0, s, c->scr_b, d_nalive, c->scr_a,
+                                                      d_ncross, bpp, dt, q, m);
+    else
+        k_push_sorted<false><<<grid, B, 0, c->stream>>>(g, c->fields, c->d_x0, c->d_y0, c->d_z0, s, c->scr_b, d_nalive, c->scr_a,
+                                                       d_ncross, bpp, dt, q, m);
+    LAUNCHED(1);
+    k_deposit_list<<<grid, B, 0, c->stream>>>(g, c->fields, c->d_x0, c->d_y0, c->d_z0, s, c->scr_a, d_ncross, bpp, dt, q);
+    LAUNCHED(1);
+    KERNEL_CHECK();
+    return 0;
+}
