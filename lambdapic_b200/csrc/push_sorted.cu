@@ -8,8 +8,8 @@
 //                    PROCESSING changes.  Dead slots never reach the particle kernel.
 //   2. k_push_sorted one thread per alive particle in cell order.  A warp now works on 1-3 neighbouring cells, so its
 //                    6x27 gather loads coalesce into a handful of L1-resident sectors, and the 27x4 stencil values
-//                    of the lanes that share a start cell are summed across the warp (segmented shuffle reduction)
-//                    before a single head lane issues the fp64 RED: ~10x fewer L2 atomics per particle.
+//                    of the lanes that share a start cell are summed across the warp (transposed through shared
+//                    memory) before a single lane issues the fp64 RED: ~10x fewer L2 atomics per particle.
 //                    Particles that cross a cell boundary during the step (a few %) are appended to a list ...
 //   3. k_deposit_list ... and deposited by the general 125-point routine, one thread each.
 // Shared-memory fp64 atomics are a CAS loop on sm_100a (ATOMS.CAST.SPIN.64), which is why the reduction happens in
@@ -20,6 +20,7 @@
 
 namespace {
 
+constexpr int PUSH_WARPS = 4;      // warps per CTA of the particle kernel (128 threads)
 constexpr int PT = 256;          // threads of the permutation CTA
 constexpr int KEY_LIMIT = 24576;  // cells per patch that fit the shared-memory histogram (96 KB)
 
@@ -97,16 +98,6 @@ __global__ void __launch_bounds__(PT) k_cell_perm(PermArgs a) {
     }
 }
 
-// sum over the lanes [lane, seg_end] of a contiguous segment; the segment head (lowest lane) ends up with the total
-__device__ __forceinline__ double seg_reduce(double v, int lane, int seg_end) {
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const double o = __shfl_down_sync(0xffffffffu, v, d);
-        if (lane + d <= seg_end) v += o;
-    }
-    return v;
-}
-
 __device__ __forceinline__ void shape3(double delta, double *S) {  // calculate_S0 restricted to its 3 non-zeros
     const double d2 = delta * delta;
     S[0] = 0.5 * (d2 + delta + 0.25);
@@ -114,8 +105,15 @@ __device__ __forceinline__ void shape3(double delta, double *S) {  // calculate_
     S[2] = 0.5 * (d2 - delta + 0.25);
 }
 
+// one RED for a finished segment: the segment head's start cell (sb = bx0, by0, bz0; bz0 < 0: nothing to deposit)
+__device__ __noinline__ void flush_red(double *dst, const int *sb, int i, int sj, int sk, int NX, int NY, int NZ, double sum) {
+    if (sb[2] < 0) return;
+    const int id = wrap_once(sb[0] + i - 1, NX) * NY * NZ + wrap_once(sb[1] + sj - 1, NY) * NZ + wrap_once(sb[2] + sk - 1, NZ);
+    atomicAdd(dst + id, sum);
+}
+
 template <bool WRITE_PART>
-__global__ void __launch_bounds__(128) k_push_sorted(Geom g, double *__restrict__ F, const double *__restrict__ px0,
+__global__ void __launch_bounds__(128, 4) k_push_sorted(Geom g, double *__restrict__ F, const double *__restrict__ px0,
                                                      const double *__restrict__ py0, const double *__restrict__ pz0, Slots s,
                                                      const int *__restrict__ perm, const i64 *__restrict__ nalive,
                                                      int *__restrict__ cross, int *__restrict__ ncross, int blocks_per_patch,
@@ -165,9 +163,6 @@ __global__ void __launch_bounds__(128) k_push_sorted(Geom g, double *__restrict_
     const int key = fast ? bz0 + g.NZ * (by0 + g.NY * bx0) : -1 - lane;
     const int prev = __shfl_up_sync(0xffffffffu, key, 1);
     const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
-    const unsigned above = lane == 31 ? 0u : (heads >> (lane + 1));
-    const int seg_end = above ? lane + __ffs(above) - 1 : 31;
-    const bool head = (heads >> lane) & 1u;
     if (!__any_sync(0xffffffffu, fast)) return;
     double S0x[3], S0y[3], S0z[3], DSx[3], DSy[3], DSz[3];
     shape3(ix0 - X0, S0x); shape3(iy0 - Y0, S0y); shape3(iz0 - Z0, S0z);
@@ -181,6 +176,25 @@ __global__ void __launch_bounds__(128) k_push_sorted(Geom g, double *__restrict_
     const double wq = fast ? w : 0.0;  // lanes outside the fast path add zeros
     const double cd = q / (g.dx * g.dy * g.dz) * wq, fdx = q / (g.dy * g.dz * dt) * wq, fdy = q / (g.dx * g.dz * dt) * wq,
                  fdz = q / (g.dx * g.dy * dt) * wq;
+    // Warp-level reduction through shared memory, one x-plane of the 3x3x3 stencil at a time.  Every lane stores
+    // its values of the plane as rows of a [30][33] tile (row stride 33 doubles: conflict-free both ways); then lane l
+    // owns row l and adds up the 32 source lanes, issuing ONE fp64 RED per segment (= run of lanes that start in the
+    // same cell).  Rows per plane: rho 9, jy 6, jz 6, jx 9 -- the last jx plane, jy row and jz column of a particle
+    // that stays in its cell are sum(DS) = 0 up to rounding (|.| <= 4 eps of the particle's largest term) and are not
+    // deposited, which makes every plane fit one round of 32 lanes.
+    __shared__ double red[PUSH_WARPS][30 * 33];
+    __shared__ int segbase[PUSH_WARPS][32][3];
+    double *tile = red[threadIdx.x >> 5];
+    int(*sb)[3] = segbase[threadIdx.x >> 5];
+    sb[lane][0] = bx0; sb[lane][1] = by0; sb[lane][2] = fast ? bz0 : -1;
+    // which row does this lane own?  [0,9) rho(j,k)  [9,15) jy(j<2,k)  [15,21) jz(j,k<2)  [21,30) jx(j,k)
+    int comp, sj, sk;
+    if (lane < 9) { comp = 3; sj = lane / 3; sk = lane - 3 * sj; }
+    else if (lane < 15) { comp = 1; sj = (lane - 9) / 3; sk = (lane - 9) - 3 * sj; }
+    else if (lane < 21) { comp = 2; sj = (lane - 15) >> 1; sk = (lane - 15) & 1; }
+    else { comp = 0; sj = (lane - 21) / 3; sk = (lane - 21) - 3 * sj; }
+    double *dst = comp == 0 ? v.jx : (comp == 1 ? v.jy : (comp == 2 ? v.jz : v.rho));
+    const double *row = tile + lane * 33;
     double jxb[3][3];
 #pragma unroll
     for (int a = 0; a < 3; a++)
@@ -188,34 +202,63 @@ __global__ void __launch_bounds__(128) k_push_sorted(Geom g, double *__restrict_
         for (int b = 0; b < 3; b++) jxb[a][b] = 0.0;
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-        const int ox = wrap_once(bx0 + i - 1, g.NX) * g.NY * g.NZ;
         const double ax = S0x[i] + 0.5 * DSx[i], cx = 0.5 * S0x[i] + LPIC_ONE_THIRD * DSx[i], fx = fdx * DSx[i];
         double jyb[3] = {0.0, 0.0, 0.0};
 #pragma unroll
         for (int j = 0; j < 3; j++) {
-            const int oy = ox + wrap_once(by0 + j - 1, g.NY) * g.NZ;
             const double ay = S0y[j] + 0.5 * DSy[j], cy = 0.5 * S0y[j] + LPIC_ONE_THIRD * DSy[j], fy = fdy * DSy[j];
             const double tz = ax * S0y[j] + cx * DSy[j];
             const double rxy = cd * S1x[i] * S1y[j];
             double jzb = 0.0;
 #pragma unroll
             for (int k = 0; k < 3; k++) {
-                jxb[k][j] -= fx * (ay * S0z[k] + cy * DSz[k]);
-                jyb[k] -= fy * (ax * S0z[k] + cx * DSz[k]);
-                jzb -= fdz * DSz[k] * tz;
-                const double r0 = seg_reduce(jxb[k][j], lane, seg_end);
-                const double r1 = seg_reduce(jyb[k], lane, seg_end);
-                const double r2 = seg_reduce(jzb, lane, seg_end);
-                const double r3 = seg_reduce(rxy * S1z[k], lane, seg_end);
-                if (head && fast) {
-                    const int id = oy + wrap_once(bz0 + k - 1, g.NZ);
-                    atomicAdd(v.jx + id, r0);
-                    atomicAdd(v.jy + id, r1);
-                    atomicAdd(v.jz + id, r2);
-                    atomicAdd(v.rho + id, r3);
+                tile[(j * 3 + k) * 33 + lane] = rxy * S1z[k];
+                if (i < 2) {
+                    jxb[k][j] -= fx * (ay * S0z[k] + cy * DSz[k]);
+                    tile[(21 + j * 3 + k) * 33 + lane] = jxb[k][j];
+                }
+                if (j < 2) {
+                    jyb[k] -= fy * (ax * S0z[k] + cx * DSz[k]);
+                    tile[(9 + j * 3 + k) * 33 + lane] = jyb[k];
+                }
+                if (k < 2) {
+                    jzb -= fdz * DSz[k] * tz;
+                    tile[(15 + j * 2 + k) * 33 + lane] = jzb;
                 }
             }
         }
+        __syncwarp();
+        if (lane < (i < 2 ? 30 : 21)) {
+            double acc = 0.0;
+            int seg = 0;  // lane index of the current segment's head
+#pragma unroll
+            for (int g4 = 0; g4 < 32; g4 += 4) {
+                const unsigned mm = (heads >> g4) & 0xFu;
+                if ((mm & 0xEu) == 0u) {  // no segment starts strictly inside this group of 4 source lanes
+                    if (g4 > 0 && (mm & 1u)) {
+                        flush_red(dst, sb[seg], i, sj, sk, g.NX, g.NY, g.NZ, acc);
+                        acc = 0.0;
+                        seg = g4;
+                    }
+                    acc += row[g4];
+                    acc += row[g4 + 1];
+                    acc += row[g4 + 2];
+                    acc += row[g4 + 3];
+                } else {
+                    for (int t = 0; t < 4; t++) {
+                        const int src = g4 + t;
+                        if (src > 0 && ((mm >> t) & 1u)) {
+                            flush_red(dst, sb[seg], i, sj, sk, g.NX, g.NY, g.NZ, acc);
+                            acc = 0.0;
+                            seg = src;
+                        }
+                        acc += row[src];
+                    }
+                }
+            }
+            flush_red(dst, sb[seg], i, sj, sk, g.NX, g.NY, g.NZ, acc);
+        }
+        __syncwarp();
     }
 }
 
