@@ -43,7 +43,9 @@ def parse():
     ap.add_argument("--cells", type=int, nargs=3, default=None, help="cells per GPU (default 256 256 256)")
     ap.add_argument("--ppc", type=int, nargs=2, default=[16, 16])
     ap.add_argument("--patch", type=int, default=16)
+    ap.add_argument("--row-tile", action="store_true", help="experimental row kernel (E/B tile in shared memory)")
     ap.add_argument("--slot-order", action="store_true", help="use the v1 particle kernel (memory order)")
+    ap.add_argument("--breakdown", action="store_true", help="print per-operator CUDA-event times of one extra step to stderr")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-cells", type=int, default=64, help="edge of the CPU sample box (cells)")
@@ -202,6 +204,7 @@ def main():
     wl = workload(args, world)
     eng = build_engine(wl, device=local, rank=rank, nranks=world)
     eng.slot_order = args.slot_order
+    eng.row_tile = args.row_tile
     if world > 1:
         from lambdapic_b200.multigpu import HaloExchanger
         eng.halo = HaloExchanger(eng, eng.grid)
@@ -248,6 +251,12 @@ def main():
             _lib.check(L.lpic_event_elapsed_ms(eng.ctx, 2 + 4 * k + 2 * s, 3 + 4 * k + 2 * s, _lib.C.byref(e)))
             push_ms.append(e.value)
     alive1 = sum(eng.count_alive(s) for s in range(eng.nspec))
+    if args.breakdown and world == 1:
+        bd = eng.step_profiled(dt, q, m, rev)
+        tot = sum(t for _, t in bd)
+        for name, t in bd:
+            print(f"  {name:28s} {t:9.3f} ms {100 * t / tot:5.1f}%", file=sys.stderr)
+        print(f"  {'TOTAL':28s} {tot:9.3f} ms", file=sys.stderr)
     step_ms = ms.value / args.steps
     if world > 1:
         t = torch.tensor([step_ms, float(alive0), float(alive1), float(launches)], dtype=torch.float64, device="cuda")

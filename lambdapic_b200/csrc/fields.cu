@@ -124,6 +124,10 @@ __global__ void __launch_bounds__(256) k_sync_guard(Geom g, double *__restrict__
     base[(size_t)p * g.ncell + dst] = base[(size_t)q * g.ncell + src];
 }
 
+// bit masks of the boundaries whose direction component along an axis is -1 / 0 / +1 (generated from kDir3 / kDir2)
+__constant__ const unsigned kAxisMask3[3][3] = {{0x3c03c1u, 0x3c03cu, 0x3c03c02u}, {0xccc444u, 0x3333u, 0x3330888u}, {0x1555110u, 0xccfu, 0x2aaa220u}};
+__constant__ const unsigned kAxisMask2[3][3] = {{0x51u, 0xcu, 0xa2u}, {0x34u, 0x3u, 0xc8u}, {0x0u, 0xffu, 0x0u}};
+
 // Current reduce: one thread per (attribute, patch, interior cell).  The thread walks the boundaries in the
 // reference's enum order (faces, edges, vertices), adds the neighbour's guard value and zeroes it, exactly as
 // sync_currents_3d does cell by cell (sync_fields3d.c:117-128), which fixes the summation order at edge and
@@ -139,13 +143,17 @@ __global__ void __launch_bounds__(256) k_sync_currents(Geom g, double *__restric
     const int o = c.k + g.NZ * (c.j + g.NY * c.i);
     double acc = base[(size_t)c.p * g.ncell + o];
     bool touched = false;
-    for (int b = 0; b < g.nb; b++) {
-        const int sx = dir_component(g.dim, b, 0), sy = dir_component(g.dim, b, 1), sz = dir_component(g.dim, b, 2);
-        if ((sx < 0 && !lox) || (sx > 0 && !hix) || (sy < 0 && !loy) || (sy > 0 && !hiy) || (sz < 0 && !loz) ||
-            (sz > 0 && !hiz))
-            continue;
+    // boundaries whose strip contains this cell, as a bit mask, visited in ascending (= enum) order
+    const unsigned(*am)[3] = g.dim == 3 ? kAxisMask3 : kAxisMask2;
+    unsigned todo = (am[0][1] | (lox ? am[0][0] : 0u) | (hix ? am[0][2] : 0u)) &
+                    (am[1][1] | (loy ? am[1][0] : 0u) | (hiy ? am[1][2] : 0u)) &
+                    (am[2][1] | (loz ? am[2][0] : 0u) | (hiz ? am[2][2] : 0u));
+    while (todo) {
+        const int b = __ffs(todo) - 1;
+        todo &= todo - 1;
         const i64 q = nbr[(i64)c.p * g.nb + b];
         if (q < 0) continue;
+        const int sx = dir_component(g.dim, b, 0), sy = dir_component(g.dim, b, 1), sz = dir_component(g.dim, b, 2);
         // dst[0,ng) += src[n,n+ng) for a MIN side, dst[n-ng,n) += src[-ng,0) for a MAX side
         const int qi = c.i - sx * g.nx, qj = c.j - sy * g.ny, qk = c.k - sz * g.nz;
         const size_t s = (size_t)q * g.ncell + sidx(g, qi, qj, qk);

@@ -124,21 +124,33 @@ __global__ void __launch_bounds__(T) k_lists(MigArgs a) {
     }
     __syncthreads();
     int nl = 0, nd = 0;
-    for (int base = 0; base < np; base += T) {
-        const int ip = base + tid;
-        bool isdead = false, leaves = false;
-        if (ip < np) {
-            isdead = a.dead[off + ip] != 0;
-            if (!isdead) leaves = classify(a, bx, off + ip) >= 0;
+    constexpr int IT = 4;  // consecutive slots per thread and scan step
+    for (int base = 0; base < np; base += T * IT) {
+        const int ip0 = base + tid * IT;
+        bool isdead[IT], leaves[IT];
+        int cl = 0, cd = 0;
+#pragma unroll
+        for (int j = 0; j < IT; j++) {
+            const int ip = ip0 + j;
+            isdead[j] = leaves[j] = false;
+            if (ip < np) {
+                isdead[j] = a.dead[off + ip] != 0;
+                if (!isdead[j]) leaves[j] = classify(a, bx, off + ip) >= 0;
+            }
+            cl += leaves[j];
+            cd += isdead[j];
         }
         int tot;
-        int incl = block_incl_sum(leaves ? 1 : 0, sw, tot);
-        if (leaves) a.la[off + nl + incl - 1] = ip;
+        int pl = nl + block_incl_sum(cl, sw, tot) - cl;
         nl += tot;
         __syncthreads();
-        incl = block_incl_sum(isdead ? 1 : 0, sw, tot);
-        if (isdead) a.la[off + np - 1 - (nd + incl - 1)] = ip;
+        int pd = nd + block_incl_sum(cd, sw, tot) - cd;
         nd += tot;
+#pragma unroll
+        for (int j = 0; j < IT; j++) {
+            if (leaves[j]) a.la[off + pl++] = ip0 + j;
+            if (isdead[j]) a.la[off + np - 1 - pd++] = ip0 + j;
+        }
         __syncthreads();
     }
     if (tid == 0) a.ndead[p] = nd;  // dead slots after the host grew the arrays

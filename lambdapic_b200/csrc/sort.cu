@@ -18,6 +18,7 @@
 namespace {
 
 constexpr int T = 256;         // threads per sort CTA
+constexpr int IT = 4;          // consecutive slots per thread and scan step
 constexpr int SMEM_BINS = 2048;  // histograms up to this many buckets live in shared memory
 
 __device__ __forceinline__ int warp_incl_sum(int v) {
@@ -102,6 +103,7 @@ __device__ __forceinline__ long long cell_of(double v) {
 
 __global__ void __launch_bounds__(T) k_sort_index(SortArgs a) {
     __shared__ int skey[T];
+    __shared__ int sinc[T];
     __shared__ int sw[T / 32];
     __shared__ int s_hist[SMEM_BINS];
     __shared__ int s_carry;
@@ -118,35 +120,63 @@ __global__ void __launch_bounds__(T) k_sort_index(SortArgs a) {
     __syncthreads();
     const double x0 = a.org[p], y0 = a.org[a.npatch + p], z0 = a.org[2 * a.npatch + p];
 
-    // ---- 1. keys with inheritance, histogram ------------------------------------------------------------
-    for (int base = 0; base < np; base += T) {
-        const int ip = base + tid;
-        bool valid = false;
-        int key = 0;
-        if (ip < np && !a.dead[off + ip]) {
-            valid = true;
-            long long ix = cell_of((a.x[off + ip] - x0) / a.dxb);
-            long long iy = cell_of((a.y[off + ip] - y0) / a.dyb);
-            long long iz = a.dim == 3 ? cell_of((a.z[off + ip] - z0) / a.dzb) : 0;
-            if (a.reverse_x) {
-                ix = ix < 0 ? 0 : (ix >= a.nxb ? a.nxb - 1 : ix);
-                iy = iy < 0 ? 0 : (iy >= a.nyb ? a.nyb - 1 : iy);
-                iz = iz < 0 ? 0 : (iz >= a.nzb ? a.nzb - 1 : iz);
-                key = (int)(iz + iy * a.nzb + (a.nxb - 1 - ix) * a.nyb * a.nzb);
-            } else if (ix >= 0 && ix < a.nxb && iy >= 0 && iy < a.nyb && iz >= 0 && iz < a.nzb) {
-                key = (int)(iz + iy * a.nzb + ix * a.nyb * a.nzb);
-            } else {
-                key = nbin - 1;
+    // ---- 1. keys with inheritance, histogram (IT consecutive slots per thread: one block scan per T*IT slots) ----
+    for (int base = 0; base < np; base += T * IT) {
+        const int ip0 = base + tid * IT;
+        int keys[IT];
+        bool valid[IT];
+        int lastv = -1;
+#pragma unroll
+        for (int j = 0; j < IT; j++) {
+            const int ip = ip0 + j;
+            valid[j] = false;
+            keys[j] = 0;
+            if (ip < np && !a.dead[off + ip]) {
+                valid[j] = true;
+                lastv = j;
+                long long ix = cell_of((a.x[off + ip] - x0) / a.dxb);
+                long long iy = cell_of((a.y[off + ip] - y0) / a.dyb);
+                long long iz = a.dim == 3 ? cell_of((a.z[off + ip] - z0) / a.dzb) : 0;
+                if (a.reverse_x) {
+                    ix = ix < 0 ? 0 : (ix >= a.nxb ? a.nxb - 1 : ix);
+                    iy = iy < 0 ? 0 : (iy >= a.nyb ? a.nyb - 1 : iy);
+                    iz = iz < 0 ? 0 : (iz >= a.nzb ? a.nzb - 1 : iz);
+                    keys[j] = (int)(iz + iy * a.nzb + (a.nxb - 1 - ix) * a.nyb * a.nzb);
+                } else if (ix >= 0 && ix < a.nxb && iy >= 0 && iy < a.nyb && iz >= 0 && iz < a.nzb) {
+                    keys[j] = (int)(iz + iy * a.nzb + ix * a.nyb * a.nzb);
+                } else {
+                    keys[j] = nbin - 1;
+                }
             }
         }
-        skey[tid] = key;
+        int mylast = 0;
+#pragma unroll
+        for (int j = 0; j < IT; j++)
+            if (j == lastv) mylast = keys[j];
+        skey[tid] = mylast;
         const int carry = s_carry;
-        const int last = block_incl_max(valid ? tid : -1, sw);  // syncs inside make skey visible
-        key = last >= 0 ? skey[last] : carry;
-        if (ip < np) a.pidx[off + ip] = key;
-        grouped_fetch_add(hist, key, ip < np);
+        sinc[tid] = block_incl_max(lastv >= 0 ? tid : -1, sw);  // syncs inside make skey visible
         __syncthreads();
-        if (tid == T - 1) s_carry = key;
+        const int prev = tid > 0 ? sinc[tid - 1] : -1;  // last thread before me that holds an alive slot
+        int run = prev >= 0 ? skey[prev] : carry;
+        int rk = -1, rc = 0;  // run-length compressed histogram update (sorted data: usually one run per thread)
+#pragma unroll
+        for (int j = 0; j < IT; j++) {
+            const int ip = ip0 + j;
+            if (valid[j]) run = keys[j];
+            if (ip < np) {
+                a.pidx[off + ip] = run;
+                if (run == rk) rc++;
+                else {
+                    if (rc) atomicAdd(&hist[rk], rc);
+                    rk = run;
+                    rc = 1;
+                }
+            }
+        }
+        if (rc) atomicAdd(&hist[rk], rc);
+        __syncthreads();
+        if (tid == T - 1) s_carry = run;
         __syncthreads();
     }
 
@@ -179,23 +209,39 @@ __global__ void __launch_bounds__(T) k_sort_index(SortArgs a) {
     // ---- 3. misplaced slots, ascending; per-bucket counts of them ------------------------------------------
     const i64 *bmax = a.bound_max + (size_t)p * nbin;
     int nbuf = 0;
-    for (int base = 0; base < np; base += T) {
-        const int ip = base + tid;
-        bool miss = false;
-        int key = 0;
-        if (ip < np) {
-            key = a.pidx[off + ip];
-            int lo = 0, hi = nbin - 1;  // owner = first bucket with bound_max > ip
+    for (int base = 0; base < np; base += T * IT) {
+        const int ip0 = base + tid * IT;
+        int key[IT];
+        bool miss[IT];
+        int nmiss = 0, owner = 0;
+        if (ip0 < np) {
+            int lo = 0, hi = nbin - 1;  // owner = first bucket with bound_max > ip0
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
-                if (bmax[mid] > ip) hi = mid; else lo = mid + 1;
+                if (bmax[mid] > ip0) hi = mid; else lo = mid + 1;
             }
-            miss = key != lo;
+            owner = lo;
+        }
+#pragma unroll
+        for (int j = 0; j < IT; j++) {
+            const int ip = ip0 + j;
+            miss[j] = false;
+            key[j] = 0;
+            if (ip < np) {
+                while (bmax[owner] <= ip) owner++;  // owners are non-decreasing along the slots
+                key[j] = a.pidx[off + ip];
+                miss[j] = key[j] != owner;
+                nmiss += miss[j];
+            }
         }
         int tot;
-        const int incl = block_incl_sum(miss ? 1 : 0, sw, tot);
-        if (miss) a.tgt[off + nbuf + incl - 1] = ip;
-        grouped_fetch_add(cur, key, miss);  // counts by key == counts by owner (see header comment)
+        int pos = nbuf + block_incl_sum(nmiss, sw, tot) - nmiss;
+#pragma unroll
+        for (int j = 0; j < IT; j++)
+            if (miss[j]) {
+                a.tgt[off + pos++] = ip0 + j;
+                atomicAdd(&cur[key[j]], 1);  // counts by key == counts by owner (see header comment)
+            }
         nbuf += tot;
         __syncthreads();
     }

@@ -112,6 +112,7 @@ class DeviceEngine:
         self.rank = 0
         self.patch_index = np.arange(npatch, dtype=np.int64)
         self.x0 = self.y0 = self.z0 = None
+        self.row_tile = False    # True: experimental row kernel with the E/B neighbourhood staged in shared memory
         self.slot_order = False  # True: round-1 v1 particle kernel (memory order) instead of the cell-ordered one
 
     # ---- lifetime --------------------------------------------------------------------------------------------
@@ -225,7 +226,8 @@ class DeviceEngine:
 
     def push_deposit(self, ispec, dt, q, m, write_part=False, slot_order=None):
         slot_order = self.slot_order if slot_order is None else slot_order
-        flags = (_lib.PUSH_WRITE_PART if write_part else 0) | (_lib.PUSH_SLOT_ORDER if slot_order else 0)
+        flags = ((_lib.PUSH_WRITE_PART if write_part else 0) | (_lib.PUSH_SLOT_ORDER if slot_order else 0)
+                 | (_lib.PUSH_ROW_TILE if self.row_tile else 0))
         check(self.L.lpic_push_deposit(self.ctx, ispec, float(dt), float(q), float(m), flags))
 
     def interpolate(self, ispec):
@@ -307,6 +309,38 @@ class DeviceEngine:
 
     def init_uniform(self, ispec, ppc, weight, uth, seed):
         check(self.L.lpic_species_init_uniform(self.ctx, ispec, int(ppc), float(weight), float(uth), int(seed)))
+
+    def step_profiled(self, dt, q, m, reverse_x):
+        """One step with a CUDA event after every operator; returns [(name, ms)] (bench.py --breakdown)."""
+        marks, slot = [], [3000]
+
+        def mark(name):
+            self.record_event(slot[0])
+            marks.append((name, slot[0]))
+            slot[0] += 1
+        mark("begin")
+        self.update_efield(0.5 * dt); mark("update E field")
+        self.sync_guard_fields(E_MASK); mark("sync E field")
+        self.update_bfield(0.5 * dt); mark("update B field")
+        self.sync_guard_fields(B_MASK); mark("sync B field")
+        for s in range(self.nspec):
+            self.sort(s, reverse_x[s]); mark(f"sort species {s}")
+        self.reset_currents(); mark("reset J,rho")
+        for s in range(self.nspec):
+            self.push_deposit(s, dt, q[s], m[s]); mark(f"push+deposit species {s}")
+        self.sync_currents(); mark("sync_currents")
+        for s in range(self.nspec):
+            self.sync_particles(s); mark(f"sync_particles species {s}")
+        self.update_bfield(0.5 * dt); mark("update B field")
+        self.sync_guard_fields(B_MASK); mark("sync B field")
+        self.update_efield(0.5 * dt); mark("update E field")
+        self.sync_guard_fields(E_MASK); mark("sync E field")
+        out = []
+        for (n0, s0), (n1, s1) in zip(marks[:-1], marks[1:]):
+            ms = C.c_double(0)
+            check(self.L.lpic_event_elapsed_ms(self.ctx, s0, s1, C.byref(ms)))
+            out.append((n1, ms.value))
+        return out
 
     # ---- one full step, periodic / unified-pusher case (simulation/simulation.py:937-1130) ---------------------
     def record_event(self, slot):
