@@ -303,42 +303,61 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "wall_ms_per_step": 1e3 * wall / args.steps}
 
     # ---- end to end through the public API with host buffers ---------------------------------------------------
+    eng.close()
     if not args.no_e2e and world == 1:
-        line["e2e"] = e2e_run(args, eng, wl, rev)
+        line["e2e"] = e2e_public_api(args, wl)
     elif world > 1:
         line["e2e"] = {"value": None, "unit": UNIT, "note": "measured at N=1 only in this round"}
     if not args.no_cpu_baseline and world == 1:
-        eng.close()
         line["cpu_baseline"] = cpu_reference_run(args, steps=2, warmup=1)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def e2e_run(args, eng, wl, rev):
-    """Same metric with the state starting and ending in HOST memory: every timed step uploads the full particle
-    and field state from the pinned host mirrors, runs the step, and downloads it again (what a drop-in for the
-    reference's host-array operators pays when a callback touches the state every step)."""
-    from lambdapic_b200 import _lib
-    t_alloc = time.perf_counter()
-    eng.download_all()  # also allocates the pinned mirrors
-    t_alloc = time.perf_counter() - t_alloc
-    h2d = eng.fields_host.nbytes + sum(sum(a.nbytes for a in eng.species[s].host.values()) for s in range(eng.nspec))
-    steps = max(1, min(args.steps, 3))
-    n_upd = 0
+def e2e_public_api(args, wl):
+    """Same metric through the call a user makes: ``Simulation3D(...).run(nsteps=K, callbacks=[diag])`` with the whole
+    state starting and ending in pinned HOST memory.  The timed region contains the H2D copy of all fields and
+    particles at run() entry, K full steps each followed by a device->host read of the step's energy diagnostic
+    (a `needs_host=False` callback at stage `end`), and the D2H copy of all state at run() exit."""
+    import lambdapic_b200 as lp
+    t_setup = time.perf_counter()
+    per = {k: "periodic" for k in ("xmin", "xmax", "ymin", "ymax", "zmin", "zmax")}
+    npx, npy, npz = wl.npatches
+    sim = lp.Simulation3D(nx=wl.cells[0], ny=wl.cells[1], nz=wl.cells[2], dx=wl.d, dy=wl.d, dz=wl.d, npatch_x=npx, npatch_y=npy,
+                          npatch_z=npz, dt_cfl=wl.dt_cfl, boundary_conditions=per, random_seed=wl.seed, store_part_fields=False)
+    sim.add_species([lp.Electron(density=wl.density, ppc=wl.ppc[0]), lp.Proton(density=wl.density, ppc=wl.ppc[1])])
+    sim.initialize()
+    rng = np.random.default_rng(wl.seed + 1)
+    for p in sim.patches:  # thermal momenta on the host mirrors (what SetTemperature does at stage `init`)
+        for isp, part in enumerate(p.particles):
+            for a in ("ux", "uy", "uz"):
+                getattr(part, a)[:] = rng.normal(0.0, wl.uth[isp], part.npart)
+            part.inv_gamma[:] = 1.0 / np.sqrt(1 + part.ux**2 + part.uy**2 + part.uz**2)
+    t_setup = time.perf_counter() - t_setup
+    hist = []
+
+    @lp.callback("end", needs_host=False)
+    def diag(sim):
+        hist.append(sim.energies())
+    steps = max(1, args.steps)
+    before = dict(sim.bridge.stats)
+    n0 = sum(int((~pt.is_dead).sum()) for p in sim.patches for pt in p.particles)
     t0 = time.perf_counter()
-    for _ in range(steps):
-        eng.upload_all()
-        n_upd += sum(eng.count_alive(s) for s in range(eng.nspec))
-        _, mig = eng.step(wl.dt, wl.q, wl.m, rev)
-        if any(r["moved"] for r in mig):
-            pass  # arena re-laid out: mirrors are re-created by download_all below
-        eng.download_all()
+    sim.run(nsteps=steps, callbacks=[diag])
     dt = time.perf_counter() - t0
-    d2h = eng.fields_host.nbytes + sum(sum(a.nbytes for a in eng.species[s].host.values()) for s in range(eng.nspec))
-    return {"value": n_upd / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "steps": steps, "ms_per_step": 1e3 * dt / steps, "pinned_alloc_s": t_alloc,
-            "mode": "per step: H2D of all fields+particles from pinned host mirrors, full PIC step, D2H of all state"}
+    n1 = sum(int((~pt.is_dead).sum()) for p in sim.patches for pt in p.particles)
+    st = sim.bridge.stats
+    tot = [sum(h.values()) for h in hist]
+    out = {"value": 0.5 * (n0 + n1) * steps / dt, "unit": UNIT,
+           "h2d_bytes_per_step": int((st["h2d_bytes"] - before["h2d_bytes"]) / steps),
+           "d2h_bytes_per_step": int((st["d2h_bytes"] - before["d2h_bytes"]) / steps + 8 * len(hist[0])),
+           "steps": steps, "ms_per_step": 1e3 * dt / steps, "setup_s": t_setup,
+           "energy_drift_rel": abs(tot[-1] - tot[0]) / tot[0],
+           "mode": "Simulation3D.run(nsteps=K): H2D of all state from pinned host mirrors at entry, K steps with a per-step "
+                   "D2H energy diagnostic, D2H of all state at exit"}
+    sim.bridge.close()
+    return out
 
 
 if __name__ == "__main__":

@@ -25,7 +25,7 @@ def _interval_triggered(sim, interval) -> bool:
     return True
 
 
-def callback(stage: Optional[str] = None, interval=1) -> Callable:
+def callback(stage: Optional[str] = None, interval=1, needs_host: bool = True) -> Callable:
     def decorator(func: Callable) -> Callable:
         _validate_interval(interval)
 
@@ -39,6 +39,7 @@ def callback(stage: Optional[str] = None, interval=1) -> Callable:
             return ret
         wrapper.stage = stage
         wrapper.interval = interval
+        wrapper.needs_host = needs_host  # False: uses only device-side diagnostics, mirrors are not synced for it
         return wrapper
     return decorator
 
@@ -46,6 +47,7 @@ def callback(stage: Optional[str] = None, interval=1) -> Callable:
 class Callback:
     interval = 1
     stage = None
+    needs_host = True
 
     def __call__(self, sim):
         _validate_interval(self.interval)

@@ -15,11 +15,15 @@ struct CellIdx {
     int p, i, j, k;
 };
 
+// t = global interior-cell number; all arithmetic after the first (block-uniform) division is 32-bit
 __device__ __forceinline__ bool interior_cell(const Geom &g, i64 t, CellIdx &c) {
     const int per = g.nx * g.ny * g.nz;
     if (t >= (i64)per * g.npatch) return false;
-    c.p = (int)(t / per);
-    int r = (int)(t - (i64)c.p * per);
+    const i64 t0 = t - threadIdx.x;  // block-uniform: one 64-bit division per warp instead of a divergent one per lane
+    const int p0 = (int)(t0 / per);
+    int r = (int)(t0 - (i64)p0 * per) + (int)threadIdx.x;
+    c.p = p0;
+    if (r >= per) { c.p += r / per; r %= per; }
     c.k = r % g.nz;
     r /= g.nz;
     c.j = r % g.ny;

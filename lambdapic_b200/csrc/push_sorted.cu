@@ -208,7 +208,16 @@ __device__ __forceinline__ void push_body(const Geom &g, double *__restrict__ F,
     const int ix0 = (int)floor(X0 + 0.5), iy0 = (int)floor(Y0 + 0.5), iz0 = (int)floor(Z0 + 0.5);
     const int ix1 = (int)floor(X1 + 0.5), iy1 = (int)floor(Y1 + 0.5), iz1 = (int)floor(Z1 + 0.5);
     const bool fast = active && ix1 == ix0 && iy1 == iy0 && iz1 == iz0;
-    if (active && !fast) cross[off + atomicAdd(&ncross[p], 1)] = local;  // general routine, second kernel
+    {   // particles that change cell go to the general routine (second kernel); one warp-aggregated append keeps the
+        // list in (roughly) cell order, so that kernel's neighbouring lanes hit neighbouring cells
+        const unsigned cm = __ballot_sync(0xffffffffu, active && !fast);
+        if (cm) {
+            int basepos = 0;
+            if (lane == __ffs(cm) - 1) basepos = atomicAdd(&ncross[p], __popc(cm));
+            basepos = __shfl_sync(0xffffffffu, basepos, __ffs(cm) - 1);
+            if (active && !fast) cross[off + basepos + __popc(cm & ((1u << lane) - 1u))] = local;
+        }
+    }
     // segments = runs of consecutive lanes that start in the same cell
     const int bx0 = wrap_base(ix0, g.NX), by0 = wrap_base(iy0, g.NY), bz0 = wrap_base(iz0, g.NZ);
     const int key = fast ? bz0 + g.NZ * (by0 + g.NY * bx0) : -1 - lane;

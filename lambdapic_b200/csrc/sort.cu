@@ -101,6 +101,11 @@ __device__ __forceinline__ long long cell_of(double v) {
     return (long long)f;
 }
 
+// floor(v / d) for a single bucket [0, d): for doubles v < d  <=>  fl(v / d) < 1 (the quotient of two doubles with
+// v < d is at most 1 - 2^-53, which is representable), so the division of the reference can be replaced by
+// comparisons without changing any result.  NaN falls out of range, as (npy_intp)floor(NaN) does.
+__device__ __forceinline__ long long one_bucket(double v, double d) { return v >= 0.0 ? (v < d ? 0 : 1) : -1; }
+
 __global__ void __launch_bounds__(T) k_sort_index(SortArgs a) {
     __shared__ int skey[T];
     __shared__ int sinc[T];
@@ -135,8 +140,8 @@ __global__ void __launch_bounds__(T) k_sort_index(SortArgs a) {
                 valid[j] = true;
                 lastv = j;
                 long long ix = cell_of((a.x[off + ip] - x0) / a.dxb);
-                long long iy = cell_of((a.y[off + ip] - y0) / a.dyb);
-                long long iz = a.dim == 3 ? cell_of((a.z[off + ip] - z0) / a.dzb) : 0;
+                long long iy = a.nyb == 1 ? one_bucket(a.y[off + ip] - y0, a.dyb) : cell_of((a.y[off + ip] - y0) / a.dyb);
+                long long iz = a.dim != 3 ? 0 : (a.nzb == 1 ? one_bucket(a.z[off + ip] - z0, a.dzb) : cell_of((a.z[off + ip] - z0) / a.dzb));
                 if (a.reverse_x) {
                     ix = ix < 0 ? 0 : (ix >= a.nxb ? a.nxb - 1 : ix);
                     iy = iy < 0 ? 0 : (iy >= a.nyb ? a.nyb - 1 : iy);
@@ -302,6 +307,35 @@ __global__ void __launch_bounds__(256) k_sort_scatter(V *__restrict__ attr, cons
     attr[off[p] + tgt[off[p] + i]] = buf[off[p] + i];
 }
 
+struct MoveArgs {
+    double *a[LPIC_NPATTR];
+    int n;
+    u8 *dead;
+};
+// all attributes in one launch (blockIdx.y = attribute, last = is_dead); staging buffer compact: [attr][sum of nbuf]
+__global__ void __launch_bounds__(256) k_sort_gather_all(MoveArgs A, double *__restrict__ buf, i64 cap, const int *__restrict__ src_of,
+                                                         const i64 *__restrict__ off, const i64 *__restrict__ nbuf,
+                                                         const i64 *__restrict__ poff, int blocks_per_patch) {
+    const int p = blockIdx.x / blocks_per_patch;
+    const i64 i = (i64)(blockIdx.x - p * blocks_per_patch) * blockDim.x + threadIdx.x;
+    if (i >= nbuf[p]) return;
+    const i64 src = off[p] + src_of[off[p] + i], dst = poff[p] + i;
+    const int y = blockIdx.y;
+    if (y < A.n) buf[(size_t)y * cap + dst] = A.a[y][src];
+    else ((u8 *)(buf + (size_t)A.n * cap))[dst] = A.dead[src];
+}
+__global__ void __launch_bounds__(256) k_sort_scatter_all(MoveArgs A, const double *__restrict__ buf, i64 cap, const int *__restrict__ tgt,
+                                                          const i64 *__restrict__ off, const i64 *__restrict__ nbuf,
+                                                          const i64 *__restrict__ poff, int blocks_per_patch) {
+    const int p = blockIdx.x / blocks_per_patch;
+    const i64 i = (i64)(blockIdx.x - p * blocks_per_patch) * blockDim.x + threadIdx.x;
+    if (i >= nbuf[p]) return;
+    const i64 dst = off[p] + tgt[off[p] + i], src = poff[p] + i;
+    const int y = blockIdx.y;
+    if (y < A.n) A.a[y][dst] = buf[(size_t)y * cap + src];
+    else A.dead[dst] = ((const u8 *)(buf + (size_t)A.n * cap))[src];
+}
+
 __global__ void k_widen(const int *__restrict__ src, i64 *__restrict__ dst, i64 n) {
     const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) dst[t] = src[t];
@@ -362,6 +396,24 @@ extern "C" int lpic_sort(lpic_ctx *c, int ispec, int reverse_x, int64_t nxb, int
     if (total > 0) {
         const int bpp = (int)div_up(mx, 256);
         const unsigned grid = (unsigned)((i64)bpp * n);
+        MoveArgs A;
+        A.n = 0;
+        for (int at = 0; at < LPIC_NPATTR; at++)
+            if (sp.attr[at]) A.a[A.n++] = sp.attr[at];
+        A.dead = sp.dead;
+        if ((i64)(A.n + 1) * total <= c->scr_cap) {
+            // one gather and one scatter launch for all attributes through a compact staging buffer
+            std::vector<i64> poff(n);
+            i64 run = 0;
+            for (i64 p = 0; p < n; p++) { poff[p] = run; run += h_nbuf[p]; }
+            i64 *d_poff = d_nbuf + n;
+            CUDA_TRY(cudaMemcpyAsync(d_poff, poff.data(), sizeof(i64) * n, cudaMemcpyHostToDevice, c->stream));
+            dim3 g2(grid, A.n + 1);
+            k_sort_gather_all<<<g2, 256, 0, c->stream>>>(A, c->scr_buf, total, c->scr_b, sp.d_off, d_nbuf, d_poff, bpp);
+            k_sort_scatter_all<<<g2, 256, 0, c->stream>>>(A, c->scr_buf, total, c->scr_a, sp.d_off, d_nbuf, d_poff, bpp);
+            LAUNCHED(2);
+            KERNEL_CHECK();
+        } else {
         for (int at = 0; at < LPIC_NPATTR; at++) {
             if (!sp.attr[at]) continue;
             k_sort_gather<double><<<grid, 256, 0, c->stream>>>(sp.attr[at], c->scr_buf, c->scr_b, sp.d_off, d_nbuf, bpp);
@@ -374,6 +426,7 @@ extern "C" int lpic_sort(lpic_ctx *c, int ispec, int reverse_x, int64_t nxb, int
         k_sort_scatter<u8><<<grid, 256, 0, c->stream>>>(sp.dead, (const u8 *)c->scr_buf, c->scr_a, sp.d_off, d_nbuf, bpp);
         LAUNCHED(1);
         KERNEL_CHECK();
+        }
     }
     st.valid = true;
     return 0;

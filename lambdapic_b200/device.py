@@ -74,16 +74,26 @@ class DeviceBridge:
         parts = [p.particles[s] for p in ps]
         npart = np.array([pt.npart for pt in parts], dtype=np.int64)
         created = np.array([pt._npart_created for pt in parts], dtype=np.int64)
-        old = [{a: np.array(getattr(pt, a)) for a in PART_ATTRS} | {"is_dead": np.array(pt.is_dead, dtype=bool)} for pt in parts]
+        old_mirror, eng.species[s] = eng.species[s], None  # host arrays may be views into it: free it after the copy
         m = eng.alloc_species(s, npart, slack=self.slack, min_extra=64, with_part=self.with_part, npart_created=created)
         for ip, pt in enumerate(parts):
+            old = {a: getattr(pt, a) for a in PART_ATTRS}   # references, no copies: one patch at a time
+            old_dead = pt.is_dead
             self._seat(pt, m, ip)
             for a in m.attrs:
-                getattr(pt, a)[...] = old[ip][a]
-            pt.is_dead[...] = old[ip]["is_dead"]
+                getattr(pt, a)[...] = old[a]
+            pt.is_dead[...] = old_dead
             if not self.with_part:
-                for a in PART_ATTRS[8:14]:
-                    setattr(pt, a, old[ip][a])
+                self._host_only_part_fields(pt)
+        if old_mirror is not None:
+            old_mirror.free()
+
+    @staticmethod
+    def _host_only_part_fields(pt):
+        """store_part_fields=False: ex_part..bz_part are not resident on the device; the host objects expose
+        read-only zero arrays of the right length (no memory behind them)."""
+        for a in PART_ATTRS[8:14]:
+            setattr(pt, a, np.broadcast_to(0.0, (pt.npart,)))
 
     def _seat(self, pt, m, ip):
         for a in m.attrs:
@@ -129,8 +139,7 @@ class DeviceBridge:
                         pt.extended = True
                     self._seat(pt, m, ip)
                     if not self.with_part:
-                        for a in PART_ATTRS[8:14]:
-                            setattr(pt, a, np.zeros(pt.npart))
+                        self._host_only_part_fields(pt)
                 pt._npart_created = int(eng.npart_created[s][ip])
         eng.download_fields(ALL_FIELDS)
         self.stats["downloads"] += 1

@@ -274,6 +274,19 @@ class Simulation:
         self._current_sync_handle = None
         self.current_synced = True
 
+    def energies(self):
+        """Field and kinetic energies [J] from device-side reductions (no host mirror traffic): dict with
+        'electric', 'magnetic' and one entry per species name."""
+        eps0, mu0 = 8.8541878188e-12, 1.25663706127e-06
+        with self.bridge.coherent():
+            eng = self.bridge.engine
+            e2, b2 = eng.field_energy_sums()
+            dV = self.dx * self.dy * (self.dz if self.dimension == 3 else 1.0)
+            out = {"electric": 0.5 * eps0 * e2 * dV, "magnetic": 0.5 * b2 / mu0 * dV}
+            for i, sp in enumerate(self.species):
+                out[sp.name] = eng.kinetic_sum(i) * sp.m * C_LIGHT**2
+        return out
+
     def maxwell_stage(self):
         """simulation.py:743-761: one full field advance without particles."""
         for upd, attrs in ((self.maxwell.update_efield, ["ex", "ey", "ez"]), (self.maxwell.update_bfield, ["bx", "by", "bz"])):
@@ -316,7 +329,10 @@ class Simulation:
         if not cbs.has_triggered_callbacks(stage):
             return
         br = self.bridge
-        was_resident = br.resident
+        # callbacks that only use device-side diagnostics (sim.energies()) declare `needs_host = False` and run
+        # without the host mirrors being refreshed (mirror elision)
+        triggered = [cb for cb in cbs.stage_callbacks[stage] if _interval_triggered(self, getattr(cb, "interval", 1))]
+        was_resident = br.resident and any(getattr(cb, "needs_host", True) for cb in triggered)
         if was_resident:
             br.download()
             br.resident = False

@@ -110,3 +110,27 @@ def test_energy_history_1000_steps_config0():
     drift = abs(got.sum(axis=1)[-1] - got.sum(axis=1)[0]) / got.sum(axis=1)[0]
     assert drift < 0.01  # the reference's own bar (tests/test_numerical_heating.py:103-133)
     sim.bridge.close()
+
+
+def test_device_side_diagnostics_skip_mirror_sync(golden2d):
+    """A callback declared needs_host=False reads sim.energies() (device reductions): no download/upload happens for it,
+    and the numbers equal the host-side sums."""
+    from lambdapic_b200 import callback
+    sim = make_sim(2)
+    seen = []
+
+    @callback("end", needs_host=False)
+    def diag(sim):
+        seen.append(sim.energies())
+    sim.initialize()
+    before = dict(sim.bridge.stats)
+    sim.run(nsteps=3, callbacks=[_golden_callbacks(True), diag])
+    st = sim.bridge.stats
+    assert st["downloads"] - before["downloads"] == 1 and st["uploads"] - before["uploads"] == 1, (before, st)  # run entry / exit only
+    assert len(seen) == 3
+    eps0 = 8.8541878188e-12
+    e2 = sum(float((p.fields.ex[:p.fields.nx, :p.fields.ny]**2 + p.fields.ey[:p.fields.nx, :p.fields.ny]**2
+                    + p.fields.ez[:p.fields.nx, :p.fields.ny]**2).sum()) for p in sim.patches)
+    assert abs(seen[-1]["electric"] - 0.5 * eps0 * e2 * sim.dx * sim.dy) <= 1e-12 * seen[-1]["electric"]
+    assert set(seen[-1]) == {"electric", "magnetic", "electron", "proton"}
+    sim.bridge.close()
