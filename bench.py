@@ -282,13 +282,14 @@ def main():
     bytes_launch = 121.0 * n_local + (48.0 + 64.0) * cells_local
     avg_push_ms = float(np.mean(push_ms))
     achieved = bytes_launch / (avg_push_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_particles<3,FUSED> (gather+Boris+Esirkepov)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "lpic_push_deposit = k_cell_perm + k_push_sorted<3> (gather+Boris+Esirkepov, cell-ordered, warp-cooperative) + k_deposit_list" if not args.slot_order else "k_particles<3,FUSED> (slot order)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6.65 TB/s",
                 "avg_launch_ms": avg_push_ms, "algorithmic_bytes_per_launch": bytes_launch,
                 "share_of_step": eng.nspec * avg_push_ms / (ms.value / args.steps)}
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        roofline["traffic"] = prof.get("k_particles_bytes_per_launch_at_bench_size")
+        roofline["traffic"] = prof.get("bytes_per_particle") * n_local if prof.get("bytes_per_particle") else None
+        roofline["traffic_source"] = prof.get("source")
     except Exception:
         pass
 
