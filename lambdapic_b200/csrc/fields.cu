@@ -107,10 +107,17 @@ struct AttrList {
 };
 __global__ void __launch_bounds__(256) k_sync_guard(Geom g, double *__restrict__ F, const i64 *__restrict__ nbr,
                                                     AttrList attrs) {
+    // direction -> boundary table in shared memory: lanes of a warp look up different entries, which would serialise
+    // in the constant cache
+    __shared__ signed char lut[27];
+    if (threadIdx.x < 27) lut[threadIdx.x] = g.dim == 3 ? kLut3[threadIdx.x] : (threadIdx.x < 9 ? kLut2[threadIdx.x] : -1);
+    __syncthreads();
     const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (i64)g.npatch * g.ncell) return;
-    const int p = (int)(t / g.ncell);
-    int r = (int)(t - (i64)p * g.ncell);
+    const i64 t0 = t - threadIdx.x;  // block-uniform 64-bit division, 32-bit arithmetic per lane
+    int p = (int)(t0 / g.ncell);
+    int r = (int)(t0 - (i64)p * g.ncell) + (int)threadIdx.x;
+    if (r >= g.ncell) { p += r / g.ncell; r %= g.ncell; }
     const int sk = r % g.NZ;
     r /= g.NZ;
     const int sj = r % g.NY, si = r / g.NY;
@@ -118,7 +125,7 @@ __global__ void __launch_bounds__(256) k_sync_guard(Geom g, double *__restrict__
     const int sx = li < 0 ? -1 : (li >= g.nx ? 1 : 0), sy = lj < 0 ? -1 : (lj >= g.ny ? 1 : 0),
               sz = lk < 0 ? -1 : (lk >= g.nz ? 1 : 0);
     if (sx == 0 && sy == 0 && sz == 0) return;
-    const int b = dir_lookup(g.dim, sx, sy, sz);
+    const int b = lut[(sx + 1) + 3 * (sy + 1) + (g.dim == 3 ? 9 * (sz + 1) : 0)];
     const i64 q = nbr[(i64)p * g.nb + b];
     if (q < 0) return;
     const int qi = li - sx * g.nx, qj = lj - sy * g.ny, qk = lk - sz * g.nz;  // interior of the neighbour
@@ -135,8 +142,16 @@ __constant__ const unsigned kAxisMask2[3][3] = {{0x51u, 0xcu, 0xa2u}, {0x34u, 0x
 // Current reduce: one thread per (attribute, patch, interior cell).  The thread walks the boundaries in the
 // reference's enum order (faces, edges, vertices), adds the neighbour's guard value and zeroes it, exactly as
 // sync_currents_3d does cell by cell (sync_fields3d.c:117-128), which fixes the summation order at edge and
-// corner cells.  Each source guard cell has a single consumer, so zeroing it here is race-free.
+// corner cells.  The consumed guard cells are zeroed by a second streaming kernel (k_zero_consumed_guards): mixing the
+// scattered zero stores with the dependent neighbour loads in one kernel made every load wait ~14k cycles (ncu:
+// long_scoreboard 269 cycles per issue at 2 % DRAM utilisation).
 __global__ void __launch_bounds__(256) k_sync_currents(Geom g, double *__restrict__ F, const i64 *__restrict__ nbr) {
+    __shared__ signed char sdir[26][3];  // per-lane lookups by boundary id: shared memory, not the constant cache
+    if (threadIdx.x < 26 * 3) {
+        const int b = threadIdx.x / 3, ax = threadIdx.x - 3 * b;
+        sdir[b][ax] = b < g.nb ? (g.dim == 3 ? kDir3[b][ax] : kDir2[b][ax]) : 0;
+    }
+    __syncthreads();
     CellIdx c;
     if (!interior_cell(g, (i64)blockIdx.x * blockDim.x + threadIdx.x, c)) return;
     const bool lox = c.i < g.ng, hix = c.i >= g.nx - g.ng;
@@ -157,15 +172,40 @@ __global__ void __launch_bounds__(256) k_sync_currents(Geom g, double *__restric
         todo &= todo - 1;
         const i64 q = nbr[(i64)c.p * g.nb + b];
         if (q < 0) continue;
-        const int sx = dir_component(g.dim, b, 0), sy = dir_component(g.dim, b, 1), sz = dir_component(g.dim, b, 2);
+        const int sx = sdir[b][0], sy = sdir[b][1], sz = sdir[b][2];
         // dst[0,ng) += src[n,n+ng) for a MIN side, dst[n-ng,n) += src[-ng,0) for a MAX side
         const int qi = c.i - sx * g.nx, qj = c.j - sy * g.ny, qk = c.k - sz * g.nz;
         const size_t s = (size_t)q * g.ncell + sidx(g, qi, qj, qk);
         acc = __dadd_rn(acc, base[s]);
-        base[s] = 0.0;
         touched = true;
     }
     if (touched) base[(size_t)c.p * g.ncell + o] = acc;
+}
+
+// zero every guard cell whose neighbour in that direction exists (that neighbour has just reduced it)
+__global__ void __launch_bounds__(256) k_zero_consumed_guards(Geom g, double *__restrict__ F, const i64 *__restrict__ nbr) {
+    __shared__ signed char lut[27];
+    if (threadIdx.x < 27) lut[threadIdx.x] = g.dim == 3 ? kLut3[threadIdx.x] : (threadIdx.x < 9 ? kLut2[threadIdx.x] : -1);
+    __syncthreads();
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (i64)g.npatch * g.ncell) return;
+    const i64 t0 = t - threadIdx.x;
+    int p = (int)(t0 / g.ncell);
+    int r = (int)(t0 - (i64)p * g.ncell) + (int)threadIdx.x;
+    if (r >= g.ncell) { p += r / g.ncell; r %= g.ncell; }
+    const int cell = r;
+    const int sk = r % g.NZ;
+    r /= g.NZ;
+    const int sj = r % g.NY, si = r / g.NY;
+    const int li = logical(si, g.nx, g.ng), lj = logical(sj, g.ny, g.ng), lk = logical(sk, g.nz, g.ngz);
+    const int sx = li < 0 ? -1 : (li >= g.nx ? 1 : 0), sy = lj < 0 ? -1 : (lj >= g.ny ? 1 : 0),
+              sz = lk < 0 ? -1 : (lk >= g.nz ? 1 : 0);
+    if (sx == 0 && sy == 0 && sz == 0) return;
+    const int b = lut[(sx + 1) + 3 * (sy + 1) + (g.dim == 3 ? 9 * (sz + 1) : 0)];
+    if (nbr[(i64)p * g.nb + b] < 0) return;
+    const size_t stride = (size_t)g.npatch * g.ncell;
+    double *base = F + (size_t)LPIC_JX * stride + (size_t)p * g.ncell + cell;
+    base[0] = 0.0; base[stride] = 0.0; base[2 * stride] = 0.0; base[3 * stride] = 0.0;
 }
 
 __global__ void __launch_bounds__(256) k_field_energy(Geom g, const double *__restrict__ F, double *__restrict__ out) {
@@ -238,7 +278,8 @@ extern "C" int lpic_sync_currents(lpic_ctx *c) {
     const Geom &g = c->g;
     dim3 grid(div_up((i64)g.npatch * g.nx * g.ny * g.nz, 256), 4);
     k_sync_currents<<<grid, 256, 0, c->stream>>>(g, c->fields, c->d_nbr);
-    LAUNCHED(1);
+    k_zero_consumed_guards<<<div_up((i64)g.npatch * g.ncell, 256), 256, 0, c->stream>>>(g, c->fields, c->d_nbr);
+    LAUNCHED(2);
     KERNEL_CHECK();
     return 0;
 }

@@ -94,18 +94,9 @@ struct SortArgs {
     i64 *nbuf;                              // (npatch)
 };
 
-__device__ __forceinline__ long long cell_of(double v) {
-    const double f = floor(v);
-    // C's (npy_intp)floor(NaN/inf) yields INT64_MIN on x86-64; keep such particles out of range
-    if (!(f >= -9.0e18 && f <= 9.0e18)) return LLONG_MIN / 2;
-    return (long long)f;
-}
-
-// floor(v / d) for a single bucket [0, d): for doubles v < d  <=>  fl(v / d) < 1 (the quotient of two doubles with
-// v < d is at most 1 - 2^-53, which is representable), so the division of the reference can be replaced by
-// comparisons without changing any result.  NaN falls out of range, as (npy_intp)floor(NaN) does.
-__device__ __forceinline__ long long one_bucket(double v, double d) { return v >= 0.0 ? (v < d ? 0 : 1) : -1; }
-
+// Single-bucket axes (ny_buckets = nz_buckets = 1, the default): floor(v / d) is 0 exactly when 0 <= v < d -- for
+// doubles v < d the rounded quotient is at most 1 - 2^-53 < 1 -- so the reference's division is replaced by two
+// comparisons there without changing any result.
 __global__ void __launch_bounds__(T) k_sort_index(SortArgs a) {
     __shared__ int skey[T];
     __shared__ int sinc[T];
@@ -139,16 +130,21 @@ __global__ void __launch_bounds__(T) k_sort_index(SortArgs a) {
             if (ip < np && !a.dead[off + ip]) {
                 valid[j] = true;
                 lastv = j;
-                long long ix = cell_of((a.x[off + ip] - x0) / a.dxb);
-                long long iy = a.nyb == 1 ? one_bucket(a.y[off + ip] - y0, a.dyb) : cell_of((a.y[off + ip] - y0) / a.dyb);
-                long long iz = a.dim != 3 ? 0 : (a.nzb == 1 ? one_bucket(a.z[off + ip] - z0, a.dzb) : cell_of((a.z[off + ip] - z0) / a.dzb));
+                // bucket coordinates as doubles (floor of the reference's quotient); NaN compares false everywhere and
+                // ends up out of range / clamped to 0, like (npy_intp)floor(NaN) = INT64_MIN does on the host
+                const double fx = floor((a.x[off + ip] - x0) / a.dxb);
+                const double vy = a.y[off + ip] - y0, vz = a.dim == 3 ? a.z[off + ip] - z0 : 0.0;
+                const double fy = a.nyb == 1 ? (vy >= 0.0 ? (vy < a.dyb ? 0.0 : 1.0) : -1.0) : floor(vy / a.dyb);
+                const double fz = a.dim != 3 ? 0.0 : (a.nzb == 1 ? (vz >= 0.0 ? (vz < a.dzb ? 0.0 : 1.0) : -1.0) : floor(vz / a.dzb));
+                const bool inx = fx >= 0.0 && fx < (double)a.nxb, iny = fy >= 0.0 && fy < (double)a.nyb,
+                           inz = fz >= 0.0 && fz < (double)a.nzb;
                 if (a.reverse_x) {
-                    ix = ix < 0 ? 0 : (ix >= a.nxb ? a.nxb - 1 : ix);
-                    iy = iy < 0 ? 0 : (iy >= a.nyb ? a.nyb - 1 : iy);
-                    iz = iz < 0 ? 0 : (iz >= a.nzb ? a.nzb - 1 : iz);
-                    keys[j] = (int)(iz + iy * a.nzb + (a.nxb - 1 - ix) * a.nyb * a.nzb);
-                } else if (ix >= 0 && ix < a.nxb && iy >= 0 && iy < a.nyb && iz >= 0 && iz < a.nzb) {
-                    keys[j] = (int)(iz + iy * a.nzb + ix * a.nyb * a.nzb);
+                    const int ix = inx ? (int)fx : (fx >= (double)a.nxb ? a.nxb - 1 : 0);
+                    const int iy = iny ? (int)fy : (fy >= (double)a.nyb ? a.nyb - 1 : 0);
+                    const int iz = inz ? (int)fz : (fz >= (double)a.nzb ? a.nzb - 1 : 0);
+                    keys[j] = iz + iy * a.nzb + (a.nxb - 1 - ix) * a.nyb * a.nzb;
+                } else if (inx && iny && inz) {
+                    keys[j] = (int)fz + (int)fy * a.nzb + (int)fx * a.nyb * a.nzb;
                 } else {
                     keys[j] = nbin - 1;
                 }
