@@ -14,6 +14,7 @@
 //   3. k_deposit_list ... and deposited by the general 125-point routine, one thread each.
 // Shared-memory fp64 atomics are a CAS loop on sm_100a (ATOMS.CAST.SPIN.64), which is why the reduction happens in
 // registers and the accumulation uses native REDG.E.ADD.F64 in L2.
+#include <stdlib.h>
 #include <algorithm>
 #include "lpic_common.cuh"
 #include "particle_math.cuh"
@@ -36,6 +37,9 @@ __device__ __forceinline__ int warp_incl_sum(int v) {
 
 struct PermArgs {
     const double *x, *y, *z;
+    const double *ux, *uy, *uz, *ig;  // predict != 0: order by the cell of x + v dt/2 (where the particle gathers AND where
+    double cdt;                       // its deposit starts: x_end - v_new dt/2 == x + v_old dt/2), padded by one cell per side
+    int predict;
     const u8 *dead;
     const i64 *off, *npart;
     const double *x0, *y0, *z0;
@@ -49,6 +53,12 @@ struct PermArgs {
 __device__ __forceinline__ int node_of(double x, double x0, double d, int n) {
     const int i = (int)floor((x - x0) / d + 0.5);
     return i < 0 ? 0 : (i >= n ? n - 1 : i);
+}
+
+// nearest node clamped to [-1, n], shifted by one: a particle may sit up to half a cell outside its patch box
+__device__ __forceinline__ int node_pad(double x, double x0, double d, int n) {
+    const int i = (int)floor((x - x0) / d + 0.5);
+    return (i < -1 ? -1 : (i > n ? n : i)) + 1;
 }
 
 __global__ void __launch_bounds__(PT) k_cell_perm(PermArgs a) {
@@ -65,6 +75,12 @@ __global__ void __launch_bounds__(PT) k_cell_perm(PermArgs a) {
         if (a.dead[off + ip]) return -1;
         const double x = a.x[off + ip], y = a.y[off + ip], z = a.z[off + ip];
         if (isnan(x) || isnan(y) || isnan(z)) return -1;
+        if (a.predict) {
+            const double h = a.cdt * a.ig[off + ip];
+            const int ix = node_pad(x + h * a.ux[off + ip], x0, a.dx, a.nx), iy = node_pad(y + h * a.uy[off + ip], y0, a.dy, a.ny),
+                      iz = node_pad(z + h * a.uz[off + ip], z0, a.dz, a.nz);
+            return iz + a.kz * (iy + a.ky * ix);
+        }
         const int ix = node_of(x, x0, a.dx, a.nx), iy = a.ky > 1 ? node_of(y, y0, a.dy, a.ny) : 0,
                   iz = a.kz > 1 ? node_of(z, z0, a.dz, a.nz) : 0;
         return iz + a.kz * (iy + a.ky * ix);
@@ -220,9 +236,14 @@ __device__ __forceinline__ void push_body(const Geom &g, double *__restrict__ F,
     }
     // segments = runs of consecutive lanes that start in the same cell
     const int bx0 = wrap_base(ix0, g.NX), by0 = wrap_base(iy0, g.NY), bz0 = wrap_base(iz0, g.NZ);
-    const int key = fast ? bz0 + g.NZ * (by0 + g.NY * bx0) : -1 - lane;
-    const int prev = __shfl_up_sync(0xffffffffu, key, 1);
-    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
+    // Lanes outside the fast path add zeros, so they must not split a run: a segment starts at lane 0 and at every
+    // fast lane whose start cell differs from the previous FAST lane's.
+    const int key = bz0 + g.NZ * (by0 + g.NY * bx0);
+    const unsigned fm = __ballot_sync(0xffffffffu, fast);
+    const unsigned before = fm & ((1u << lane) - 1u);
+    const int pf = before ? 31 - __clz(before) : -1;
+    const int pkey = __shfl_sync(0xffffffffu, key, pf < 0 ? 0 : pf);
+    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || (fast && (pf < 0 || key != pkey)));
     if (!__any_sync(0xffffffffu, fast)) return;
     double S0x[3], S0y[3], S0z[3], DSx[3], DSy[3], DSz[3];
     shape3(ix0 - X0, S0x); shape3(iy0 - Y0, S0y); shape3(iz0 - Z0, S0z);
@@ -400,10 +421,19 @@ int lpic_push_deposit_sorted(lpic_ctx *c, int ispec, double dt, double q, double
     PermArgs a;
     a.x = sp.attr[LPIC_P_X]; a.y = sp.attr[LPIC_P_Y]; a.z = sp.attr[LPIC_P_Z]; a.dead = sp.dead;
     a.off = sp.d_off; a.npart = sp.d_npart; a.x0 = c->d_x0; a.y0 = c->d_y0; a.z0 = c->d_z0;
-    a.nx = g.nx; a.ny = g.ny; a.nz = g.nz; a.kx = g.nx; a.ky = g.ny; a.kz = g.nz;
-    if ((i64)a.kx * a.ky * a.kz > KEY_LIMIT) a.kz = 1;
-    if ((i64)a.kx * a.ky * a.kz > KEY_LIMIT) a.ky = 1;
-    if ((i64)a.kx * a.ky * a.kz > KEY_LIMIT) return 1;
+    a.ux = sp.attr[LPIC_P_UX]; a.uy = sp.attr[LPIC_P_UY]; a.uz = sp.attr[LPIC_P_UZ]; a.ig = sp.attr[LPIC_P_INV_GAMMA];
+    a.cdt = LPIC_C_LIGHT * 0.5 * dt;
+    a.nx = g.nx; a.ny = g.ny; a.nz = g.nz;
+    static const bool no_predict = getenv("LPIC_PERM_CURRENT_CELL") != nullptr;  // tuning knob: order by the current cell
+    a.predict = !no_predict && !use_row_tile && (i64)(g.nx + 2) * (g.ny + 2) * (g.nz + 2) <= KEY_LIMIT;
+    if (a.predict) {
+        a.kx = g.nx + 2; a.ky = g.ny + 2; a.kz = g.nz + 2;
+    } else {
+        a.kx = g.nx; a.ky = g.ny; a.kz = g.nz;
+        if ((i64)a.kx * a.ky * a.kz > KEY_LIMIT) a.kz = 1;
+        if ((i64)a.kx * a.ky * a.kz > KEY_LIMIT) a.ky = 1;
+        if ((i64)a.kx * a.ky * a.kz > KEY_LIMIT) return 1;
+    }
     a.dx = g.dx; a.dy = g.dy; a.dz = g.dz;
     a.perm = c->scr_b;
     i64 *d_nalive = c->d_tmp64 + 64;
@@ -414,7 +444,7 @@ int lpic_push_deposit_sorted(lpic_ctx *c, int ispec, double dt, double q, double
     // 128-thread iteration runs mostly empty lanes and the tile load is not overlapped.  Kept opt-in for round 2
     // (multi-row CTAs with a double-buffered TMA tile).
     const int nrows = g.nx * g.ny;
-    const bool rows = a.kz == g.nz && a.ky == g.ny && g.ng >= 2 && (g.NZ == 14 || g.NZ == 22 || g.NZ == 38) &&
+    const bool rows = !a.predict && a.kz == g.nz && a.ky == g.ny && g.ng >= 2 && (g.NZ == 14 || g.NZ == 22 || g.NZ == 38) &&
                       use_row_tile;
     a.rowstart = nullptr;
     if (rows) {
