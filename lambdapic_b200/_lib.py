@@ -11,7 +11,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblpic_b200.so")
+LIB_PATH = os.environ.get("LPIC_B200_LIB", os.path.join(HERE, "liblpic_b200.so"))  # override: A/B builds of the library
 
 FIELD_ATTRS = ["ex", "ey", "ez", "bx", "by", "bz", "jx", "jy", "jz", "rho"]  # core/fields.py:71-75
 PART_ATTRS = ["x", "y", "z", "w", "ux", "uy", "uz", "inv_gamma",
