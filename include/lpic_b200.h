@@ -92,6 +92,20 @@ int lpic_species_extend(lpic_ctx *ctx, int ispec, const int64_t *ext, const uint
 int lpic_update_efield(lpic_ctx *ctx, double dt);
 int lpic_update_bfield(lpic_ctx *ctx, double dt);
 
+/* ---- CPML open boundaries (core/boundary/cpml.py; selected per patch by core/maxwell/solver/solver.py:52-106).
+ *      One instance = one PML face of one patch.  inst_slot = position in the patch's pml_boundary list (the psi
+ *      corrections of a patch are applied in that order).  ranges: (ninst, 4) = efield_start, efield_end, bfield_start,
+ *      bfield_end along the face's axis.  profiles: (ninst, 6, nmax) = kappa_e, sigma_e, a_e, kappa_b, sigma_b, a_b along
+ *      that axis (kappa = 1, sigma = a = 0 outside the layer).  After this call lpic_update_efield / _bfield use the
+ *      kappa-scaled update in the patches that own an instance and advance the psi currents (cpml.py:527-730).
+ *      psi arena: [instance][E1, E2, B1, B2][nx*ny*nz]; E1/E2/B1/B2 in the reference's order per axis
+ *      (x: psi_ey_x psi_ez_x psi_by_x psi_bz_x; y: psi_ex_y psi_ez_y psi_bx_y psi_bz_y; z: psi_ex_z psi_ey_z psi_bx_z psi_by_z). */
+int lpic_pml_configure(lpic_ctx *ctx, int64_t ninst, const int64_t *inst_patch, const int64_t *inst_axis, const int64_t *inst_slot,
+                       const int64_t *ranges, const double *profiles, int64_t nmax);
+int64_t lpic_pml_psi_words(const lpic_ctx *ctx);
+int lpic_pml_upload_psi(lpic_ctx *ctx, const double *host);
+int lpic_pml_download_psi(lpic_ctx *ctx, double *host);
+
 /* ---- guard cells: core/patch/sync_fields3d.c:350-620 / :84-348, sync_fields2d.c:150-255 / :43-148;
  *      facade core/patch/patch.py:670-703.  attr_mask: bit a = field attribute a. */
 int lpic_sync_guard_fields(lpic_ctx *ctx, uint32_t attr_mask);

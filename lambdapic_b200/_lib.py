@@ -49,6 +49,10 @@ SIGNATURES = {
     "lpic_species_extend": (_int, [_vp, _int, _vp, _vp, _vp]),
     "lpic_update_efield": (_int, [_vp, _dbl]),
     "lpic_update_bfield": (_int, [_vp, _dbl]),
+    "lpic_pml_configure": (_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64]),
+    "lpic_pml_psi_words": (_i64, [_vp]),
+    "lpic_pml_upload_psi": (_int, [_vp, _vp]),
+    "lpic_pml_download_psi": (_int, [_vp, _vp]),
     "lpic_sync_guard_fields": (_int, [_vp, _u32]),
     "lpic_sync_currents": (_int, [_vp]),
     "lpic_reset_currents": (_int, [_vp]),

@@ -7,6 +7,8 @@
 //
 // HBM roofline note: all four kernels are pure streaming; one thread owns one (patch, cell).
 // Threads run along z (the contiguous axis) so a warp reads 128-256 B runs; neighbours in y/x come from L1/L2.
+#include <math.h>
+#include <vector>
 #include "lpic_common.cuh"
 
 namespace {
@@ -37,7 +39,8 @@ __device__ __forceinline__ int sidx(const Geom &g, int i, int j, int k) {
 
 // E += (dt c^2) curl B - (dt/eps0) J on interior cells; backward differences reach index -1 (low guard).
 template <int DIM>
-__global__ void __launch_bounds__(256) k_update_efield(Geom g, double *__restrict__ F, double bfactor, double jfactor) {
+__global__ void __launch_bounds__(256) k_update_efield(Geom g, double *__restrict__ F, double bfactor, double jfactor,
+                                                       const u8 *__restrict__ is_pml, const double *__restrict__ kappa, int nmax) {
     CellIdx c;
     if (!interior_cell(g, (i64)blockIdx.x * blockDim.x + threadIdx.x, c)) return;
     const size_t stride = (size_t)g.npatch * g.ncell;
@@ -47,6 +50,30 @@ __global__ void __launch_bounds__(256) k_update_efield(Geom g, double *__restric
     const double *jx = base + LPIC_JX * stride, *jy = base + LPIC_JY * stride, *jz = base + LPIC_JZ * stride;
     const int o = sidx(g, c.i, c.j, c.k), xm = sidx(g, c.i - 1, c.j, c.k), ym = sidx(g, c.i, c.j - 1, c.k);
     const double bxc = bx[o], byc = by[o], bzc = bz[o];
+    if (is_pml && is_pml[c.p]) {
+        // kappa-scaled update of a CPML edge patch (core/boundary/cpml.py:342-362 2D, :437-457 3D); note that the 2D and
+        // 3D forms associate the products differently -- both are reproduced literally
+        const double *kp = kappa + (size_t)c.p * 6 * nmax;  // [e|b][axis][nmax], e first
+        const double bfx = __ddiv_rn(bfactor, kp[c.i]), bfy = __ddiv_rn(bfactor, kp[nmax + c.j]);
+        if (DIM == 3) {
+            const int zm = sidx(g, c.i, c.j, c.k - 1);
+            const double bfz = __ddiv_rn(bfactor, kp[2 * nmax + c.k]);
+            const double cx = __dsub_rn(__ddiv_rn(__dmul_rn(bfy, __dsub_rn(bzc, bz[ym])), g.dy), __ddiv_rn(__dmul_rn(bfz, __dsub_rn(byc, by[zm])), g.dz));
+            const double cy = __dsub_rn(__ddiv_rn(__dmul_rn(bfz, __dsub_rn(bxc, bx[zm])), g.dz), __ddiv_rn(__dmul_rn(bfx, __dsub_rn(bzc, bz[xm])), g.dx));
+            const double cz = __dsub_rn(__ddiv_rn(__dmul_rn(bfx, __dsub_rn(byc, by[xm])), g.dx), __ddiv_rn(__dmul_rn(bfy, __dsub_rn(bxc, bx[ym])), g.dy));
+            ex[o] = __dadd_rn(ex[o], __dsub_rn(cx, __dmul_rn(jfactor, jx[o])));
+            ey[o] = __dadd_rn(ey[o], __dsub_rn(cy, __dmul_rn(jfactor, jy[o])));
+            ez[o] = __dadd_rn(ez[o], __dsub_rn(cz, __dmul_rn(jfactor, jz[o])));
+        } else {
+            const double cx = __dmul_rn(bfy, __ddiv_rn(__dsub_rn(bzc, bz[ym]), g.dy));
+            const double cy = __dmul_rn(bfx, __ddiv_rn(-__dsub_rn(bzc, bz[xm]), g.dx));
+            const double cz = __dsub_rn(__dmul_rn(bfx, __ddiv_rn(__dsub_rn(byc, by[xm]), g.dx)), __dmul_rn(bfy, __ddiv_rn(__dsub_rn(bxc, bx[ym]), g.dy)));
+            ex[o] = __dadd_rn(ex[o], __dsub_rn(cx, __dmul_rn(jfactor, jx[o])));
+            ey[o] = __dadd_rn(ey[o], __dsub_rn(cy, __dmul_rn(jfactor, jy[o])));
+            ez[o] = __dadd_rn(ez[o], __dsub_rn(cz, __dmul_rn(jfactor, jz[o])));
+        }
+        return;
+    }
     if (DIM == 3) {
         const int zm = sidx(g, c.i, c.j, c.k - 1);
         // ex += bfactor*((bz[c]-bz[ym])/dy - (by[c]-by[zm])/dz) - jfactor*jx[c]       (cpu.py:92-97)
@@ -69,7 +96,8 @@ __global__ void __launch_bounds__(256) k_update_efield(Geom g, double *__restric
 
 // B -= dt curl E on interior cells; forward differences reach index n (high guard).
 template <int DIM>
-__global__ void __launch_bounds__(256) k_update_bfield(Geom g, double *__restrict__ F, double dt) {
+__global__ void __launch_bounds__(256) k_update_bfield(Geom g, double *__restrict__ F, double dt, const u8 *__restrict__ is_pml,
+                                                       const double *__restrict__ kappa, int nmax) {
     CellIdx c;
     if (!interior_cell(g, (i64)blockIdx.x * blockDim.x + threadIdx.x, c)) return;
     const size_t stride = (size_t)g.npatch * g.ncell;
@@ -78,6 +106,28 @@ __global__ void __launch_bounds__(256) k_update_bfield(Geom g, double *__restric
     double *bx = base + LPIC_BX * stride, *by = base + LPIC_BY * stride, *bz = base + LPIC_BZ * stride;
     const int o = sidx(g, c.i, c.j, c.k), xp = sidx(g, c.i + 1, c.j, c.k), yp = sidx(g, c.i, c.j + 1, c.k);
     const double exc = ex[o], eyc = ey[o], ezc = ez[o];
+    if (is_pml && is_pml[c.p]) {  // core/boundary/cpml.py:364-377 (2D), :459-477 (3D)
+        const double *kp = kappa + ((size_t)c.p * 6 + 3) * nmax;
+        const double efx = __ddiv_rn(dt, kp[c.i]), efy = __ddiv_rn(dt, kp[nmax + c.j]);
+        if (DIM == 3) {
+            const int zp = sidx(g, c.i, c.j, c.k + 1);
+            const double efz = __ddiv_rn(dt, kp[2 * nmax + c.k]);
+            const double cx = __dsub_rn(__ddiv_rn(__dmul_rn(efy, __dsub_rn(ez[yp], ezc)), g.dy), __ddiv_rn(__dmul_rn(efz, __dsub_rn(ey[zp], eyc)), g.dz));
+            const double cy = __dsub_rn(__ddiv_rn(__dmul_rn(efz, __dsub_rn(ex[zp], exc)), g.dz), __ddiv_rn(__dmul_rn(efx, __dsub_rn(ez[xp], ezc)), g.dx));
+            const double cz = __dsub_rn(__ddiv_rn(__dmul_rn(efx, __dsub_rn(ey[xp], eyc)), g.dx), __ddiv_rn(__dmul_rn(efy, __dsub_rn(ex[yp], exc)), g.dy));
+            bx[o] = __dsub_rn(bx[o], cx);
+            by[o] = __dsub_rn(by[o], cy);
+            bz[o] = __dsub_rn(bz[o], cz);
+        } else {
+            const double cx = __dmul_rn(efy, __ddiv_rn(__dsub_rn(ez[yp], ezc), g.dy));
+            const double cy = __dmul_rn(efx, __ddiv_rn(-__dsub_rn(ez[xp], ezc), g.dx));
+            const double cz = __dsub_rn(__dmul_rn(efx, __ddiv_rn(__dsub_rn(ey[xp], eyc), g.dx)), __dmul_rn(efy, __ddiv_rn(__dsub_rn(ex[yp], exc), g.dy)));
+            bx[o] = __dsub_rn(bx[o], cx);
+            by[o] = __dsub_rn(by[o], cy);
+            bz[o] = __dsub_rn(bz[o], cz);
+        }
+        return;
+    }
     if (DIM == 3) {
         const int zp = sidx(g, c.i, c.j, c.k + 1);
         double cx = __dsub_rn(__ddiv_rn(__dsub_rn(ez[yp], ezc), g.dy), __ddiv_rn(__dsub_rn(ey[zp], eyc), g.dz));
@@ -94,6 +144,50 @@ __global__ void __launch_bounds__(256) k_update_bfield(Geom g, double *__restric
         by[o] = __dsub_rn(by[o], __dmul_rn(dt, cy));
         bz[o] = __dsub_rn(bz[o], __dmul_rn(dt, cz));
     }
+}
+
+// psi update of the PML faces in one slot and the correction of the two components each face drives
+// (core/boundary/cpml.py:527-730).  grid.y = instance inside the slot; one thread per interior cell of its patch.
+//   E: x: (ey,-,bz) (ez,+,by)   y: (ex,+,bz) (ez,-,bx)   z: (ex,-,by) (ey,+,bx)      backward difference of B, fac = dt c^2
+//   B: x: (by,+,ez) (bz,-,ey)   y: (bx,-,ez) (bz,+,ex)   z: (bx,+,ey) (by,-,ex)      forward difference of E,  fac = dt
+__global__ void __launch_bounds__(256) k_pml_psi(Geom g, double *__restrict__ F, const int *__restrict__ inst, const i64 *__restrict__ order,
+                                                 i64 first, const double *__restrict__ coef, double *__restrict__ psi, int nmax,
+                                                 i64 ncint, int is_b, double fac) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= g.nx * g.ny * g.nz) return;
+    const i64 e = first + blockIdx.y;
+    const int *in = inst + e * 8;
+    const int p = in[0], axis = in[1], lo = in[2 + 2 * is_b], hi = in[3 + 2 * is_b];
+    const int k = t % g.nz, j = (t / g.nz) % g.ny, i = t / (g.nz * g.ny);
+    const int ipos = axis == 0 ? i : (axis == 1 ? j : k);
+    if (ipos < lo || ipos >= hi) return;
+    // component table: index into the field arena (LPIC_EX.. LPIC_BZ)
+    int c1, c2, g1, g2;
+    double s1, s2;
+    if (!is_b) {
+        if (axis == 0) { c1 = LPIC_EY; s1 = -1; g1 = LPIC_BZ; c2 = LPIC_EZ; s2 = 1; g2 = LPIC_BY; }
+        else if (axis == 1) { c1 = LPIC_EX; s1 = 1; g1 = LPIC_BZ; c2 = LPIC_EZ; s2 = -1; g2 = LPIC_BX; }
+        else { c1 = LPIC_EX; s1 = -1; g1 = LPIC_BY; c2 = LPIC_EY; s2 = 1; g2 = LPIC_BX; }
+    } else {
+        if (axis == 0) { c1 = LPIC_BY; s1 = 1; g1 = LPIC_EZ; c2 = LPIC_BZ; s2 = -1; g2 = LPIC_EY; }
+        else if (axis == 1) { c1 = LPIC_BX; s1 = -1; g1 = LPIC_EZ; c2 = LPIC_BZ; s2 = 1; g2 = LPIC_EX; }
+        else { c1 = LPIC_BX; s1 = 1; g1 = LPIC_EY; c2 = LPIC_BY; s2 = -1; g2 = LPIC_EX; }
+    }
+    const size_t stride = (size_t)g.npatch * g.ncell;
+    double *base = F + (size_t)p * g.ncell;
+    const int o = sidx(g, i, j, k);
+    const int d = is_b ? 1 : -1;
+    const int nbr = sidx(g, i + (axis == 0 ? d : 0), j + (axis == 1 ? d : 0), k + (axis == 2 ? d : 0));
+    const double bco = coef[((size_t)e * 4 + 2 * is_b) * nmax + ipos], cco = coef[((size_t)e * 4 + 2 * is_b + 1) * nmax + ipos];
+    const double a1 = base[g1 * stride + o], n1 = base[g1 * stride + nbr], a2 = base[g2 * stride + o], n2 = base[g2 * stride + nbr];
+    const double d1 = is_b ? __dsub_rn(n1, a1) : __dsub_rn(a1, n1), d2 = is_b ? __dsub_rn(n2, a2) : __dsub_rn(a2, n2);
+    double *ps = psi + ((size_t)order[e] * 4 + 2 * is_b) * ncint + t;
+    const double p1 = __dadd_rn(__dmul_rn(bco, ps[0]), __dmul_rn(cco, d1));
+    const double p2 = __dadd_rn(__dmul_rn(bco, ps[ncint]), __dmul_rn(cco, d2));
+    ps[0] = p1;
+    ps[ncint] = p2;
+    base[c1 * stride + o] = __dadd_rn(base[c1 * stride + o], __dmul_rn(s1, __dmul_rn(fac, p1)));
+    base[c2 * stride + o] = __dadd_rn(base[c2 * stride + o], __dmul_rn(s2, __dmul_rn(fac, p2)));
 }
 
 // storage index -> logical index along one axis
@@ -234,30 +328,75 @@ __global__ void __launch_bounds__(256) k_field_energy(Geom g, const double *__re
 
 }  // namespace
 
+// psi coefficients for this dt (bcoeff = exp(-(sigma/kappa + a) dt), ccoeff = (bcoeff - 1) sigma / kappa / (sigma + kappa a) / d,
+// core/boundary/cpml.py:535-536), then one psi launch per slot so that the faces of a patch are applied in list order
+static int pml_advance(lpic_ctx *c, int is_b, double dt) {
+    PmlState *pm = c->pml;
+    const Geom &g = c->g;
+    if (pm->ninst == 0) return 0;
+    if (pm->coef_dt[is_b] != dt) {
+        std::vector<double> co((size_t)pm->ninst * 2 * pm->nmax, 0.0);
+        const double dd[3] = {g.dx, g.dy, g.dz};
+        for (i64 e = 0; e < pm->ninst; e++) {
+            const double *kap = pm->h_prof + ((size_t)e * 6 + 3 * is_b) * pm->nmax, *sig = kap + pm->nmax, *a = sig + pm->nmax;
+            for (i64 i = 0; i < pm->nmax; i++) {
+                const double bco = exp(-(sig[i] / kap[i] + a[i]) * dt);
+                const double den = sig[i] + kap[i] * a[i];
+                co[((size_t)e * 2) * pm->nmax + i] = bco;
+                co[((size_t)e * 2 + 1) * pm->nmax + i] = den != 0.0 ? (bco - 1) * sig[i] / kap[i] / den / dd[pm->h_axis[e]] : 0.0;
+            }
+        }
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        for (i64 e = 0; e < pm->ninst; e++)
+            CUDA_TRY(cudaMemcpy(pm->d_coef + ((size_t)e * 4 + 2 * is_b) * pm->nmax, co.data() + (size_t)e * 2 * pm->nmax,
+                                sizeof(double) * 2 * pm->nmax, cudaMemcpyHostToDevice));
+        pm->coef_dt[is_b] = dt;
+    }
+    const double fac = is_b ? dt : dt * (LPIC_C_LIGHT * LPIC_C_LIGHT);
+    for (int sl = 0; sl < pm->nslot; sl++) {
+        const i64 cnt = pm->slot_first[sl + 1] - pm->slot_first[sl];
+        if (cnt == 0) continue;
+        dim3 grid(div_up((i64)g.nx * g.ny * g.nz, 256), (unsigned)cnt);
+        k_pml_psi<<<grid, 256, 0, c->stream>>>(g, c->fields, pm->d_inst, (const i64 *)pm->d_order, pm->slot_first[sl], pm->d_coef,
+                                               pm->d_psi, (int)pm->nmax, pm->ncint, is_b, fac);
+        LAUNCHED(1);
+    }
+    KERNEL_CHECK();
+    return 0;
+}
+
 extern "C" int lpic_update_efield(lpic_ctx *c, double dt) {
     const Geom &g = c->g;
     const i64 n = (i64)g.npatch * g.nx * g.ny * g.nz;
     // bfactor = dt*c**2, jfactor = dt/epsilon_0 (core/maxwell/cpu.py:90-91)
     const double bfactor = dt * (LPIC_C_LIGHT * LPIC_C_LIGHT), jfactor = dt / LPIC_EPS0;
+    const PmlState *pm = c->pml;
+    const u8 *isp = pm ? pm->d_is_pml : nullptr;
+    const double *kap = pm ? pm->d_kappa : nullptr;
+    const int nmax = pm ? (int)pm->nmax : 0;
     if (g.dim == 3)
-        k_update_efield<3><<<div_up(n, 256), 256, 0, c->stream>>>(g, c->fields, bfactor, jfactor);
+        k_update_efield<3><<<div_up(n, 256), 256, 0, c->stream>>>(g, c->fields, bfactor, jfactor, isp, kap, nmax);
     else
-        k_update_efield<2><<<div_up(n, 256), 256, 0, c->stream>>>(g, c->fields, bfactor, jfactor);
+        k_update_efield<2><<<div_up(n, 256), 256, 0, c->stream>>>(g, c->fields, bfactor, jfactor, isp, kap, nmax);
     LAUNCHED(1);
     KERNEL_CHECK();
-    return 0;
+    return pm ? pml_advance(c, 0, dt) : 0;
 }
 
 extern "C" int lpic_update_bfield(lpic_ctx *c, double dt) {
     const Geom &g = c->g;
     const i64 n = (i64)g.npatch * g.nx * g.ny * g.nz;
+    const PmlState *pm = c->pml;
+    const u8 *isp = pm ? pm->d_is_pml : nullptr;
+    const double *kap = pm ? pm->d_kappa : nullptr;
+    const int nmax = pm ? (int)pm->nmax : 0;
     if (g.dim == 3)
-        k_update_bfield<3><<<div_up(n, 256), 256, 0, c->stream>>>(g, c->fields, dt);
+        k_update_bfield<3><<<div_up(n, 256), 256, 0, c->stream>>>(g, c->fields, dt, isp, kap, nmax);
     else
-        k_update_bfield<2><<<div_up(n, 256), 256, 0, c->stream>>>(g, c->fields, dt);
+        k_update_bfield<2><<<div_up(n, 256), 256, 0, c->stream>>>(g, c->fields, dt, isp, kap, nmax);
     LAUNCHED(1);
     KERNEL_CHECK();
-    return 0;
+    return pm ? pml_advance(c, 1, dt) : 0;
 }
 
 extern "C" int lpic_sync_guard_fields(lpic_ctx *c, uint32_t attr_mask) {
@@ -297,6 +436,86 @@ extern "C" int lpic_field_energy_sums(lpic_ctx *c, double *out2) {
     LAUNCHED(1);
     KERNEL_CHECK();
     CUDA_TRY(cudaMemcpyAsync(out2, c->d_tmpf, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+void lpic_free_pml(lpic_ctx *c) {
+    PmlState *pm = c->pml;
+    if (!pm) return;
+    cudaFree(pm->d_is_pml); cudaFree(pm->d_kappa); cudaFree(pm->d_inst); cudaFree(pm->d_coef); cudaFree(pm->d_psi); cudaFree(pm->d_order);
+    delete[] pm->h_prof; delete[] pm->h_order; delete[] pm->h_axis;
+    delete pm;
+    c->pml = nullptr;
+}
+
+extern "C" int lpic_pml_configure(lpic_ctx *c, int64_t ninst, const int64_t *inst_patch, const int64_t *inst_axis,
+                                  const int64_t *inst_slot, const int64_t *ranges, const double *profiles, int64_t nmax) {
+    const Geom &g = c->g;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    lpic_free_pml(c);
+    if (ninst <= 0) return 0;
+    REQUIRE(nmax >= g.nx && nmax >= g.ny && nmax >= g.nz, "nmax must cover the longest patch axis");
+    PmlState *pm = new PmlState();
+    c->pml = pm;
+    pm->ninst = ninst; pm->nmax = nmax; pm->ncint = (i64)g.nx * g.ny * g.nz;
+    // group the instances by slot (the order in which a patch applies its faces)
+    std::vector<i64> order;
+    pm->nslot = 0;
+    for (i64 e = 0; e < ninst; e++) {
+        REQUIRE(inst_slot[e] >= 0 && inst_slot[e] < 4 && inst_axis[e] >= 0 && inst_axis[e] < g.dim && inst_patch[e] >= 0 &&
+                    inst_patch[e] < g.npatch, "bad PML instance %lld", (long long)e);
+        pm->nslot = std::max(pm->nslot, (int)inst_slot[e] + 1);
+    }
+    for (int sl = 0; sl < pm->nslot; sl++) {
+        pm->slot_first[sl] = (i64)order.size();
+        for (i64 e = 0; e < ninst; e++)
+            if (inst_slot[e] == sl) order.push_back(e);
+    }
+    for (int sl = pm->nslot; sl <= 4; sl++) pm->slot_first[sl] = (i64)order.size();
+    pm->h_order = new i64[ninst]; pm->h_axis = new int[ninst];
+    pm->h_prof = new double[(size_t)ninst * 6 * nmax];
+    std::vector<int> inst((size_t)ninst * 8, 0);
+    std::vector<u8> isp(g.npatch, 0);
+    std::vector<double> kap((size_t)g.npatch * 6 * nmax, 1.0);
+    for (i64 s = 0; s < ninst; s++) {
+        const i64 e = order[s];
+        pm->h_order[s] = e;
+        pm->h_axis[s] = (int)inst_axis[e];
+        memcpy(pm->h_prof + (size_t)s * 6 * nmax, profiles + (size_t)e * 6 * nmax, sizeof(double) * 6 * nmax);
+        int *in = inst.data() + s * 8;
+        in[0] = (int)inst_patch[e]; in[1] = (int)inst_axis[e];
+        for (int r = 0; r < 4; r++) in[2 + r] = (int)ranges[e * 4 + r];
+        isp[inst_patch[e]] = 1;
+        // this face's kappa profile replaces the default 1.0 along its axis (solver.py:88-106)
+        for (int w = 0; w < 2; w++)
+            memcpy(kap.data() + (((size_t)inst_patch[e] * 2 + w) * 3 + inst_axis[e]) * nmax, profiles + ((size_t)e * 6 + 3 * w) * nmax,
+                   sizeof(double) * nmax);
+    }
+    CUDA_TRY(cudaMalloc(&pm->d_is_pml, g.npatch));
+    CUDA_TRY(cudaMemcpy(pm->d_is_pml, isp.data(), g.npatch, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&pm->d_kappa, sizeof(double) * kap.size()));
+    CUDA_TRY(cudaMemcpy(pm->d_kappa, kap.data(), sizeof(double) * kap.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&pm->d_inst, sizeof(int) * inst.size()));
+    CUDA_TRY(cudaMemcpy(pm->d_inst, inst.data(), sizeof(int) * inst.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&pm->d_order, sizeof(i64) * ninst));
+    CUDA_TRY(cudaMemcpy(pm->d_order, pm->h_order, sizeof(i64) * ninst, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&pm->d_coef, sizeof(double) * (size_t)ninst * 4 * nmax));
+    CUDA_TRY(cudaMemset(pm->d_coef, 0, sizeof(double) * (size_t)ninst * 4 * nmax));
+    CUDA_TRY(cudaMalloc(&pm->d_psi, sizeof(double) * (size_t)ninst * 4 * pm->ncint));
+    CUDA_TRY(cudaMemset(pm->d_psi, 0, sizeof(double) * (size_t)ninst * 4 * pm->ncint));
+    return 0;
+}
+
+extern "C" int64_t lpic_pml_psi_words(const lpic_ctx *c) { return c->pml ? c->pml->ninst * 4 * c->pml->ncint : 0; }
+extern "C" int lpic_pml_upload_psi(lpic_ctx *c, const double *host) {
+    if (!c->pml) return 0;
+    CUDA_TRY(cudaMemcpyAsync(c->pml->d_psi, host, sizeof(double) * (size_t)lpic_pml_psi_words(c), cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+extern "C" int lpic_pml_download_psi(lpic_ctx *c, double *host) {
+    if (!c->pml) return 0;
+    CUDA_TRY(cudaMemcpyAsync(host, c->pml->d_psi, sizeof(double) * (size_t)lpic_pml_psi_words(c), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return 0;
 }

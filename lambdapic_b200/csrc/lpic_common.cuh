@@ -67,6 +67,22 @@ struct HaloPlan {
     i64 *d_mig_recv_cnt = nullptr, *d_mig_recv_poff = nullptr, *d_mig_incoming = nullptr;
 };
 
+// CPML state (fields.cu): per-patch kappa profiles, per-instance psi arrays and coefficient profiles
+struct PmlState {
+    i64 ninst = 0, nmax = 0, ncint = 0;
+    int nslot = 0;
+    u8 *d_is_pml = nullptr;          // (npatch)
+    double *d_kappa = nullptr;       // (npatch, 2 [e,b], 3 [axis], nmax)
+    int *d_inst = nullptr;           // (ninst, 8): patch, axis, e_lo, e_hi, b_lo, b_hi, -, -   (grouped by slot)
+    i64 slot_first[5] = {0, 0, 0, 0, 0};
+    double *h_prof = nullptr;        // (ninst, 6, nmax) host copy, slot-grouped order
+    double *d_coef = nullptr;        // (ninst, 4 [bE, cE, bB, cB], nmax) for the dt of the last call
+    double coef_dt[2] = {-1.0, -1.0};
+    double *d_psi = nullptr;         // (ninst, 4, ncint), CALLER's instance order
+    i64 *h_order = nullptr, *d_order = nullptr;  // slot-grouped position -> caller's instance index
+    int *h_axis = nullptr;
+};
+
 struct lpic_ctx {
     Geom g;
     int device = 0;
@@ -88,6 +104,7 @@ struct lpic_ctx {
     double *d_sort_org = nullptr;            // (3, npatch) bucket origins
     i64 *d_tmp64 = nullptr;                  // small reductions (>= 8 + npatch words)
     double *d_tmpf = nullptr;
+    struct PmlState *pml = nullptr;   // null: no open boundaries
     struct HaloPlan *halo = nullptr;  // inter-rank exchange plan (halo.cu), null on a single rank
     cudaEvent_t *events = nullptr;  // lazily created, 4096 slots
     int *d_rowstart = nullptr;      // (npatch, nx*ny + 1) row starts of the cell permutation (push_sorted.cu)

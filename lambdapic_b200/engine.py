@@ -124,6 +124,8 @@ class DeviceEngine:
                 if s is not None:
                     s.free()
             self._fbuf.free()
+            if getattr(self, "_psibuf", None) is not None:
+                self._psibuf.free()
 
     def __del__(self):
         try:
@@ -158,6 +160,39 @@ class DeviceEngine:
     def download_fields(self, mask=ALL_FIELDS):
         check(self.L.lpic_download_fields(self.ctx, mask, _ptr(self.fields_host)))
 
+    # ---- CPML ------------------------------------------------------------------------------------------------
+    def configure_pml(self, instances):
+        """instances: list of (patch, axis, slot, (e_lo, e_hi, b_lo, b_hi), profiles[6, nmax]).  Allocates the psi arena on
+        the device and its pinned host mirror `psi_host` of shape (ninst, 4, nx, ny[, nz])."""
+        n = len(instances)
+        self.pml_instances = instances
+        if getattr(self, "_psibuf", None) is not None:
+            self._psibuf.free()
+        self._psibuf, self.psi_host = None, None
+        if n == 0:
+            check(self.L.lpic_pml_configure(self.ctx, 0, None, None, None, None, None, 0))
+            return
+        nmax = max(self.nx, self.ny, self.nz)
+        i64 = lambda a: np.ascontiguousarray(a, dtype=np.int64)  # noqa: E731
+        patch, axis, slot = i64([i[0] for i in instances]), i64([i[1] for i in instances]), i64([i[2] for i in instances])
+        ranges = i64([i[3] for i in instances]).reshape(n, 4)
+        prof = np.ascontiguousarray(np.stack([i[4] for i in instances]), dtype=np.float64)
+        assert prof.shape == (n, 6, nmax)
+        check(self.L.lpic_pml_configure(self.ctx, n, _ptr(patch), _ptr(axis), _ptr(slot), _ptr(ranges), _ptr(prof), nmax))
+        words = int(self.L.lpic_pml_psi_words(self.ctx))
+        self._psibuf = HostBuffer(8 * words)
+        interior = (self.nx, self.ny) + ((self.nz,) if self.dim == 3 else ())
+        self.psi_host = self._psibuf.array(np.float64, words).reshape((n, 4) + interior)
+        self.psi_host[...] = 0.0
+
+    def upload_psi(self):
+        if getattr(self, "psi_host", None) is not None:
+            check(self.L.lpic_pml_upload_psi(self.ctx, _ptr(self.psi_host)))
+
+    def download_psi(self):
+        if getattr(self, "psi_host", None) is not None:
+            check(self.L.lpic_pml_download_psi(self.ctx, _ptr(self.psi_host)))
+
     # ---- particles -------------------------------------------------------------------------------------------
     def alloc_species(self, ispec, npart, slack=1.5, min_extra=64, with_part=False, npart_created=None):
         npart = np.ascontiguousarray(npart, dtype=np.int64)
@@ -182,6 +217,7 @@ class DeviceEngine:
 
     def upload_all(self):
         self.upload_fields()
+        self.upload_psi()
         for s in range(self.nspec):
             if self.species[s] is not None:
                 self.upload_particles(s)
@@ -189,6 +225,7 @@ class DeviceEngine:
 
     def download_all(self):
         self.download_fields()
+        self.download_psi()
         for s in range(self.nspec):
             if self.species[s] is not None:
                 self.download_particles(s)

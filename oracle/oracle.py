@@ -138,13 +138,54 @@ class OPatch:
         self.neighbor_ipatch = np.ascontiguousarray(neighbor_ipatch, dtype=np.int64)
         self.particles = []
         self.fields = None
-    # patch.py:105-148 without PML
-    xmin = property(lambda s: s.x0)
-    xmax = property(lambda s: s.x0 + (s.nx - 1) * s.dx)
-    ymin = property(lambda s: s.y0)
-    ymax = property(lambda s: s.y0 + (s.ny - 1) * s.dy)
-    zmin = property(lambda s: s.z0)
-    zmax = property(lambda s: s.z0 + (s.nz - 1) * s.dz)
+        self.pml = []  # OPml objects in the order the reference adds them (xmin, xmax, ymin, ymax, zmin, zmax)
+
+    def _shrink(self, face, d):  # core/patch/patch.py:105-148: the particle box excludes the PML
+        return next((m.thickness * d for m in self.pml if m.face == face), 0.0)
+    xmin = property(lambda s: s.x0 + s._shrink("xmin", s.dx))
+    xmax = property(lambda s: s.x0 + (s.nx - 1) * s.dx - s._shrink("xmax", s.dx))
+    ymin = property(lambda s: s.y0 + s._shrink("ymin", s.dy))
+    ymax = property(lambda s: s.y0 + (s.ny - 1) * s.dy - s._shrink("ymax", s.dy))
+    zmin = property(lambda s: s.z0 + s._shrink("zmin", s.dz))
+    zmax = property(lambda s: s.z0 + (s.nz - 1) * s.dz - s._shrink("zmax", s.dz))
+
+
+AXIS = {"x": 0, "y": 1, "z": 2}
+# (corrected component, sign, differenced source) pairs per axis; core/boundary/cpml.py:527-730
+PSI_TABLE = {0: dict(E=[("ey", -1.0, "bz"), ("ez", +1.0, "by")], B=[("by", +1.0, "ez"), ("bz", -1.0, "ey")]),
+             1: dict(E=[("ex", +1.0, "bz"), ("ez", -1.0, "bx")], B=[("bx", -1.0, "ez"), ("bz", +1.0, "ex")]),
+             2: dict(E=[("ex", -1.0, "by"), ("ey", +1.0, "bx")], B=[("bx", +1.0, "ey"), ("by", -1.0, "ex")])}
+
+
+class OPml:
+    """One CPML face of a patch: coefficient profiles and psi arrays (core/boundary/cpml.py:11-131, 247-340)."""
+
+    def __init__(self, face, n, d, shape, dx, thickness=6, kappa_max=20.0, a_max=0.15, sigma_max=0.7):
+        self.face, self.axis, self.side = face, AXIS[face[0]], face[1:]
+        self.thickness, self.n, self.d = thickness, n, d
+        m, ma = 3, 1
+        sig_maxval = sigma_max * C_LIGHT * 0.8 * (m + 1.0) / dx  # the reference scales every face with dx (cpml.py:60)
+        self.kappa_e, self.kappa_b = np.ones(n), np.ones(n)
+        self.sigma_e, self.sigma_b, self.a_e, self.a_b = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n)
+
+        def coeff(pos, sl, kappa, sigma, a):
+            kappa[sl] = 1 + (kappa_max - 1) * pos**m
+            sigma[sl] = sig_maxval * pos**m
+            a[sl] = a_max * (1 - pos)**ma
+        t = thickness
+        if self.side == "min":
+            coeff(1.0 - np.arange(t, dtype=float) / t, np.s_[:t], self.kappa_e, self.sigma_e, self.a_e)
+            coeff(1.0 - (np.arange(t, dtype=float) + 0.5) / t, np.s_[:t], self.kappa_b, self.sigma_b, self.a_b)
+            self.e_range, self.b_range = (0, t), (0, t)
+        else:
+            coeff(1.0 - np.arange(t, dtype=float)[::-1] / t, np.s_[n - t:n], self.kappa_e, self.sigma_e, self.a_e)
+            coeff(1.0 - (np.arange(t, dtype=float) + 0.5)[::-1] / t, np.s_[n - t - 1:n - 1], self.kappa_b, self.sigma_b, self.a_b)
+            self.e_range, self.b_range = (n - t, n), (n - t - 1, n - 1)
+        ax = "xyz"[self.axis]
+        self.names = dict(E=[f"psi_{c}_{ax}" for c, _, _ in PSI_TABLE[self.axis]["E"]],
+                          B=[f"psi_{c}_{ax}" for c, _, _ in PSI_TABLE[self.axis]["B"]])
+        for nm in self.names["E"] + self.names["B"]:
+            setattr(self, nm, np.zeros(shape))
 
 
 class OSorter:
@@ -212,6 +253,20 @@ class OState:
                 part.is_dead = np.ascontiguousarray(g[f"{tag}/p/{ip}/{s}/is_dead"]).astype(bool).copy()
                 part.npart = part.x.size
                 part._npart_created = part.npart  # capacity == ids handed out (prune is never on the path)
+        if "meta/pml_faces" in g.files:
+            n_ax = (st.nx, st.ny, st.nz)
+            d_ax = (st.dx, st.dy, st.dz)
+            shape = (st.nx, st.ny) + ((st.nz,) if dim == 3 else ())
+            cls2face = {"PMLXmin": "xmin", "PMLXmax": "xmax", "PMLYmin": "ymin", "PMLYmax": "ymax", "PMLZmin": "zmin", "PMLZmax": "zmax"}
+            for ip, p in enumerate(st.patches):
+                for ipml, cname in enumerate(str(g["meta/pml_faces"][ip]).split(",")):
+                    if not cname:
+                        continue
+                    face = cls2face[cname]
+                    m = OPml(face, n_ax[AXIS[face[0]]], d_ax[AXIS[face[0]]], shape, st.dx, thickness=int(g["meta/cpml_thickness"]))
+                    for nm in m.names["E"] + m.names["B"]:
+                        getattr(m, nm)[...] = g[f"{tag}/pml/{ip}/{ipml}/{nm}"]
+                    p.pml.append(m)
         st.sorters = [OSorter(st, s) for s in range(st.nspec)]
         return st
 
@@ -245,18 +300,51 @@ class OState:
 # --------------------------------------------------------------------------------------------------
 # operators
 # --------------------------------------------------------------------------------------------------
+def _kappas(st, p, which):
+    n_ax = (st.nx, st.ny, st.nz)
+    ks = [np.ones(n_ax[a]) for a in range(st.dim)]
+    for m in p.pml:  # core/maxwell/solver/solver.py:88-106
+        ks[m.axis] = m.kappa_e if which == "e" else m.kappa_b
+    return ks
+
+
+def _advance_psi(st, p, which, dt):
+    """pml.advance_e_currents / advance_b_currents for every face of the patch, in list order."""
+    L = lib()
+    f = p.fields
+    for m in p.pml:
+        (c1, s1, g1), (c2, s2, g2) = PSI_TABLE[m.axis][which]
+        n1, n2 = m.names[which]
+        kap, sig, a = (m.kappa_e, m.sigma_e, m.a_e) if which == "E" else (m.kappa_b, m.sigma_b, m.a_b)
+        lo, hi = m.e_range if which == "E" else m.b_range
+        L.orc_update_psi(_p(getattr(f, c1)), _p(getattr(f, c2)), _p(getattr(f, g1)), _p(getattr(f, g2)),
+                         _p(getattr(m, n1)), _p(getattr(m, n2)), _c_dbl(s1), _c_dbl(s2), _p(kap), _p(sig), _p(a),
+                         _c_i64(m.axis), _c_i64(0 if which == "E" else 1), _c_i64(lo), _c_i64(hi), _c_i64(st.dim),
+                         _c_i64(st.nx), _c_i64(st.ny), _c_i64(st.nz), _c_i64(st.ng), _c_dbl(m.d), _c_dbl(dt))
+
+
 def update_efield(st: OState, dt: float):
     L = lib()
     bfac, jfac = dt * C_LIGHT**2, dt / EPSILON_0
     for p in st.patches:
         f = p.fields
         a = [_p(getattr(f, n)) for n in FIELD_ATTRS[:9]]
-        if st.dim == 3:
+        if p.pml:
+            ks = [_p(k) for k in _kappas(st, p, "e")]
+            if st.dim == 3:
+                L.orc_update_efield_cpml_3d(*a, *ks, _c_i64(st.nx), _c_i64(st.ny), _c_i64(st.nz), _c_i64(st.ng),
+                                            _c_dbl(st.dx), _c_dbl(st.dy), _c_dbl(st.dz), _c_dbl(bfac), _c_dbl(jfac))
+            else:
+                L.orc_update_efield_cpml_2d(*a, *ks, _c_i64(st.nx), _c_i64(st.ny), _c_i64(st.ng),
+                                            _c_dbl(st.dx), _c_dbl(st.dy), _c_dbl(bfac), _c_dbl(jfac))
+        elif st.dim == 3:
             L.orc_update_efield_3d(*a, _c_i64(st.nx), _c_i64(st.ny), _c_i64(st.nz), _c_i64(st.ng),
                                    _c_dbl(st.dx), _c_dbl(st.dy), _c_dbl(st.dz), _c_dbl(bfac), _c_dbl(jfac))
         else:
             L.orc_update_efield_2d(*a, _c_i64(st.nx), _c_i64(st.ny), _c_i64(st.ng),
                                    _c_dbl(st.dx), _c_dbl(st.dy), _c_dbl(bfac), _c_dbl(jfac))
+    for p in st.patches:
+        _advance_psi(st, p, "E", dt)
 
 
 def update_bfield(st: OState, dt: float):
@@ -264,11 +352,20 @@ def update_bfield(st: OState, dt: float):
     for p in st.patches:
         f = p.fields
         a = [_p(getattr(f, n)) for n in FIELD_ATTRS[:6]]
-        if st.dim == 3:
+        if p.pml:
+            ks = [_p(k) for k in _kappas(st, p, "b")]
+            if st.dim == 3:
+                L.orc_update_bfield_cpml_3d(*a, *ks, _c_i64(st.nx), _c_i64(st.ny), _c_i64(st.nz), _c_i64(st.ng),
+                                            _c_dbl(st.dx), _c_dbl(st.dy), _c_dbl(st.dz), _c_dbl(dt))
+            else:
+                L.orc_update_bfield_cpml_2d(*a, *ks, _c_i64(st.nx), _c_i64(st.ny), _c_i64(st.ng), _c_dbl(st.dx), _c_dbl(st.dy), _c_dbl(dt))
+        elif st.dim == 3:
             L.orc_update_bfield_3d(*a, _c_i64(st.nx), _c_i64(st.ny), _c_i64(st.nz), _c_i64(st.ng),
                                    _c_dbl(st.dx), _c_dbl(st.dy), _c_dbl(st.dz), _c_dbl(dt))
         else:
             L.orc_update_bfield_2d(*a, _c_i64(st.nx), _c_i64(st.ny), _c_i64(st.ng), _c_dbl(st.dx), _c_dbl(st.dy), _c_dbl(dt))
+    for p in st.patches:
+        _advance_psi(st, p, "B", dt)
 
 
 def sync_guard_fields(st: OState, attrs, backend="port"):

@@ -579,3 +579,115 @@ void orc_migrate_fill(double **attrs, i64 nattrs, i64 ia_x, i64 ia_y, i64 ia_z, 
     for (i64 i = 0; i < npatch * nb; i++) free(lists[i]);
     free(lists); free(cnt);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * CPML (convolutional PML) edge patches: kappa-scaled Yee update and the psi auxiliary currents.
+ * core/boundary/cpml.py:342-362 (2D), :437-477 (3D), :527-730 (psi); coefficients :118-126.
+ * Expression order is the reference's (numba, no contraction).  kappa_* are per-patch 1-D arrays along
+ * each axis (1.0 outside the layer).  2D and 3D associate the products differently, as the reference does.
+ * ---------------------------------------------------------------------------------------------- */
+void orc_update_efield_cpml_3d(double *ex, double *ey, double *ez, const double *bx, const double *by, const double *bz,
+                               const double *jx, const double *jy, const double *jz, const double *kex, const double *key,
+                               const double *kez, i64 nx, i64 ny, i64 nz, i64 ng, double dx, double dy, double dz,
+                               double bfactor, double jfactor) {
+    const i64 NX = nx + 2 * ng, NY = ny + 2 * ng, NZ = nz + 2 * ng;
+    for (i64 i = 0; i < nx; i++) {
+        const double bfx = bfactor / kex[i];
+        for (i64 j = 0; j < ny; j++) {
+            const double bfy = bfactor / key[j];
+            for (i64 k = 0; k < nz; k++) {
+                const double bfz = bfactor / kez[k];
+                i64 c = IX3(i, j, k), xm = IX3(i - 1, j, k), ym = IX3(i, j - 1, k), zm = IX3(i, j, k - 1);
+                ex[c] += (bfy * (bz[c] - bz[ym]) / dy - bfz * (by[c] - by[zm]) / dz) - jfactor * jx[c];
+                ey[c] += (bfz * (bx[c] - bx[zm]) / dz - bfx * (bz[c] - bz[xm]) / dx) - jfactor * jy[c];
+                ez[c] += (bfx * (by[c] - by[xm]) / dx - bfy * (bx[c] - bx[ym]) / dy) - jfactor * jz[c];
+            }
+        }
+    }
+}
+
+void orc_update_bfield_cpml_3d(const double *ex, const double *ey, const double *ez, double *bx, double *by, double *bz,
+                               const double *kbx, const double *kby, const double *kbz, i64 nx, i64 ny, i64 nz, i64 ng,
+                               double dx, double dy, double dz, double dt) {
+    const i64 NX = nx + 2 * ng, NY = ny + 2 * ng, NZ = nz + 2 * ng;
+    for (i64 i = 0; i < nx; i++) {
+        const double efx = dt / kbx[i];
+        for (i64 j = 0; j < ny; j++) {
+            const double efy = dt / kby[j];
+            for (i64 k = 0; k < nz; k++) {
+                const double efz = dt / kbz[k];
+                i64 c = IX3(i, j, k), xp = IX3(i + 1, j, k), yp = IX3(i, j + 1, k), zp = IX3(i, j, k + 1);
+                bx[c] -= (efy * (ez[yp] - ez[c]) / dy - efz * (ey[zp] - ey[c]) / dz);
+                by[c] -= (efz * (ex[zp] - ex[c]) / dz - efx * (ez[xp] - ez[c]) / dx);
+                bz[c] -= (efx * (ey[xp] - ey[c]) / dx - efy * (ex[yp] - ex[c]) / dy);
+            }
+        }
+    }
+}
+
+void orc_update_efield_cpml_2d(double *ex, double *ey, double *ez, const double *bx, const double *by, const double *bz,
+                               const double *jx, const double *jy, const double *jz, const double *kex, const double *key,
+                               i64 nx, i64 ny, i64 ng, double dx, double dy, double bfactor, double jfactor) {
+    const i64 NX = nx + 2 * ng, NY = ny + 2 * ng;
+    for (i64 i = 0; i < nx; i++) {
+        const double bfx = bfactor / kex[i];
+        for (i64 j = 0; j < ny; j++) {
+            const double bfy = bfactor / key[j];
+            i64 c = IX2(i, j), xm = IX2(i - 1, j), ym = IX2(i, j - 1);
+            ex[c] += bfy * ((bz[c] - bz[ym]) / dy) - jfactor * jx[c];
+            ey[c] += bfx * (-(bz[c] - bz[xm]) / dx) - jfactor * jy[c];
+            ez[c] += bfx * ((by[c] - by[xm]) / dx) - bfy * ((bx[c] - bx[ym]) / dy) - jfactor * jz[c];
+        }
+    }
+}
+
+void orc_update_bfield_cpml_2d(const double *ex, const double *ey, const double *ez, double *bx, double *by, double *bz,
+                               const double *kbx, const double *kby, i64 nx, i64 ny, i64 ng, double dx, double dy, double dt) {
+    const i64 NX = nx + 2 * ng, NY = ny + 2 * ng;
+    for (i64 i = 0; i < nx; i++) {
+        const double efx = dt / kbx[i];
+        for (i64 j = 0; j < ny; j++) {
+            const double efy = dt / kby[j];
+            i64 c = IX2(i, j), xp = IX2(i + 1, j), yp = IX2(i, j + 1);
+            bx[c] -= efy * ((ez[yp] - ez[c]) / dy);
+            by[c] -= efx * (-(ez[xp] - ez[c]) / dx);
+            bz[c] -= efx * ((ey[xp] - ey[c]) / dx) - efy * ((ex[yp] - ex[c]) / dy);
+        }
+    }
+}
+
+/* psi update of one PML face and the correction of the two field components it drives.
+ * axis 0/1/2 = x/y/z.  is_b = 0: E-side (backward difference of B, fac = dt c^2); 1: B-side (forward difference of E,
+ * fac = dt).  f1/f2: the two corrected components, s1/s2 their signs, g1/g2: the differenced source components:
+ *   E: x: (ey,-,bz) (ez,+,by)   y: (ex,+,bz) (ez,-,bx)   z: (ex,-,by) (ey,+,bx)
+ *   B: x: (by,+,ez) (bz,-,ey)   y: (bx,-,ez) (bz,+,ex)   z: (bx,+,ey) (by,-,ex)
+ * psi arrays have the interior shape (nx, ny[, nz]).  kappa/sigma/a: 1-D along the axis. */
+void orc_update_psi(double *f1, double *f2, const double *g1, const double *g2, double *psi1, double *psi2, double s1, double s2,
+                    const double *kappa, const double *sigma, const double *a, i64 axis, i64 is_b, i64 start, i64 stop,
+                    i64 dim, i64 nx, i64 ny, i64 nz, i64 ng, double d, double dt) {
+    const i64 NX = nx + 2 * ng, NY = ny + 2 * ng, NZ = dim == 3 ? nz + 2 * ng : 1;
+    if (dim == 2) nz = 1;
+    const double fac = is_b ? dt : dt * C_LIGHT * C_LIGHT;
+    const i64 n[3] = {nx, ny, nz};
+    for (i64 i = 0; i < nx; i++)
+        for (i64 j = 0; j < ny; j++)
+            for (i64 k = 0; k < nz; k++) {
+                const i64 idx[3] = {i, j, k};
+                const i64 ipos = idx[axis];
+                if (ipos < start || ipos >= stop) continue;
+                const double kap = kappa[ipos], sig = sigma[ipos], ac = a[ipos];
+                const double bcoeff = exp(-(sig / kap + ac) * dt);
+                const double ccoeff = (bcoeff - 1) * sig / kap / (sig + kap * ac) / d;
+                i64 o[3] = {i, j, k};
+                o[axis] += is_b ? 1 : -1;
+                const i64 c = wrapneg(k, NZ) + wrapneg(j, NY) * NZ + wrapneg(i, NX) * NY * NZ;
+                const i64 nb = wrapneg(o[2], NZ) + wrapneg(o[1], NY) * NZ + wrapneg(o[0], NX) * NY * NZ;
+                const i64 pi = k + n[2] * (j + n[1] * i);
+                const double d1 = is_b ? g1[nb] - g1[c] : g1[c] - g1[nb];
+                const double d2 = is_b ? g2[nb] - g2[c] : g2[c] - g2[nb];
+                psi1[pi] = bcoeff * psi1[pi] + ccoeff * d1;
+                psi2[pi] = bcoeff * psi2[pi] + ccoeff * d2;
+                f1[c] += s1 * (fac * psi1[pi]);
+                f2[c] += s2 * (fac * psi2[pi]);
+            }
+}

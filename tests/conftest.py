@@ -22,3 +22,15 @@ def golden3d():
 def golden2d():
     import numpy as np
     return np.load(os.path.join(ROOT, "tests", "golden", "ref_step_2d.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_pml3d():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "ref_pml_3d.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_pml2d():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "ref_pml_2d.npz"))

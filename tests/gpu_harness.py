@@ -131,3 +131,54 @@ def compare_split_state_with_golden(engines, grids, g, tag, rtol):
                     worst = max(worst, e)
                     assert e <= rtol, f"particle {a} global patch {gp} spec {s}: {e:.3e}"
     return worst
+
+
+def engine_from_pml_golden(g, tag, with_part=True):
+    """Engine for the open-boundary golden cases (tests/golden/ref_pml_*.npz): neighbour table and shrunk particle boxes
+    from the reference, CPML faces rebuilt with lambdapic_b200.pml from the recorded class names, psi loaded."""
+    import types as _t
+    from lambdapic_b200 import pml as pmlmod
+    dim = int(g["meta/dim"])
+    nx, ny, nz, ng = (int(g[f"meta/{k}"]) for k in ("nx", "ny", "nz", "n_guard"))
+    dx, dy, dz = (float(g[f"meta/{k}"]) for k in ("dx", "dy", "dz"))
+    x0, y0, z0 = g["meta/x0"], g["meta/y0"], g["meta/z0"]
+    npatch, nspec = len(x0), int(g["meta/nspec"])
+    eng = DeviceEngine(dim, npatch, nx, ny, nz, ng, dx, dy, dz, nspec)
+    box = g["meta/boxes"].astype(float).copy()
+    half = np.array([dx, dx, dy, dy, dz if dim == 3 else 0.0, dz if dim == 3 else 0.0]) / 2
+    box += np.array([-1, 1, -1, 1, -1, 1]) * half
+    glob = g["meta/bounds_global"]
+    eng.set_geometry(x0, y0, z0, g["meta/neighbor_ipatch"], box, glob)
+    cls2face = {"PMLXmin": "xmin", "PMLXmax": "xmax", "PMLYmin": "ymin", "PMLYmax": "ymax", "PMLZmin": "zmin", "PMLZmax": "zmax"}
+    fields = _t.SimpleNamespace(nx=nx, ny=ny, dx=dx, dy=dy)
+    if dim == 3:
+        fields.nz, fields.dz = nz, dz
+    inst, names = [], []
+    nmax = max(nx, ny, nz if dim == 3 else 1)
+    for ip in range(npatch):
+        for slot, cname in enumerate(str(g["meta/pml_faces"][ip]).split(",")):
+            if not cname:
+                continue
+            m = pmlmod.FACE_CLASS[cls2face[cname]](fields, thickness=int(g["meta/cpml_thickness"]))
+            inst.append((ip, m.axis, slot, (m.efield_start, m.efield_end, m.bfield_start, m.bfield_end), m.profiles(nmax)))
+            names.append((ip, slot, pmlmod.PSI_NAMES[m.axis]))
+    eng.configure_pml(inst)
+    for e, (ip, slot, nms) in enumerate(names):
+        for r, nm in enumerate(nms):
+            eng.psi_host[e, r] = g[f"{tag}/pml/{ip}/{slot}/{nm}"]
+    eng.psi_names = names
+    for ip in range(npatch):
+        for a in FIELD_ATTRS:
+            eng.field_view(a, ip)[...] = g[f"{tag}/f/{ip}/{a}"]
+    for s in range(nspec):
+        npart = [g[f"{tag}/p/{ip}/{s}/x"].size for ip in range(npatch)]
+        m = eng.alloc_species(s, npart, slack=1.5, min_extra=64, with_part=with_part)
+        for ip in range(npatch):
+            for a in m.attrs:
+                m.view(a, ip)[...] = g[f"{tag}/p/{ip}/{s}/{a}"]
+            m.view("is_dead", ip)[...] = g[f"{tag}/p/{ip}/{s}/is_dead"].astype(bool)
+        eng.configure_sort(s, nx, 1, 1, dx, glob[3] - glob[2], (glob[5] - glob[4]) if dim == 3 else 1.0,
+                           x0 - dx / 2, y0 - dy / 2, z0 - dz / 2)
+    eng.upload_all()
+    meta = dict(dt=float(g["meta/dt"]), q=[float(v) for v in g["meta/q"]], m=[float(v) for v in g["meta/m"]], dim=dim)
+    return eng, meta

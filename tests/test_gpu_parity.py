@@ -206,3 +206,22 @@ def test_three_particle_kernels_agree_on_thermal_plasma(patch):
     del rng
     for eng, _ in views:
         eng.close()
+
+
+@pytest.mark.parametrize("case", ["golden_pml3d", "golden_pml2d"])
+@pytest.mark.parametrize("k", [0, 1, 2])
+def test_cpml_single_step_matches_reference_golden(case, k, request):
+    """Open (CPML) boundaries on the device: fields / currents / particles <= 1e-12, slot order bit-exact, psi arrays
+    <= 1e-12 of their max-abs (the coefficients contain an exp() evaluated on the host)."""
+    g = request.getfixturevalue(case)
+    h = _harness()
+    eng, meta = h.engine_from_pml_golden(g, f"t{k}")
+    rev = [bool(int(g[f"t1/reverse_x/{s}"])) for s in range(eng.nspec)]
+    eng.step(meta["dt"], meta["q"], meta["m"], rev, write_part=True)
+    st = h.host_view(eng, with_sorter=False)
+    assert check_state_against_golden(st, g, f"t{k + 1}", rtol=1e-12, check_sorter=False) <= 1e-12
+    for e, (ip, slot, nms) in enumerate(eng.psi_names):
+        for r, nm in enumerate(nms):
+            ref = g[f"t{k + 1}/pml/{ip}/{slot}/{nm}"]
+            assert rel_err(eng.psi_host[e, r], ref) <= 1e-12, (ip, slot, nm)
+    eng.close()

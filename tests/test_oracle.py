@@ -62,3 +62,36 @@ def test_charge_conservation_known_answer(golden3d):
     expect = sum(st.q[s] * float(p.particles[s].w[~p.particles[s].is_dead].sum()) for p in st.patches for s in range(st.nspec)) / dV
     scale = sum(abs(st.q[s]) * float(p.particles[s].w.sum()) for p in st.patches for s in range(st.nspec)) / dV
     assert abs(total - expect) <= 1e-10 * scale
+
+
+def _psi_worst(st, g, tag):
+    worst = 0.0
+    for ip, p in enumerate(st.patches):
+        for ipml, m in enumerate(p.pml):
+            for nm in m.names["E"] + m.names["B"]:
+                ref = g[f"{tag}/pml/{ip}/{ipml}/{nm}"]
+                worst = max(worst, float(np.abs(getattr(m, nm) - ref).max()) / max(float(np.abs(ref).max()), 1e-300))
+    return worst
+
+
+@pytest.mark.parametrize("case", ["golden_pml3d", "golden_pml2d"])
+@pytest.mark.parametrize("k", [0, 1, 2])
+def test_cpml_port_matches_reference(case, k, request):
+    """Open boundaries: kappa-scaled FDTD, psi currents, shrunk particle boxes, leavers without neighbour
+    (core/boundary/cpml.py) against the unmodified reference's dumps; psi arrays bit-exact."""
+    g = request.getfixturevalue(case)
+    st = _load(g, k)
+    orc.step(st, "port")
+    assert check_state_against_golden(st, g, f"t{k + 1}", rtol=1e-13, check_sorter=False) < 1e-13
+    assert _psi_worst(st, g, f"t{k + 1}") == 0.0
+
+
+@pytest.mark.skipif(not orc.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("case", ["golden_pml3d", "golden_pml2d"])
+def test_cpml_with_reference_extensions_bit_exact(case, request):
+    g = request.getfixturevalue(case)
+    st = _load(g, 0)
+    for k in range(3):
+        orc.step(st, "ref")
+        assert check_state_against_golden(st, g, f"t{k + 1}", rtol=0.0, check_sorter=False) == 0.0
+        assert _psi_worst(st, g, f"t{k + 1}") == 0.0
