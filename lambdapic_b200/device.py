@@ -50,6 +50,25 @@ class DeviceBridge:
         rank = ps[0].rank or 0
         self.engine.set_geometry(x0, y0, z0, nbr, box, glob, rank, np.array([p.index for p in ps], dtype=np.int64))
 
+    # ---- CPML --------------------------------------------------------------------------------------------------
+    def configure_pml(self):
+        """Register every patch's PML faces with the device (after Simulation._init_pml) and seat their psi arrays."""
+        from .pml import PSI_NAMES
+        eng, ps = self.engine, self.patches
+        nmax = max(eng.nx, eng.ny, eng.nz)
+        inst, owners = [], []
+        for ip, p in enumerate(ps):
+            for slot, m in enumerate(p.pml_boundary):
+                inst.append((ip, m.axis, slot, (m.efield_start, m.efield_end, m.bfield_start, m.bfield_end), m.profiles(nmax)))
+                owners.append(m)
+        old = [[np.array(getattr(m, nm)) for nm in PSI_NAMES[m.axis]] for m in owners]
+        eng.configure_pml(inst)
+        for e, m in enumerate(owners):
+            for r, nm in enumerate(PSI_NAMES[m.axis]):
+                eng.psi_host[e, r] = old[e][r]
+                setattr(m, nm, eng.psi_host[e, r])
+        self._set_geometry()  # particle boxes shrink by the PML thickness
+
     # ---- species -----------------------------------------------------------------------------------------------
     def _recreate_engine_species(self):
         """(Re)allocate the device arenas from the host particle objects (all species)."""
@@ -66,6 +85,8 @@ class DeviceBridge:
             for ip, p in enumerate(ps):
                 for a in FIELD_ATTRS:
                     setattr(p.fields, a, eng.field_view(a, ip))
+            if any(p.pml_boundary for p in ps):
+                self.configure_pml()
         for s in range(nspec):
             self._alloc_species_from_host(s)
 
@@ -142,6 +163,7 @@ class DeviceBridge:
                         self._host_only_part_fields(pt)
                 pt._npart_created = int(eng.npart_created[s][ip])
         eng.download_fields(ALL_FIELDS)
+        eng.download_psi()
         self.stats["downloads"] += 1
         self.stats["d2h_bytes"] += self.state_bytes()
 
@@ -151,6 +173,8 @@ class DeviceBridge:
         for s in range(eng.nspec):
             m = eng.species[s]
             n += m.total * (8 * len(m.attrs) + 1)
+        if getattr(eng, "psi_host", None) is not None:
+            n += eng.psi_host.nbytes
         return int(n)
 
     @contextmanager

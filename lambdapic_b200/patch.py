@@ -56,13 +56,20 @@ class Patch:
         self.pml_boundary = []
         self.fields = None
 
-    # particle box of the patch (core/patch/patch.py:105-148; no PML shrink on the periodic path)
-    xmin = property(lambda s: s.x0)
-    xmax = property(lambda s: s.x0 + (s.nx - 1) * s.dx)
-    ymin = property(lambda s: s.y0)
-    ymax = property(lambda s: s.y0 + (s.ny - 1) * s.dy)
-    zmin = property(lambda s: s.z0)
-    zmax = property(lambda s: s.z0 + (s.nz - 1) * s.dz)
+    # particle box of the patch; a CPML face shrinks it by its thickness (core/patch/patch.py:105-148)
+    def _pml_cells(self, face):
+        return next((m.thickness for m in self.pml_boundary if m.face == face), 0)
+    xmin = property(lambda s: s.x0 + s._pml_cells("xmin") * s.dx)
+    xmax = property(lambda s: s.x0 + (s.nx - 1) * s.dx - s._pml_cells("xmax") * s.dx)
+    ymin = property(lambda s: s.y0 + s._pml_cells("ymin") * s.dy)
+    ymax = property(lambda s: s.y0 + (s.ny - 1) * s.dy - s._pml_cells("ymax") * s.dy)
+    zmin = property(lambda s: s.z0 + s._pml_cells("zmin") * s.dz)
+    zmax = property(lambda s: s.z0 + (s.nz - 1) * s.dz - s._pml_cells("zmax") * s.dz)
+
+    def add_pml_boundary(self, pml) -> None:
+        """core/patch/patch.py:185-187, 291-298, 382-386: at most one face per axis."""
+        assert all(m.axis != pml.axis for m in self.pml_boundary), "a patch cannot hold two PML faces of one axis; use more patches"
+        self.pml_boundary.append(pml)
 
     def add_particles(self, particles: ParticlesBase) -> None:
         self.particles.append(particles)

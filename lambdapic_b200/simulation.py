@@ -136,9 +136,8 @@ class Simulation:
             if (bc[f"{a}min"] == "periodic") != (bc[f"{a}max"] == "periodic"):
                 raise ValueError(f"{a}min and {a}max must both be periodic")
         self.boundary_conditions = bc
-        if any(v == "pml" for v in bc.values()):
-            raise NotImplementedError("CPML boundaries are the next tier of the B200 path (SURVEY.md 8(f)-1); "
-                                      "this build accelerates periodic domains only")
+        if not isinstance(self.cpml_thickness, (int, np.integer)) or self.cpml_thickness < 1:
+            raise ValueError("cpml_thickness must be a positive integer")
 
     def __post_init__(self):
         self.stages = list(self.STAGES)
@@ -179,7 +178,25 @@ class Simulation:
     # ---- initialisation (simulation.py:284-423) -----------------------------------------------------------------
     def _grid(self, rank, size):
         return make_patch_grid(2, self.npatch_x, self.npatch_y, 1, self.nx_per_patch, self.ny_per_patch, 1,
-                               self.dx, self.dy, 0.0, self.n_guard, (True, True, True), rank, size)
+                               self.dx, self.dy, 0.0, self.n_guard, self._periodic(), rank, size)
+
+    def _periodic(self):
+        bc = self.boundary_conditions
+        return tuple(bc.get(f"{a}min", "periodic") == "periodic" for a in "xyz")
+
+    def _init_pml(self):
+        """CPML faces for the patches on a non-periodic domain edge, in the reference's order xmin, xmax, ymin, ymax
+        (, zmin, zmax) (simulation.py:450-464)."""
+        from .pml import FACE_CLASS
+        npatch = {"x": self.npatch_x, "y": self.npatch_y, "z": getattr(self, "npatch_z", 1)}
+        for p in self.patches:
+            for ax in self._axes():
+                idx = getattr(p, f"ipatch_{ax}")
+                for side, edge in (("min", 0), ("max", npatch[ax] - 1)):
+                    if idx == edge and self.boundary_conditions[f"{ax}{side}"] == "pml":
+                        p.add_pml_boundary(FACE_CLASS[f"{ax}{side}"](p.fields, thickness=self.cpml_thickness))
+        if any(p.pml_boundary for p in self.patches):
+            self.bridge.configure_pml()
 
     def create_patches(self, grid) -> Patches:
         patches = Patches(self.dimension)
@@ -210,6 +227,7 @@ class Simulation:
             self.mpi = MultiRankMPI(self, comm)
         else:
             self.mpi = SingleRankMPI(comm)
+        self._init_pml()
         for s in self.species:
             self.patches.add_species(s, aux_attrs=s._aux_attrs)
         # simulation.py:700-716: seed -> default_rng(seed).spawn(size)[rank]
@@ -462,7 +480,7 @@ class Simulation3D(Simulation):
 
     def _grid(self, rank, size):
         return make_patch_grid(3, self.npatch_x, self.npatch_y, self.npatch_z, self.nx_per_patch, self.ny_per_patch,
-                               self.nz_per_patch, self.dx, self.dy, self.dz, self.n_guard, (True, True, True), rank, size)
+                               self.nz_per_patch, self.dx, self.dy, self.dz, self.n_guard, self._periodic(), rank, size)
 
     def create_patches(self, grid) -> Patches:
         patches = Patches(3)

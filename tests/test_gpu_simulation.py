@@ -134,3 +134,58 @@ def test_device_side_diagnostics_skip_mirror_sync(golden2d):
     assert abs(seen[-1]["electric"] - 0.5 * eps0 * e2 * sim.dx * sim.dy) <= 1e-12 * seen[-1]["electric"]
     assert set(seen[-1]) == {"electric", "magnetic", "electron", "proton"}
     sim.bridge.close()
+
+
+@pytest.mark.parametrize("dim,case", [(3, "golden_pml3d"), (2, "golden_pml2d")])
+def test_public_api_with_cpml_boundaries_matches_reference(dim, case, request):
+    """The script of oracle/make_golden.py:run_pml_case run on lambdapic_b200: CPML on every side, patches at the edge own
+    up to three faces, particle boxes shrink by the layer thickness, leavers without neighbour are killed."""
+    from lambdapic_b200 import Electron, Proton, Simulation, Simulation3D, callback
+    from lambdapic_b200.pml import PSI_NAMES
+    g = request.getfixturevalue(case)
+    d, n0 = 0.8e-6 / 20, 1.742e27
+    if dim == 3:
+        sim = Simulation3D(nx=16, ny=16, nz=18, dx=d, dy=d * 1.25, dz=d * 0.8, npatch_x=2, npatch_y=2, npatch_z=2, dt_cfl=0.95,
+                           boundary_conditions={k: "pml" for k in ("xmin", "xmax", "ymin", "ymax", "zmin", "zmax")},
+                           cpml_thickness=6, random_seed=777)
+        dens = lambda x, y, z: n0  # noqa: E731
+    else:
+        sim = Simulation(nx=32, ny=24, dx=d, dy=d * 1.25, npatch_x=2, npatch_y=2, dt_cfl=0.95,
+                         boundary_conditions={k: "pml" for k in ("xmin", "xmax", "ymin", "ymax")}, cpml_thickness=6, random_seed=778)
+        dens = lambda x, y: n0  # noqa: E731
+    sim.add_species([Electron(density=dens, ppc=2), Proton(density=dens, ppc=1)])
+
+    @callback("init")
+    def seed(sim):  # same statements as oracle/make_golden.py:run_pml_case.seed
+        rng = np.random.default_rng(5)
+        for p in sim.patches:
+            for isp, part in enumerate(p.particles):
+                n = part.npart
+                sig = 0.4 if isp == 0 else 0.03
+                part.ux[:] = rng.normal(0.1 if isp == 0 else -0.01, sig, n)
+                part.uy[:] = rng.normal(0.0, sig, n)
+                part.uz[:] = rng.normal(0.0, sig, n)
+                part.inv_gamma[:] = 1.0 / np.sqrt(1 + part.ux**2 + part.uy**2 + part.uz**2)
+            f = p.fields
+            for a, amp in (("ex", 3e11), ("ey", -2e11), ("ez", 1e11), ("bx", 500.0), ("by", -800.0), ("bz", 300.0)):
+                arr = getattr(f, a)
+                arr[...] = amp * rng.standard_normal(arr.shape)
+    seen = {}
+
+    @callback("start")
+    def at_start(sim):
+        if "t0" not in seen:
+            seen["t0"] = check_state_against_golden(types.SimpleNamespace(patches=sim.patches, sorters=None), g, "t0", rtol=0.0,
+                                                    check_sorter=False)
+    for it in range(3):
+        sim.run(nsteps=1, callbacks=[seed, at_start] if it == 0 else [at_start])
+        worst = check_state_against_golden(types.SimpleNamespace(patches=sim.patches, sorters=None), g, f"t{it + 1}",
+                                           rtol=1e-12 if it == 0 else 1e-11, check_sorter=False)
+        for ip, p in enumerate(sim.patches):
+            assert ",".join(type(m).__name__ for m in p.pml_boundary) == str(g["meta/pml_faces"][ip])
+            for ipml, m in enumerate(p.pml_boundary):
+                for nm in PSI_NAMES[m.axis]:
+                    ref = g[f"t{it + 1}/pml/{ip}/{ipml}/{nm}"]
+                    assert np.abs(getattr(m, nm) - ref).max() <= 1e-11 * max(np.abs(ref).max(), 1e-300), (ip, nm)
+    assert seen["t0"] == 0.0 and worst <= 1e-11
+    sim.bridge.close()

@@ -55,8 +55,12 @@ def test_config_validation():
         Simulation(nx=10, ny=8, dx=D, dy=D, npatch_x=3, npatch_y=2, boundary_conditions=per)
     with pytest.raises(ValueError):
         Simulation(nx=16, ny=16, dx=D, dy=D, npatch_x=2, npatch_y=2, nsteps=1, sim_time=1e-15, boundary_conditions=per)
-    with pytest.raises(NotImplementedError):
-        Simulation(nx=16, ny=16, dx=D, dy=D, npatch_x=2, npatch_y=2)  # default boundaries are PML: next tier
+    sim = Simulation(nx=16, ny=16, dx=D, dy=D, npatch_x=2, npatch_y=2)  # default boundaries: CPML on every side
+    assert sim._periodic()[:2] == (False, False) and sim.cpml_thickness == 6
+    grid = sim._grid(0, 1)
+    assert (grid.neighbor_ipatch[0] >= 0).sum() == 3  # a corner patch of an open 2x2 domain keeps 3 neighbours
+    with pytest.raises(ValueError):
+        Simulation(nx=16, ny=16, dx=D, dy=D, npatch_x=2, npatch_y=2, boundary_conditions={"xmin": "periodic", "xmax": "pml"})
     sim = Simulation(nx=64, ny=32, dx=D, dy=D, boundary_conditions=per)
     assert sim.npatch_x == 4 and sim.npatch_y == 2  # auto patching: 16-cell tiles
     assert sim.STAGES[0] == "init" and sim.DEFAULT_STAGE == "end" and len(sim.STAGES) == 14
