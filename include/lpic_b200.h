@@ -106,6 +106,12 @@ int64_t lpic_pml_psi_words(const lpic_ctx *ctx);
 int lpic_pml_upload_psi(lpic_ctx *ctx, const double *host);
 int lpic_pml_download_psi(lpic_ctx *ctx, double *host);
 
+/* ---- laser antenna at xmin (callback/laser.py:17-77, 171-186, 218-241): rewrites B at the plane laserpos-1 of the listed
+ *      (xmin edge) patches from per-patch source planes.  ranges: (n, 4) = iy_start, iy_end, iz_start, iz_end (interior
+ *      minus the transverse PML); ey_src / ez_src: (n, NY[, NZ]) host arrays in the padded, wrapped layout of one x-plane. */
+int lpic_laser_bfields(lpic_ctx *ctx, int64_t laserpos, int64_t n, const int64_t *patches, const int64_t *ranges,
+                       const double *ey_src, const double *ez_src, double dt);
+
 /* ---- guard cells: core/patch/sync_fields3d.c:350-620 / :84-348, sync_fields2d.c:150-255 / :43-148;
  *      facade core/patch/patch.py:670-703.  attr_mask: bit a = field attribute a. */
 int lpic_sync_guard_fields(lpic_ctx *ctx, uint32_t attr_mask);

@@ -53,6 +53,7 @@ SIGNATURES = {
     "lpic_pml_psi_words": (_i64, [_vp]),
     "lpic_pml_upload_psi": (_int, [_vp, _vp]),
     "lpic_pml_download_psi": (_int, [_vp, _vp]),
+    "lpic_laser_bfields": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _dbl]),
     "lpic_sync_guard_fields": (_int, [_vp, _u32]),
     "lpic_sync_currents": (_int, [_vp]),
     "lpic_reset_currents": (_int, [_vp]),

@@ -190,6 +190,49 @@ __global__ void __launch_bounds__(256) k_pml_psi(Geom g, double *__restrict__ F,
     base[c2 * stride + o] = __dadd_rn(base[c2 * stride + o], __dmul_rn(s2, __dmul_rn(fac, p2)));
 }
 
+// Laser antenna (callback/laser.py:17-77): one thread per (listed patch, y, z) of the antenna plane.  Every product and sum
+// is an explicit intrinsic in the reference's left-to-right order, so the result is bit-identical to the numba kernel.
+__global__ void __launch_bounds__(128) k_laser(Geom g, double *__restrict__ F, const int *__restrict__ patches, const int *__restrict__ ranges,
+                                               const double *__restrict__ ey_src, const double *__restrict__ ez_src, int laserpos,
+                                               double dt) {
+    const int e = blockIdx.y;
+    const int p = patches[e];
+    const int *rg = ranges + 4 * e;
+    const int plane = g.NY * g.NZ;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= plane) return;
+    const int sk = t % g.NZ, sj = t / g.NZ;
+    const int iy = sj < g.ny + g.ng ? sj : sj - g.NY, iz = sk < g.nz + g.ngz ? sk : sk - g.NZ;  // logical indices
+    if (iy < rg[0] || iy >= rg[1]) return;
+    const size_t stride = (size_t)g.npatch * g.ncell;
+    double *base = F + (size_t)p * g.ncell;
+    const double *ey = base + LPIC_EY * stride, *ez = base + LPIC_EZ * stride, *jy = base + LPIC_JY * stride, *jz = base + LPIC_JZ * stride;
+    double *bx = base + LPIC_BX * stride, *by = base + LPIC_BY * stride, *bz = base + LPIC_BZ * stride;
+    // bx[laserpos-1, iy, :] = bx[0, iy, :]  -- the whole padded z row
+    bx[sidx(g, laserpos - 1, iy, 0) + sk] = bx[sidx(g, 0, iy, 0) + sk];
+    if (g.dim == 3 && (iz < rg[2] || iz >= rg[3])) return;
+    if (g.dim == 2 && sk != 0) return;
+    const double c = LPIC_C_LIGHT;
+    const int o0 = sidx(g, 0, iy, iz), om = sidx(g, -1, iy, iz), ol = sidx(g, laserpos, iy, iz), ot = sidx(g, laserpos - 1, iy, iz);
+    const double cdtdx = __ddiv_rn(__dmul_rn(c, dt), g.dx);
+    const double inv = __ddiv_rn(1.0, __dmul_rn(__dadd_rn(cdtdx, 1.0), c));
+    const double dteps = __ddiv_rn(dt, LPIC_EPS0), dtc2 = __dmul_rn(dt, __dmul_rn(c, c)), back = __dmul_rn(__dsub_rn(cdtdx, 1.0), c);
+    const double half_c = __dmul_rn(c, 0.5);
+    const size_t s = (size_t)e * plane + t;
+    double vz = __dadd_rn(__dmul_rn(4.0, ey_src[s]), __dmul_rn(2.0, __dadd_rn(ey[o0], __dmul_rn(half_c, __dadd_rn(bz[o0], bz[om])))));
+    vz = __dsub_rn(vz, __dmul_rn(2.0, ey[ol]));
+    if (g.dim == 3) vz = __dsub_rn(vz, __ddiv_rn(__dmul_rn(dtc2, __dsub_rn(bx[ol], bx[sidx(g, laserpos, iy, iz - 1)])), g.dz));
+    vz = __dadd_rn(vz, __dmul_rn(dteps, jy[ol]));
+    vz = __dadd_rn(vz, __dmul_rn(back, bz[ol]));
+    double vy = __dsub_rn(__dmul_rn(-4.0, ez_src[s]), __dmul_rn(2.0, __dsub_rn(ez[o0], __dmul_rn(half_c, __dadd_rn(by[o0], by[om])))));
+    vy = __dadd_rn(vy, __dmul_rn(2.0, ez[ol]));
+    vy = __dsub_rn(vy, __ddiv_rn(__dmul_rn(dtc2, __dsub_rn(bx[ol], bx[sidx(g, laserpos, iy - 1, iz)])), g.dy));
+    vy = __dsub_rn(vy, __dmul_rn(dteps, jz[ol]));
+    vy = __dadd_rn(vy, __dmul_rn(back, by[ol]));
+    bz[ot] = __dmul_rn(inv, vz);
+    by[ot] = __dmul_rn(inv, vy);
+}
+
 // storage index -> logical index along one axis
 __device__ __forceinline__ int logical(int s, int n, int ng) { return s < n + ng ? s : s - (n + 2 * ng); }
 
@@ -517,5 +560,35 @@ extern "C" int lpic_pml_download_psi(lpic_ctx *c, double *host) {
     if (!c->pml) return 0;
     CUDA_TRY(cudaMemcpyAsync(host, c->pml->d_psi, sizeof(double) * (size_t)lpic_pml_psi_words(c), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int lpic_laser_bfields(lpic_ctx *c, int64_t laserpos, int64_t n, const int64_t *patches, const int64_t *ranges,
+                                  const double *ey_src, const double *ez_src, double dt) {
+    const Geom &g = c->g;
+    if (n <= 0) return 0;
+    REQUIRE(laserpos >= 1 && laserpos < g.nx, "laserpos %lld outside the patch", (long long)laserpos);
+    const size_t plane = (size_t)g.NY * g.NZ;
+    std::vector<int> hp(n), hr(4 * n);
+    for (i64 e = 0; e < n; e++) {
+        REQUIRE(patches[e] >= 0 && patches[e] < g.npatch, "bad patch in the laser list");
+        hp[e] = (int)patches[e];
+        for (int r = 0; r < 4; r++) hr[4 * e + r] = (int)ranges[4 * e + r];
+    }
+    int *d_i = nullptr;
+    double *d_s = nullptr;
+    CUDA_TRY(cudaMalloc(&d_i, sizeof(int) * 5 * n));
+    CUDA_TRY(cudaMalloc(&d_s, sizeof(double) * 2 * n * plane));
+    CUDA_TRY(cudaMemcpyAsync(d_i, hp.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_i + n, hr.data(), sizeof(int) * 4 * n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_s, ey_src, sizeof(double) * n * plane, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_s + n * plane, ez_src, sizeof(double) * n * plane, cudaMemcpyHostToDevice, c->stream));
+    dim3 grid(div_up((i64)plane, 128), (unsigned)n);
+    k_laser<<<grid, 128, 0, c->stream>>>(g, c->fields, d_i, d_i + n, d_s, d_s + n * plane, (int)laserpos, dt);
+    LAUNCHED(1);
+    KERNEL_CHECK();
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    cudaFree(d_i);
+    cudaFree(d_s);
     return 0;
 }

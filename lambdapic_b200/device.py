@@ -210,5 +210,9 @@ class DeviceBridge:
                         p.particles[s].extended = True
         return total
 
+    def laser_bfields(self, laserpos, patches, ranges, ey_src, ez_src, dt):
+        with self.coherent():
+            self.engine.laser_bfields(laserpos, patches, ranges, ey_src, ez_src, dt)
+
     def close(self):
         self.engine.close()

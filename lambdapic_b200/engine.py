@@ -279,6 +279,15 @@ class DeviceEngine:
     def deposit(self, ispec, dt, q):
         check(self.L.lpic_deposit(self.ctx, ispec, float(dt), float(q)))
 
+    def laser_bfields(self, laserpos, patches, ranges, ey_src, ez_src, dt):
+        """Laser antenna at xmin for the listed edge patches; ey_src / ez_src: (n, NY[, NZ]) in the padded layout."""
+        i64 = lambda a: np.ascontiguousarray(a, dtype=np.int64)  # noqa: E731
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
+        patches, ranges, ey_src, ez_src = i64(patches), i64(ranges), f64(ey_src), f64(ez_src)
+        assert ey_src.shape == (len(patches),) + self.shape[1:] == ez_src.shape
+        check(self.L.lpic_laser_bfields(self.ctx, int(laserpos), len(patches), _ptr(patches), _ptr(ranges), _ptr(ey_src),
+                                        _ptr(ez_src), float(dt)))
+
     def weighted_drift(self, ispec):
         out = np.zeros(2)
         check(self.L.lpic_weighted_drift(self.ctx, ispec, _ptr(out)))
@@ -383,7 +392,7 @@ class DeviceEngine:
     def record_event(self, slot):
         check(self.L.lpic_event_record(self.ctx, int(slot)))
 
-    def step(self, dt, q, m, reverse_x, write_part=False, event_slot=None):
+    def step(self, dt, q, m, reverse_x, write_part=False, event_slot=None, laser=None):
         self.update_efield(0.5 * dt); self.sync_guard_fields(E_MASK)
         self.update_bfield(0.5 * dt); self.sync_guard_fields(B_MASK)
         nbuf = [self.sort(s, reverse_x[s]) for s in range(self.nspec)]
@@ -396,6 +405,9 @@ class DeviceEngine:
                 self.record_event(event_slot + 2 * s + 1)
         self.sync_currents()
         mig = [self.sync_particles(s) for s in range(self.nspec)]
-        self.update_bfield(0.5 * dt); self.sync_guard_fields(B_MASK)
+        self.update_bfield(0.5 * dt)
+        if laser is not None:  # stage `_laser` (simulation.py:1098-1103): (laserpos, patches, ranges, ey_src, ez_src)
+            self.laser_bfields(*laser, dt)
+        self.sync_guard_fields(B_MASK)
         self.update_efield(0.5 * dt); self.sync_guard_fields(E_MASK)
         return nbuf, mig

@@ -549,7 +549,26 @@ def update_lists(st: OState):
             p.particles[s].extended = False
 
 
-def step(st: OState, backend="port"):
+def laser_stage(st: OState, sources, laserpos):
+    """Stage `_laser` (callback/laser.py:109-137, 171-186, 218-241): rewrite B at the antenna plane of the xmin edge
+    patches from the given source planes.  sources: {ipatch: (ey_src, ez_src)} shaped like one padded x-plane."""
+    L = lib()
+    for ip, (ey_s, ez_s) in sources.items():
+        p = st.patches[ip]
+        f = p.fields
+        iy0, iy1, iz0, iz1 = 0, st.ny, 0, st.nz
+        for m in p.pml:
+            if m.face == "ymin": iy0 = m.thickness
+            if m.face == "ymax": iy1 = st.ny - m.thickness
+            if m.face == "zmin": iz0 = m.thickness
+            if m.face == "zmax": iz1 = st.nz - m.thickness
+        ey_s, ez_s = np.ascontiguousarray(ey_s, dtype=np.float64), np.ascontiguousarray(ez_s, dtype=np.float64)
+        L.orc_laser_bfields(*[_p(getattr(f, a)) for a in FIELD_ATTRS[:9]], _c_i64(st.dim), _c_i64(st.nx), _c_i64(st.ny), _c_i64(st.nz),
+                            _c_i64(st.ng), _c_dbl(st.dx), _c_dbl(st.dy), _c_dbl(st.dz), _c_dbl(st.dt), _c_i64(laserpos),
+                            _c_i64(iy0), _c_i64(iy1), _c_i64(iz0), _c_i64(iz1), _p(ey_s), _p(ez_s))
+
+
+def step(st: OState, backend="port", laser=None):
     """One full PIC step, simulation/simulation.py:937-1130 (periodic, unified pusher, no callbacks)."""
     dt = st.dt
     E, B = ("ex", "ey", "ez"), ("bx", "by", "bz")
@@ -563,5 +582,8 @@ def step(st: OState, backend="port"):
     sync_currents(st, backend)
     sync_particles(st, backend)
     update_lists(st)
-    update_bfield(st, 0.5 * dt); sync_guard_fields(st, B, backend)
+    update_bfield(st, 0.5 * dt)
+    if laser is not None:  # stage `_laser` sits between the B update and its guard sync (simulation.py:1098-1103)
+        laser_stage(st, *laser)
+    sync_guard_fields(st, B, backend)
     update_efield(st, 0.5 * dt); sync_guard_fields(st, E, backend)

@@ -691,3 +691,36 @@ void orc_update_psi(double *f1, double *f2, const double *g1, const double *g2, 
                 f2[c] += s2 * (fac * psi2[pi]);
             }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Laser antenna at xmin: B at the plane laserpos-1 of an xmin edge patch is rewritten from the source fields.
+ * callback/laser.py:17-45 (2D), :47-77 (3D).  Expression order as the reference (numba, no contraction).
+ * ey_src / ez_src have the shape of one x-plane of the padded grid: (NY) or (NY, NZ), wrapped indexing.
+ * ---------------------------------------------------------------------------------------------- */
+void orc_laser_bfields(const double *ex, const double *ey, const double *ez, double *bx, double *by, double *bz,
+                       const double *jx, const double *jy, const double *jz, i64 dim, i64 nx, i64 ny, i64 nz, i64 ng,
+                       double dx, double dy, double dz, double dt, i64 laserpos, i64 iy0, i64 iy1, i64 iz0, i64 iz1,
+                       const double *ey_src, const double *ez_src) {
+    const double c = C_LIGHT, eps0 = 8.8541878188e-12;
+    const i64 NX = nx + 2 * ng, NY = ny + 2 * ng, NZ = dim == 3 ? nz + 2 * ng : 1;
+    if (dim == 2) { iz0 = 0; iz1 = 1; }
+    for (i64 iy = iy0; iy < iy1; iy++) /* bx[laserpos-1, iy, :] = bx[0, iy, :] (the whole padded z row in 3D) */
+        for (i64 sk = 0; sk < NZ; sk++)
+            bx[sk + NZ * (wrapneg(iy, NY) + NY * wrapneg(laserpos - 1, NX))] = bx[sk + NZ * (wrapneg(iy, NY) + NY * 0)];
+    const double inv = 1 / ((c * dt / dx + 1) * c);
+    for (i64 iy = iy0; iy < iy1; iy++)
+        for (i64 iz = iz0; iz < iz1; iz++) {
+#define AT(i, j, k) (wrapneg(k, NZ) + NZ * (wrapneg(j, NY) + NY * wrapneg(i, NX)))
+            const i64 s = wrapneg(iz, NZ) + NZ * wrapneg(iy, NY);
+            const i64 o0 = AT(0, iy, iz), om = AT(-1, iy, iz), ol = AT(laserpos, iy, iz), ot = AT(laserpos - 1, iy, iz);
+            double vz = 4 * ey_src[s] + 2 * (ey[o0] + c * 0.5 * (bz[o0] + bz[om])) - 2 * ey[ol];
+            if (dim == 3) vz = vz - (dt * (c * c)) * (bx[ol] - bx[AT(laserpos, iy, iz - 1)]) / dz;
+            vz = vz + dt / eps0 * jy[ol] + (c * dt / dx - 1) * c * bz[ol];
+            double vy = -4 * ez_src[s] - 2 * (ez[o0] - c * 0.5 * (by[o0] + by[om])) + 2 * ez[ol] -
+                        (dt * (c * c)) * (bx[ol] - bx[AT(laserpos, iy - 1, iz)]) / dy - dt / eps0 * jz[ol] +
+                        (c * dt / dx - 1) * c * by[ol];
+            bz[ot] = inv * vz;
+            by[ot] = inv * vy;
+#undef AT
+        }
+}

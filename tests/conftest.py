@@ -34,3 +34,15 @@ def golden_pml3d():
 def golden_pml2d():
     import numpy as np
     return np.load(os.path.join(ROOT, "tests", "golden", "ref_pml_2d.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_laser3d():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "ref_laser_3d.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_laser2d():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "ref_laser_2d.npz"))

@@ -189,3 +189,51 @@ def test_public_api_with_cpml_boundaries_matches_reference(dim, case, request):
                     assert np.abs(getattr(m, nm) - ref).max() <= 1e-11 * max(np.abs(ref).max(), 1e-300), (ip, nm)
     assert seen["t0"] == 0.0 and worst <= 1e-11
     sim.bridge.close()
+
+
+@pytest.mark.parametrize("dim,case,nsteps", [(3, "golden_laser3d", 2), (2, "golden_laser2d", 3)])
+def test_public_api_laser_into_cpml_box_matches_reference(dim, case, nsteps, request):
+    """BASELINE.json configs[1]/[3] in miniature: CPML box, plasma, and a laser antenna at xmin built from the same
+    SimpleLaser + (Laguerre-)Gaussian combination as the reference run; the laser callback runs device-side
+    (needs_host=False), so no mirror traffic is caused by the per-step `_laser` stage."""
+    from lambdapic_b200 import Electron, Proton, Simulation, Simulation3D, callback
+    from tests.test_laser_sources import golden_laser
+    g = request.getfixturevalue(case)
+    d, n0 = 0.8e-6 / 20, 1.742e27
+    if dim == 3:
+        sim = Simulation3D(nx=16, ny=16, nz=18, dx=d, dy=d * 1.25, dz=d * 0.8, npatch_x=2, npatch_y=2, npatch_z=2, dt_cfl=0.95,
+                           boundary_conditions={k: "pml" for k in ("xmin", "xmax", "ymin", "ymax", "zmin", "zmax")},
+                           cpml_thickness=6, random_seed=777)
+        dens = lambda x, y, z: n0  # noqa: E731
+    else:
+        sim = Simulation(nx=32, ny=24, dx=d, dy=d * 1.25, npatch_x=2, npatch_y=2, dt_cfl=0.95,
+                         boundary_conditions={k: "pml" for k in ("xmin", "xmax", "ymin", "ymax")}, cpml_thickness=6, random_seed=778)
+        dens = lambda x, y: n0  # noqa: E731
+    sim.add_species([Electron(density=dens, ppc=2), Proton(density=dens, ppc=1)])
+
+    @callback("init")
+    def seed(sim):
+        rng = np.random.default_rng(5)
+        for p in sim.patches:
+            for isp, part in enumerate(p.particles):
+                n = part.npart
+                sig = 0.4 if isp == 0 else 0.03
+                part.ux[:] = rng.normal(0.1 if isp == 0 else -0.01, sig, n)
+                part.uy[:] = rng.normal(0.0, sig, n)
+                part.uz[:] = rng.normal(0.0, sig, n)
+                part.inv_gamma[:] = 1.0 / np.sqrt(1 + part.ux**2 + part.uy**2 + part.uz**2)
+            f = p.fields
+            for a, amp in (("ex", 3e11), ("ey", -2e11), ("ez", 1e11), ("bx", 500.0), ("by", -800.0), ("bz", 300.0)):
+                arr = getattr(f, a)
+                arr[...] = amp * rng.standard_normal(arr.shape)
+    laser = golden_laser(dim)
+    sim.initialize()
+    before = dict(sim.bridge.stats)
+    for it in range(nsteps):
+        sim.run(nsteps=1, callbacks=[seed, laser] if it == 0 else [laser])
+        worst = check_state_against_golden(types.SimpleNamespace(patches=sim.patches, sorters=None), g, f"t{it + 1}",
+                                           rtol=1e-12 if it == 0 else 1e-11, check_sorter=False)
+    assert worst <= 1e-11
+    st = sim.bridge.stats
+    assert st["uploads"] - before["uploads"] == nsteps and st["downloads"] - before["downloads"] == nsteps  # run entry/exit only
+    sim.bridge.close()

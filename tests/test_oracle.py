@@ -95,3 +95,22 @@ def test_cpml_with_reference_extensions_bit_exact(case, request):
         orc.step(st, "ref")
         assert check_state_against_golden(st, g, f"t{k + 1}", rtol=0.0, check_sorter=False) == 0.0
         assert _psi_worst(st, g, f"t{k + 1}") == 0.0
+
+
+def _laser_sources(g, k, npatch):
+    return {ip: (g[f"src/{k}/{ip}/ey"], g[f"src/{k}/{ip}/ez"]) for ip in range(npatch) if f"src/{k}/{ip}/ey" in g.files}
+
+
+@pytest.mark.parametrize("case,nsteps", [("golden_laser3d", 2), ("golden_laser2d", 3)])
+def test_laser_antenna_port_and_reference_extensions(case, nsteps, request):
+    """Stage `_laser` (callback/laser.py:17-77) restated in C, fed with the reference's own source planes: bit-exact with
+    the reference extensions as back-end, <= 1e-13 with the C port of the particle path."""
+    g = request.getfixturevalue(case)
+    lp = int(g["meta/cpml_thickness"]) + 2
+    for backend, rtol in (("port", 1e-13), ("ref", 0.0)):
+        if backend == "ref" and not orc.have_ref():
+            continue
+        for k in range(nsteps):
+            st = _load(g, k)
+            orc.step(st, backend, laser=(_laser_sources(g, k, len(st.patches)), lp))
+            assert check_state_against_golden(st, g, f"t{k + 1}", rtol=rtol, check_sorter=False) <= rtol
