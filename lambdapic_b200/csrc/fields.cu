@@ -567,7 +567,7 @@ extern "C" int lpic_laser_bfields(lpic_ctx *c, int64_t laserpos, int64_t n, cons
                                   const double *ey_src, const double *ez_src, double dt) {
     const Geom &g = c->g;
     if (n <= 0) return 0;
-    REQUIRE(laserpos >= 1 && laserpos < g.nx, "laserpos %lld outside the patch", (long long)laserpos);
+    REQUIRE(laserpos >= 1 && laserpos < g.nx + g.ng, "laserpos %lld outside the padded patch", (long long)laserpos);
     const size_t plane = (size_t)g.NY * g.NZ;
     std::vector<int> hp(n), hr(4 * n);
     for (i64 e = 0; e < n; e++) {
