@@ -21,3 +21,17 @@ def test_nccl_ranks_match_single_rank_reference(nranks):
                          capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, (out.stdout[-2000:], out.stderr[-3000:])
     assert out.stdout.count("nccl-parity ok") == nranks
+
+
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_public_api_simulation_on_nccl_ranks(nranks):
+    """Simulation3D + MultiRankMPI (the reference's sim.mpi interface over NCCL) against the 1-rank reference."""
+    import torch
+    if torch.cuda.device_count() < nranks:
+        pytest.skip(f"needs {nranks} GPUs")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}",
+                          "--master-addr", "127.0.0.1", "--master-port", "29547", os.path.join(ROOT, "tests", "nccl_sim_worker.py")],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, (out.stdout[-2000:], out.stderr[-3000:])
+    assert out.stdout.count("nccl-sim-parity ok") == nranks
