@@ -67,7 +67,7 @@ def host_view(eng, nbuf=None, with_sorter=True):
     return st
 
 
-def split_engines_from_golden(g, tag, nranks, with_part=False):
+def split_engines_from_golden(g, tag, nranks, with_part=False, slack=1.5, min_extra=64):
     """One DeviceEngine per emulated rank (all on cuda:0), each owning its block of the golden state's patches."""
     from lambdapic_b200.workloads import make_patch_grid
     dim = int(g["meta/dim"])
@@ -87,7 +87,7 @@ def split_engines_from_golden(g, tag, nranks, with_part=False):
                 eng.field_view(a, k)[...] = g[f"{tag}/f/{gp}/{a}"]
         for s in range(nspec):
             npart = [g[f"{tag}/p/{gp}/{s}/x"].size for gp in pg.index]
-            m = eng.alloc_species(s, npart, slack=1.5, min_extra=64, with_part=with_part)
+            m = eng.alloc_species(s, npart, slack=slack, min_extra=min_extra, with_part=with_part)
             for k, gp in enumerate(pg.index):
                 for a in m.attrs:
                     m.view(a, k)[...] = g[f"{tag}/p/{gp}/{s}/{a}"]

@@ -33,6 +33,26 @@ def test_emulated_ranks_match_single_rank_reference(case, nranks, request):
         e.close()
 
 
+def test_emulated_ranks_with_arena_relayout_during_remote_migration(golden3d):
+    """Zero physical slack: the first remote arrivals force lpic_species_extend to re-lay-out the arena in the middle of
+    the inter-rank migration (extend -> relist -> pack -> unpack)."""
+    import torch
+    from lambdapic_b200.multigpu import RankProgram, drive_in_process, torch_alloc
+    from tests import gpu_harness as h
+    g = golden3d
+    engines, grids, meta = h.split_engines_from_golden(g, "t0", 2, slack=1.0, min_extra=0)
+    progs = [RankProgram(e, pg, torch_alloc(torch.device("cuda", 0))) for e, pg in zip(engines, grids)]
+    rev = [bool(int(g[f"t1/reverse_x/{s}"])) for s in range(engines[0].nspec)]
+    grew = False
+    for k in range(3):
+        res = drive_in_process([p.step(meta["dt"], meta["q"], meta["m"], rev) for p in progs])
+        grew = grew or any(r[1][s]["extended"] or r[1][s]["local"]["moved"] for r in res for s in range(engines[0].nspec))
+        h.compare_split_state_with_golden(engines, grids, g, f"t{k + 1}", rtol=1e-11)
+    assert grew
+    for e in engines:
+        e.close()
+
+
 def test_exchange_plan_lines_up_between_ranks():
     """Sender and receiver derive the same entry order and sizes without negotiation (runs on the GPU box because the
     plan is registered with the device library, which also checks it)."""
