@@ -12,6 +12,10 @@
 //                    memory) before a single lane issues the fp64 RED: ~10x fewer L2 atomics per particle.
 //                    Particles that cross a cell boundary during the step (a few %) are appended to a list ...
 //   3. k_deposit_list ... and deposited by the general 125-point routine, one thread each.
+// The instruction stream of the fully unrolled kernel (5.4 k SASS instructions, 86 KB) does not fit the 32 KB L1.5
+// instruction cache; template parameter COMPACT keeps the component / plane / source-lane loops rolled (2.1 k
+// instructions) with bit-identical arithmetic.  Round-1 measurements (profiles/r1_push_variants.txt): no_instruction
+// stalls vanish, the extra loop overhead eats the gain -- unrolled stays the default, LPIC_PUSH_COMPACT=1 selects the other.
 // Shared-memory fp64 atomics are a CAS loop on sm_100a (ATOMS.CAST.SPIN.64), which is why the reduction happens in
 // registers and the accumulation uses native REDG.E.ADD.F64 in L2.
 #include <stdlib.h>
@@ -34,6 +38,11 @@ __device__ __forceinline__ int warp_incl_sum(int v) {
     }
     return v;
 }
+
+// per-launch constants evaluated once on the host (same IEEE operations as the per-thread expressions they replace)
+struct PushConst {
+    double cdt, efactor, bfactor, inv_dx, inv_dy, inv_dz, q_dV, q_dydzdt, q_dxdzdt, q_dxdydt;
+};
 
 struct PermArgs {
     const double *x, *y, *z;
@@ -179,19 +188,56 @@ __device__ __forceinline__ bool gather_eb_tile(const Geom &g, const double *__re
     return true;
 }
 
+template <typename T>
+__device__ __forceinline__ T sel3(const T *a, int i) { return i == 0 ? a[0] : (i == 1 ? a[1] : a[2]); }
+
+// gather_eb<3> with the six components as a loop that the COMPACT kernel keeps rolled (one 27-point body in the
+// instruction stream instead of six): which of the node-centred (g) / cell-centred (h) weight sets a component uses
+// along x, y, z is a bit of the masks below (ex(h,g,g) ey(g,h,g) ez(g,g,h) bx(g,h,h) by(h,g,h) bz(h,h,g)).
+template <bool COMPACT>
+__device__ __forceinline__ void gather_eb_loop(const Geom &g, const PatchView &v, double x, double y, double z, double *eb,
+                                               const PushConst &k) {
+    const double X = (x - v.x0) * k.inv_dx, Y = (y - v.y0) * k.inv_dy, Z = (z - v.z0) * k.inv_dz;
+    const double fX = floor(X), fY = floor(Y), fZ = floor(Z), rX = floor(X + 0.5), rY = floor(Y + 0.5), rZ = floor(Z + 0.5);
+    double gx[3], gy[3], gz[3], hx[3], hy[3], hz[3];
+    tsc3(rX - X, gx); tsc3(fX - X + 0.5, hx);
+    tsc3(rY - Y, gy); tsc3(fY - Y + 0.5, hy);
+    tsc3(rZ - Z, gz); tsc3(fZ - Z + 0.5, hz);
+    int ogx[3], ohx[3], ogy[3], ohy[3], ogz[3], ohz[3];
+    offsets3((int)rX, g.NX, g.NY * g.NZ, ogx); offsets3((int)fX, g.NX, g.NY * g.NZ, ohx);
+    offsets3((int)rY, g.NY, g.NZ, ogy); offsets3((int)fY, g.NY, g.NZ, ohy);
+    offsets3((int)rZ, g.NZ, 1, ogz); offsets3((int)fZ, g.NZ, 1, ohz);
+    const size_t stride = (size_t)g.npatch * g.ncell;
+#pragma unroll(COMPACT ? 1 : 6)
+    for (int c = 0; c < 6; c++) {
+        const bool sx = (0x31 >> c) & 1, sy = (0x2A >> c) & 1, sz = (0x1C >> c) & 1;
+        double fx[3], fy[3], fz[3];
+        int ox[3], oy[3], oz[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            fx[a] = sx ? hx[a] : gx[a]; ox[a] = sx ? ohx[a] : ogx[a];
+            fy[a] = sy ? hy[a] : gy[a]; oy[a] = sy ? ohy[a] : ogy[a];
+            fz[a] = sz ? hz[a] : gz[a]; oz[a] = sz ? ohz[a] : ogz[a];
+        }
+        const double val = gather27(v.ex + c * stride, fx, fy, fz, ox, oy, oz);
+#pragma unroll
+        for (int a = 0; a < 6; a++) eb[a] = c == a ? val : eb[a];
+    }
+}
+
 // One warp-iteration of the fused step for the particles perm[off + t], t < n.  NZT > 0: E/B come from the
 // shared-memory tile of row (tx0 + 2, ty0 + 2); NZT == 0: from global memory through L1.
-template <bool WRITE_PART, int NZT>
+template <bool WRITE_PART, int NZT, bool COMPACT>
 __device__ __forceinline__ void push_body(const Geom &g, double *__restrict__ F, const double *__restrict__ px0,
                                           const double *__restrict__ py0, const double *__restrict__ pz0, const Slots &s,
                                           const int *__restrict__ perm, int *__restrict__ cross, int *__restrict__ ncross,
                                           double dt, double q, double m, int p, i64 t, i64 n, const double *__restrict__ tile,
-                                          int tx0, int ty0) {
+                                          int tx0, int ty0, const PushConst &k) {
     const int lane = threadIdx.x & 31;
     const bool active = t < n;
     const i64 off = s.off[p];
     const PatchView v = patch_view(g, F, px0, py0, pz0, p);
-    const double cdt = LPIC_C_LIGHT * 0.5 * dt;
+    const double cdt = k.cdt;
     double x = 0, y = 0, z = 0, ux = 0, uy = 0, uz = 0, ig = 1, w = 0;
     i64 ip = 0;
     int local = 0;
@@ -202,16 +248,15 @@ __device__ __forceinline__ void push_body(const Geom &g, double *__restrict__ F,
         ux = s.ux[ip]; uy = s.uy[ip]; uz = s.uz[ip]; ig = s.ig[ip];
         w = s.w[ip];
         x += cdt * ig * ux; y += cdt * ig * uy; z += cdt * ig * uz;
-        double eb[6];
+        double eb[6] = {0, 0, 0, 0, 0, 0};
         bool got = false;
         if (NZT > 0) got = gather_eb_tile<(NZT > 0 ? NZT : 8)>(g, tile, tx0, ty0, v.x0, v.y0, v.z0, x, y, z, eb);
-        if (!got) gather_eb<3>(g, v, x, y, z, eb);
+        if (!got) gather_eb_loop<COMPACT>(g, v, x, y, z, eb, k);
         if (WRITE_PART) {
 #pragma unroll
             for (int a = 0; a < 6; a++) s.part[a][ip] = eb[a];
         }
-        const double efactor = q * dt / (2 * m * LPIC_C_LIGHT), bfactor = q * dt / (2 * m);
-        boris_kick(ux, uy, uz, ig, eb, efactor, bfactor);
+        boris_kick(ux, uy, uz, ig, eb, k.efactor, k.bfactor);
         s.ux[ip] = ux; s.uy[ip] = uy; s.uz[ip] = uz; s.ig[ip] = ig;
         x += cdt * ig * ux; y += cdt * ig * uy; z += cdt * ig * uz;
         s.x[ip] = x; s.y[ip] = y; s.z[ip] = z;
@@ -255,8 +300,7 @@ __device__ __forceinline__ void push_body(const Geom &g, double *__restrict__ F,
         DSx[i] -= S0x[i]; DSy[i] -= S0y[i]; DSz[i] -= S0z[i];
     }
     const double wq = fast ? w : 0.0;  // lanes outside the fast path add zeros
-    const double cd = q / (g.dx * g.dy * g.dz) * wq, fdx = q / (g.dy * g.dz * dt) * wq, fdy = q / (g.dx * g.dz * dt) * wq,
-                 fdz = q / (g.dx * g.dy * dt) * wq;
+    const double cd = k.q_dV * wq, fdx = k.q_dydzdt * wq, fdy = k.q_dxdzdt * wq, fdz = k.q_dxdydt * wq;
     // Warp-level reduction through shared memory, one x-plane of the 3x3x3 stencil at a time.  Every lane stores
     // its values of the plane as rows of a [30][33] tile (row stride 33 doubles: conflict-free both ways); then lane l
     // owns row l and adds up the 32 source lanes, issuing ONE fp64 RED per segment (= run of lanes that start in the
@@ -281,20 +325,21 @@ __device__ __forceinline__ void push_body(const Geom &g, double *__restrict__ F,
     for (int a = 0; a < 3; a++)
 #pragma unroll
         for (int b = 0; b < 3; b++) jxb[a][b] = 0.0;
-#pragma unroll
+#pragma unroll(COMPACT ? 1 : 3)
     for (int i = 0; i < 3; i++) {
-        const double ax = S0x[i] + 0.5 * DSx[i], cx = 0.5 * S0x[i] + LPIC_ONE_THIRD * DSx[i], fx = fdx * DSx[i];
+        const double s0x = sel3(S0x, i), dsx = sel3(DSx, i), s1x = sel3(S1x, i);
+        const double ax = s0x + 0.5 * dsx, cx = 0.5 * s0x + LPIC_ONE_THIRD * dsx, fx = fdx * dsx;
         double jyb[3] = {0.0, 0.0, 0.0};
 #pragma unroll
         for (int j = 0; j < 3; j++) {
             const double ay = S0y[j] + 0.5 * DSy[j], cy = 0.5 * S0y[j] + LPIC_ONE_THIRD * DSy[j], fy = fdy * DSy[j];
             const double tz = ax * S0y[j] + cx * DSy[j];
-            const double rxy = cd * S1x[i] * S1y[j];
+            const double rxy = cd * s1x * S1y[j];
             double jzb = 0.0;
 #pragma unroll
             for (int k = 0; k < 3; k++) {
                 rtile[(j * 3 + k) * 33 + lane] = rxy * S1z[k];
-                if (i < 2) {
+                if (COMPACT || i < 2) {  // rolled: the last plane's rows 21..29 are written but never read
                     jxb[k][j] -= fx * (ay * S0z[k] + cy * DSz[k]);
                     rtile[(21 + j * 3 + k) * 33 + lane] = jxb[k][j];
                 }
@@ -312,7 +357,7 @@ __device__ __forceinline__ void push_body(const Geom &g, double *__restrict__ F,
         if (lane < (i < 2 ? 30 : 21)) {
             double acc = 0.0;
             int seg = 0;  // lane index of the current segment's head
-#pragma unroll
+#pragma unroll(COMPACT ? 1 : 8)
             for (int g4 = 0; g4 < 32; g4 += 4) {
                 const unsigned mm = (heads >> g4) & 0xFu;
                 if ((mm & 0xEu) == 0u) {  // no segment starts strictly inside this group of 4 source lanes
@@ -343,17 +388,17 @@ __device__ __forceinline__ void push_body(const Geom &g, double *__restrict__ F,
     }
 }
 
-template <bool WRITE_PART>
+template <bool WRITE_PART, bool COMPACT>
 __global__ void __launch_bounds__(128, 4) k_push_sorted(Geom g, double *__restrict__ F, const double *__restrict__ px0,
                                                      const double *__restrict__ py0, const double *__restrict__ pz0, Slots s,
                                                      const int *__restrict__ perm, const i64 *__restrict__ nalive,
                                                      int *__restrict__ cross, int *__restrict__ ncross, int blocks_per_patch,
-                                                     double dt, double q, double m) {
+                                                     double dt, double q, double m, PushConst k) {
     const int p = blockIdx.x / blocks_per_patch;
     const i64 t = (i64)(blockIdx.x - p * blocks_per_patch) * blockDim.x + threadIdx.x;
     const i64 n = nalive[p];
     if (t - (threadIdx.x & 31) >= n) return;  // whole warp beyond the alive particles of this patch
-    push_body<WRITE_PART, 0>(g, F, px0, py0, pz0, s, perm, cross, ncross, dt, q, m, p, t, n, nullptr, 0, 0);
+    push_body<WRITE_PART, 0, COMPACT>(g, F, px0, py0, pz0, s, perm, cross, ncross, dt, q, m, p, t, n, nullptr, 0, 0, k);
 }
 
 // One CTA per (patch, row of cells along z): the row's E/B neighbourhood (5 x 5 x NZ nodes x 6 components, logical
@@ -364,7 +409,7 @@ __global__ void __launch_bounds__(128, 3) k_push_rows(Geom g, double *__restrict
                                                    const double *__restrict__ py0, const double *__restrict__ pz0, Slots s,
                                                    const int *__restrict__ perm, const int *__restrict__ rowstart, int nrows,
                                                    int *__restrict__ cross, int *__restrict__ ncross, double dt, double q,
-                                                   double m) {
+                                                   double m, PushConst k) {
     extern __shared__ double eb_tile[];
     const int p = blockIdx.x / nrows, r = blockIdx.x - p * nrows;
     const int start = rowstart[(size_t)p * (nrows + 1) + r], end = rowstart[(size_t)p * (nrows + 1) + r + 1];
@@ -386,7 +431,7 @@ __global__ void __launch_bounds__(128, 3) k_push_rows(Geom g, double *__restrict
     __syncthreads();
     const int lane = threadIdx.x & 31;
     for (i64 t = start + threadIdx.x; t - lane < end; t += blockDim.x)
-        push_body<WRITE_PART, NZT>(g, F, px0, py0, pz0, s, perm, cross, ncross, dt, q, m, p, t, end, eb_tile, ix - 2, iy - 2);
+        push_body<WRITE_PART, NZT, false>(g, F, px0, py0, pz0, s, perm, cross, ncross, dt, q, m, p, t, end, eb_tile, ix - 2, iy - 2, k);
 }
 
 // general deposit for the particles that changed cell during the step
@@ -471,11 +516,17 @@ int lpic_push_deposit_sorted(lpic_ctx *c, int ispec, double dt, double q, double
     LAUNCHED(1);
     const int B = 128;
     Slots s = make_slots(sp);
+    PushConst pk;
+    pk.cdt = LPIC_C_LIGHT * 0.5 * dt;
+    pk.efactor = q * dt / (2 * m * LPIC_C_LIGHT); pk.bfactor = q * dt / (2 * m);
+    pk.inv_dx = 1.0 / g.dx; pk.inv_dy = 1.0 / g.dy; pk.inv_dz = 1.0 / g.dz;
+    pk.q_dV = q / (g.dx * g.dy * g.dz); pk.q_dydzdt = q / (g.dy * g.dz * dt);
+    pk.q_dxdzdt = q / (g.dx * g.dz * dt); pk.q_dxdydt = q / (g.dx * g.dy * dt);
     if (rows) {
         const unsigned grid = (unsigned)((i64)nrows * g.npatch);
 #define ROW_LAUNCH(W, N)                                                                                                  \
     k_push_rows<W, N><<<grid, B, 6 * 25 * N * 8, c->stream>>>(g, c->fields, c->d_x0, c->d_y0, c->d_z0, s, c->scr_b, c->d_rowstart, \
-                                                             nrows, c->scr_a, d_ncross, dt, q, m)
+                                                             nrows, c->scr_a, d_ncross, dt, q, m, pk)
         if (g.NZ == 14) { if (write_part) ROW_LAUNCH(true, 14); else ROW_LAUNCH(false, 14); }
         else if (g.NZ == 22) { if (write_part) ROW_LAUNCH(true, 22); else ROW_LAUNCH(false, 22); }
         else { if (write_part) ROW_LAUNCH(true, 38); else ROW_LAUNCH(false, 38); }
@@ -483,12 +534,16 @@ int lpic_push_deposit_sorted(lpic_ctx *c, int ispec, double dt, double q, double
     } else {
         const int bpp = (int)div_up(sp.max_npart, B);
         const unsigned grid = (unsigned)((i64)bpp * g.npatch);
-        if (write_part)
-            k_push_sorted<true><<<grid, B, 0, c->stream>>>(g, c->fields, c->d_x0, c->d_y0, c->d_z0, s, c->scr_b, d_nalive, c->scr_a,
-                                                          d_ncross, bpp, dt, q, m);
-        else
-            k_push_sorted<false><<<grid, B, 0, c->stream>>>(g, c->fields, c->d_x0, c->d_y0, c->d_z0, s, c->scr_b, d_nalive, c->scr_a,
-                                                           d_ncross, bpp, dt, q, m);
+        // LPIC_PUSH_COMPACT: keep the loops over components / stencil planes / source lanes rolled (2.1 k SASS instructions,
+        // fits the 32 KB L1.5 instruction cache: no_instruction stall 3.9 -> 0 cycles/issue, but 35 % more instructions
+        // executed; measured within 2 % of the unrolled kernel, which stays the default)
+        static const bool compact = getenv("LPIC_PUSH_COMPACT") != nullptr;
+#define SORTED_LAUNCH(W, C)                                                                                                \
+    k_push_sorted<W, C><<<grid, B, 0, c->stream>>>(g, c->fields, c->d_x0, c->d_y0, c->d_z0, s, c->scr_b, d_nalive, c->scr_a, \
+                                                  d_ncross, bpp, dt, q, m, pk)
+        if (write_part) { if (compact) SORTED_LAUNCH(true, true); else SORTED_LAUNCH(true, false); }
+        else { if (compact) SORTED_LAUNCH(false, true); else SORTED_LAUNCH(false, false); }
+#undef SORTED_LAUNCH
     }
     LAUNCHED(1);
     k_deposit_list<<<(unsigned)std::min<i64>(g.npatch, 148 * 8), B, 0, c->stream>>>(g, c->fields, c->d_x0, c->d_y0, c->d_z0, s, c->scr_a, d_ncross, 0, dt, q);
