@@ -54,6 +54,7 @@ struct PermArgs {
     const double *x0, *y0, *z0;
     int nx, ny, nz, kx, ky, kz;  // kx,ky,kz: key grid (nz -> 1 etc. when a patch has more cells than KEY_LIMIT)
     double dx, dy, dz;
+    int *keys;     // arena scratch: cell key of every slot (-1: dead), written by the counting pass, read by the scatter pass
     int *perm;     // arena: local slot numbers of the alive particles in cell order
     i64 *nalive;   // per patch
     int *rowstart; // (npatch, kx*ky + 1): first perm position of every (ix, iy) row of cells, or null
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(PT) k_cell_perm(PermArgs a) {
     };
     for (int ip = tid; ip < np; ip += PT) {
         const int k = key_of(ip);
+        a.keys[off + ip] = k;
         if (k >= 0) atomicAdd(&hist[k], 1);
     }
     __syncthreads();
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(PT) k_cell_perm(PermArgs a) {
         if (a.rowstart) a.rowstart[(size_t)p * (a.kx * a.ky + 1) + a.kx * a.ky] = run;
     }
     for (int ip = tid; ip < np; ip += PT) {
-        const int k = key_of(ip);
+        const int k = a.keys[off + ip];
         if (k >= 0) a.perm[off + atomicAdd(&hist[k], 1)] = ip;
     }
 }
@@ -481,6 +483,7 @@ int lpic_push_deposit_sorted(lpic_ctx *c, int ispec, double dt, double q, double
     }
     a.dx = g.dx; a.dy = g.dy; a.dz = g.dz;
     a.perm = c->scr_b;
+    a.keys = (int *)c->scr_buf;  // the sort's staging buffer is idle during the push
     i64 *d_nalive = c->d_tmp64 + 64;
     int *d_ncross = (int *)(c->d_tmp64 + 64 + g.npatch);
     a.nalive = d_nalive;
