@@ -50,6 +50,14 @@ class DeviceBridge:
         rank = ps[0].rank or 0
         self.engine.set_geometry(x0, y0, z0, nbr, box, glob, rank, np.array([p.index for p in ps], dtype=np.int64))
 
+    def refresh_geometry(self, pml_changed=False):
+        """Re-register origins, neighbour tables and particle boxes after the host objects changed them
+        (MovingWindow); `pml_changed`: the set of CPML faces changed too."""
+        if pml_changed:
+            self.configure_pml()
+        else:
+            self._set_geometry()
+
     # ---- CPML --------------------------------------------------------------------------------------------------
     def configure_pml(self):
         """Register every patch's PML faces with the device (after Simulation._init_pml) and seat their psi arrays."""

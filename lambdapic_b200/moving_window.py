@@ -1,0 +1,147 @@
+"""MovingWindow callback (reference: callback/utils.py:471-840): follow the laser along x by recycling one column of
+patches at a time.  Same constructor, stage (`start`) and bookkeeping (total_shift, patch_this_shift, num_shifts) as the
+reference; the shift itself works on the host mirrors of the DeviceBridge:
+
+  non-shift steps  nothing crosses PCIe (`needs_host = False`: the bridge does not refresh the mirrors for this callback);
+  shift steps      download -> rotate ipatch_x / x0 / axes of the recycled column, rebuild the neighbour tables, drop the
+                   PMLX faces (first activation), re-load the recycled patches' particles from the density profile with the
+                   reference's generator stream, zero their fields and psi, recompute the sort origins -> re-register the
+                   geometry with the device and upload.  One column is recycled every nx_per_patch*dx/(v dt) steps, so the
+                   round trip is amortised over ~10-70 steps; a device-side recycle is the next step.
+
+Single rank only in this round: with more than one rank the exchange plan would have to be rebuilt after every shift.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Union
+
+from .patch import load_patch_particles, loader_spacing
+from .workloads import C_LIGHT
+
+
+class MovingWindow:
+    DEFAULT_STAGE = "start"
+    needs_host = False  # the callback manages the mirrors itself, and only on shift steps
+
+    def __init__(self, velocity: Union[float, Callable[[float], float]], start_time: Optional[float] = None,
+                 inject_particles: bool = True, stop_inject_time: Optional[float] = None):
+        self.stage = self.DEFAULT_STAGE
+        self.velocity = velocity
+        self.start_time = start_time
+        self.inject_particles = inject_particles
+        self.stop_inject_time = stop_inject_time
+        self.total_shift = None
+        self.patch_this_shift = None
+        self.num_shifts: int = 0
+
+    def __call__(self, sim):
+        patch_Lx = sim.nx_per_patch * sim.dx
+        if self.start_time is None:
+            self.start_time = sim.Lx / C_LIGHT
+        if self.total_shift is None:
+            self.total_shift = patch_Lx
+        if self.patch_this_shift is None:
+            self.patch_this_shift = patch_Lx
+        if sim.time < self.start_time:
+            return
+        if sim.mpi.size > 1:
+            raise NotImplementedError("MovingWindow: single rank only in this round (the inter-GPU exchange plan is static)")
+        drop_pmlx = self.num_shifts == 0 and any(m.axis == 0 for p in sim.patches for m in p.pml_boundary)
+
+        current_velocity = self.velocity(sim.time) if callable(self.velocity) else self.velocity
+        shift_amount = current_velocity * sim.dt
+        self.total_shift += shift_amount
+        self.patch_this_shift += shift_amount
+        self.num_shifts += 1
+        direction = 0
+        if self.patch_this_shift >= patch_Lx:
+            direction = 1
+            self.patch_this_shift -= patch_Lx
+        elif self.patch_this_shift <= -patch_Lx:
+            direction = -1
+            self.patch_this_shift += patch_Lx
+        if not (drop_pmlx or direction):
+            return
+
+        br = sim.bridge
+        was_resident = br.resident
+        if was_resident:
+            br.download()
+            br.resident = False
+        if drop_pmlx:  # the x faces stop absorbing once the window moves (callback/utils.py:545-552)
+            for p in sim.patches:
+                p.pml_boundary = [m for m in p.pml_boundary if m.axis != 0]
+        if direction:
+            new_patches = self._shift(sim, direction)
+            self._update_patch_info(sim)
+            self._fill_particles(sim, new_patches)
+            for p in new_patches:  # recycled patches start from vacuum fields
+                for attr in p.fields.attrs:
+                    getattr(p.fields, attr).fill(0.0)
+                for m in p.pml_boundary:
+                    for k, v in vars(m).items():
+                        if k.startswith("psi"):
+                            v.fill(0.0)
+            for sorter in sim.sorter:
+                sorter.generate_field_lists()
+                sorter.generate_particle_lists()
+        br.refresh_geometry(pml_changed=drop_pmlx)
+        if was_resident:
+            br.upload()
+            br.resident = True
+
+    @staticmethod
+    def _shift(sim, direction):
+        """callback/utils.py:591-646: the trailing column jumps ahead by Lx; every other column moves one index back."""
+        last = sim.npatch_x - 1
+        new_patches = []
+        for p in sim.patches:
+            if direction > 0 and p.ipatch_x == 0 or direction < 0 and p.ipatch_x == last:
+                p.ipatch_x = last if direction > 0 else 0
+                # in-place additions, as the reference does them: the axes are NOT recomputed from the new origin
+                p.x0 += direction * sim.Lx
+                p.xaxis += direction * sim.Lx
+                p.fields.x0 += direction * sim.Lx
+                p.fields.xaxis += direction * sim.Lx
+                new_patches.append(p)
+            else:
+                p.ipatch_x -= direction
+        return new_patches
+
+    @staticmethod
+    def _update_patch_info(sim):
+        """callback/utils.py:648-716 (single rank: the allgather is the identity)."""
+        ps = sim.patches
+        if sim.dimension == 3:
+            index_map = {(p.ipatch_x, p.ipatch_y, p.ipatch_z): p.index for p in ps}
+            ps.init_rect_neighbor_index_3d(sim.npatch_x, sim.npatch_y, sim.npatch_z, boundary_conditions=sim.boundary_conditions,
+                                           patch_index_map=index_map)
+            ps.init_neighbor_ipatch_3d()
+            ps.init_neighbor_rank_3d({p.index: p.rank for p in ps})
+        else:
+            index_map = {(p.ipatch_x, p.ipatch_y): p.index for p in ps}
+            ps.init_rect_neighbor_index_2d(sim.npatch_x, sim.npatch_y, boundary_conditions=sim.boundary_conditions,
+                                           patch_index_map=index_map)
+            ps.init_neighbor_ipatch_2d()
+            ps.init_neighbor_rank_2d({p.index: p.rank for p in ps})
+
+    def _fill_particles(self, sim, new_patches):
+        """callback/utils.py:718-840: every species with a density profile is re-initialised in the recycled patches
+        (fresh ids continue the patch's counter) and loaded from one new generator per patch, spawned per species."""
+        if not new_patches or not self.inject_particles:
+            return
+        if self.stop_inject_time is not None and sim.time >= self.stop_inject_time:
+            return
+        dim = sim.dimension
+        from .patch import _node_profiles
+        for ispec, s in enumerate(sim.species):
+            if s.density is None:
+                continue
+            gens = sim.rand_gen.spawn(len(new_patches))
+            d = loader_spacing(new_patches[0], dim)
+            for k, p in enumerate(new_patches):
+                _, ppc = _node_profiles(s, p, dim)
+                part = p.particles[ispec]
+                part.initialize(int(ppc.sum()))
+                load_patch_particles(s, p, part, gens[k], dim, d)
+        sim.update_lists()

@@ -97,6 +97,15 @@ class ParticleSort(EnableOp):
         self.nbuf_last = 0
         self._configured_for = None
 
+    def generate_field_lists(self):
+        """Bucket origins follow the patch origins (particle_sort.py:178-203,316-342); called again after a
+        MovingWindow shift."""
+        ps = self.patches
+        self.x0s = [p.x0 - ps.dx / 2 for p in ps]
+        self.y0s = [p.y0 - ps.dy / 2 for p in ps]
+        self.z0s = [getattr(p, "z0", 0.0) - (ps.dz / 2 if self.dimension == 3 else 0.0) for p in ps]
+        self._configured_for = None
+
     def _configure(self):
         eng = self.bridge.engine
         if self._configured_for is not eng:

@@ -161,6 +161,68 @@ class Patches:
         """Returns npart_to_extend summed over species, per patch (int64), like the reference."""
         return self._need_bridge().sync_particles()
 
+    # ---- neighbour tables (core/patch/patch.py:446-667); used again after a MovingWindow shift ----------------------
+    def _init_rect_neighbor_index(self, npatch, boundary_conditions, patch_index_map):
+        from .workloads import DIR2, DIR3
+        dim = self.dimension
+        dirs = DIR3 if dim == 3 else DIR2
+        axes = "xyz"[:dim]
+        if not patch_index_map:
+            patch_index_map = {tuple(getattr(p, f"ipatch_{a}") for a in axes): p.index for p in self.patches}
+        ntot = int(np.prod(npatch[:dim]))
+        for p in self.patches:
+            p.neighbor_index.fill(-1)
+            for b, off in enumerate(dirs):
+                pos, ok = [], True
+                for a, ax in enumerate(axes):
+                    n = getattr(p, f"ipatch_{ax}") + off[a]
+                    if n < 0:
+                        if boundary_conditions[f"{ax}min"] != "periodic":
+                            ok = False
+                            break
+                        n = npatch[a] - 1
+                    elif n >= npatch[a]:
+                        if boundary_conditions[f"{ax}max"] != "periodic":
+                            ok = False
+                            break
+                        n = 0
+                    pos.append(n)
+                if not ok:
+                    continue
+                idx = patch_index_map.get(tuple(pos))
+                if idx is None:
+                    if len(patch_index_map) == ntot:
+                        raise KeyError(tuple(pos))
+                    continue
+                p.neighbor_index[b] = idx
+
+    def init_rect_neighbor_index_2d(self, npatch_x, npatch_y, *, boundary_conditions, patch_index_map=None):
+        self._init_rect_neighbor_index((npatch_x, npatch_y), boundary_conditions, patch_index_map or {})
+
+    def init_rect_neighbor_index_3d(self, npatch_x, npatch_y, npatch_z, boundary_conditions, patch_index_map=None):
+        self._init_rect_neighbor_index((npatch_x, npatch_y, npatch_z), boundary_conditions, patch_index_map or {})
+
+    def _init_neighbor_ipatch(self):
+        """Local list position of every same-rank neighbour (core/patch/patch.py:641-667)."""
+        where = {p.index: ip for ip, p in enumerate(self.patches)}
+        for p in self.patches:
+            p.neighbor_ipatch.fill(-1)
+            for b, idx in enumerate(p.neighbor_index):
+                if idx >= 0 and idx in where:
+                    p.neighbor_ipatch[b] = where[idx]
+    init_neighbor_ipatch_2d = init_neighbor_ipatch_3d = _init_neighbor_ipatch
+
+    def _init_neighbor_rank(self, patch_rank_map=None):
+        patch_rank_map = dict(patch_rank_map or {})
+        for p in self.patches:
+            patch_rank_map[p.index] = p.rank
+        for p in self.patches:
+            p.neighbor_rank.fill(-1)
+            for b, idx in enumerate(p.neighbor_index):
+                if idx >= 0 and patch_rank_map[idx] != p.rank:
+                    p.neighbor_rank[b] = patch_rank_map[idx]
+    init_neighbor_rank_2d = init_neighbor_rank_3d = _init_neighbor_rank
+
     # ---- particle loading (host side so that seeds reproduce the reference's positions) ---------------------
     def calculate_npart(self, species: Species):
         """core/patch/patch.py:796-844 + core/patch/cpu.py:6-19,46-63: sum of int(ppc) over nodes with density > min."""
@@ -190,33 +252,46 @@ class Patches:
         x, y(, z) = uniform(-d/2, d/2, ppc) + node, w = density*dV/ppc -- drawn in that order so that the
         random stream matches the reference's numba loop exactly."""
         gens = rand_gen.spawn(self.npatches)
-        dim = self.dimension
         for ispec, s in enumerate(self.species):
             if s.density is None:
                 continue
+            d = loader_spacing(self.patches[0], self.dimension)
             for ip, p in enumerate(self.patches):
-                dens, ppc = _node_profiles(s, p, dim)
-                part = p.particles[ispec]
-                n = int(ppc.sum())
-                if n == 0:
-                    continue
-                d = (p.dx, p.dy) + ((p.dz,) if dim == 3 else ())
-                grids = np.meshgrid(*((p.xaxis, p.yaxis) + ((p.zaxis,) if dim == 3 else ())), indexing="ij")
-                ppc_f, dens_f = ppc.ravel(), dens.ravel()
-                nodes = [g.ravel() for g in grids]
-                u = gens[ip].random(dim * n)
-                # stream layout: node-major, then axis, then the ppc draws of that axis
-                first = np.concatenate([[0], np.cumsum(ppc_f)[:-1]])            # first particle of each node
-                node_of = np.repeat(np.arange(ppc_f.size), ppc_f)               # node of each particle
-                k = np.arange(n) - first[node_of]                               # index inside the node
-                for a, name in enumerate(("x", "y", "z")[:dim]):
-                    pos = dim * first[node_of] + a * ppc_f[node_of] + k
-                    low, rng = -d[a] / 2, d[a] / 2 - (-d[a] / 2)
-                    getattr(part, name)[:n] = (low + rng * u[pos]) + nodes[a][node_of]
-                wnode = dens_f.copy()
-                for da in d:  # dens*dx*dy*dz / ppc in the reference's association (core/patch/cpu.py:43,99)
-                    wnode = wnode * da
-                part.w[:n] = wnode[node_of] / ppc_f[node_of]
+                load_patch_particles(s, p, p.particles[ispec], gens[ip], self.dimension, d)
+
+
+def loader_spacing(first_patch: Patch, dim: int):
+    """The loader takes dx, dy(, dz) from the axes of the FIRST patch of the list it is given (core/patch/cpu.py:23-24,
+    70-72): exact for a patch at the origin, 1 ulp(x0)-level off after a MovingWindow shifted the axes in place."""
+    axes = (first_patch.xaxis, first_patch.yaxis) + ((first_patch.zaxis,) if dim == 3 else ())
+    return tuple(float(ax[1] - ax[0]) for ax in axes)
+
+
+def load_patch_particles(s: Species, p: Patch, part: ParticlesBase, gen: np.random.Generator, dim: int, d) -> int:
+    """Positions and weights of one (patch, species) from the patch's generator (core/patch/cpu.py:22-43,66-99).
+    `part` must already hold int(ppc.sum()) slots; d = loader_spacing(first patch of the list being loaded).
+    Returns the number of particles loaded."""
+    dens, ppc = _node_profiles(s, p, dim)
+    n = int(ppc.sum())
+    if n == 0:
+        return 0
+    grids = np.meshgrid(*((p.xaxis, p.yaxis) + ((p.zaxis,) if dim == 3 else ())), indexing="ij")
+    ppc_f, dens_f = ppc.ravel(), dens.ravel()
+    nodes = [g.ravel() for g in grids]
+    u = gen.random(dim * n)
+    # stream layout: node-major, then axis, then the ppc draws of that axis
+    first = np.concatenate([[0], np.cumsum(ppc_f)[:-1]])            # first particle of each node
+    node_of = np.repeat(np.arange(ppc_f.size), ppc_f)               # node of each particle
+    k = np.arange(n) - first[node_of]                               # index inside the node
+    for a, name in enumerate(("x", "y", "z")[:dim]):
+        pos = dim * first[node_of] + a * ppc_f[node_of] + k
+        low, rng = -d[a] / 2, d[a] / 2 - (-d[a] / 2)
+        getattr(part, name)[:n] = (low + rng * u[pos]) + nodes[a][node_of]
+    wnode = dens_f.copy()
+    for da in d:  # dens*dx*dy*dz / ppc in the reference's association (core/patch/cpu.py:43,99)
+        wnode = wnode * da
+    part.w[:n] = wnode[node_of] / ppc_f[node_of]
+    return n
 
 
 def _node_profiles(species: Species, p: Patch, dim: int):

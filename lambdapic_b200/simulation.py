@@ -202,7 +202,9 @@ class Simulation:
         patches = Patches(self.dimension)
         for k, g in enumerate(grid.index):
             ix, iy = int(g % self.npatch_x), int(g // self.npatch_x)
-            p = Patch2D(grid.rank, int(g), ix, iy, float(grid.x0[k]), float(grid.y0[k]), grid.nx, grid.ny, self.dx, self.dy)
+            # origins in the reference's arithmetic, i*L/npatch (simulation.py:482-483), not i*n*d: 1 ulp apart for some sizes
+            p = Patch2D(grid.rank, int(g), ix, iy, ix * self.Lx / self.npatch_x, iy * self.Ly / self.npatch_y,
+                        grid.nx, grid.ny, self.dx, self.dy)
             p.neighbor_index[:] = grid.neighbor_index[k]
             p.neighbor_ipatch[:] = grid.neighbor_ipatch[k]
             p.neighbor_rank[:] = grid.neighbor_rank[k]
@@ -486,8 +488,8 @@ class Simulation3D(Simulation):
         patches = Patches(3)
         for k, g in enumerate(grid.index):
             ix, iy, iz = int(g % self.npatch_x), int((g // self.npatch_x) % self.npatch_y), int(g // (self.npatch_x * self.npatch_y))
-            p = Patch3D(grid.rank, int(g), ix, iy, iz, float(grid.x0[k]), float(grid.y0[k]), float(grid.z0[k]),
-                        grid.nx, grid.ny, grid.nz, self.dx, self.dy, self.dz)
+            p = Patch3D(grid.rank, int(g), ix, iy, iz, ix * self.Lx / self.npatch_x, iy * self.Ly / self.npatch_y,
+                        iz * self.Lz / self.npatch_z, grid.nx, grid.ny, grid.nz, self.dx, self.dy, self.dz)  # simulation.py:1393
             p.neighbor_index[:] = grid.neighbor_index[k]
             p.neighbor_ipatch[:] = grid.neighbor_ipatch[k]
             p.neighbor_rank[:] = grid.neighbor_rank[k]

@@ -587,3 +587,154 @@ def step(st: OState, backend="port", laser=None):
         laser_stage(st, *laser)
     sync_guard_fields(st, B, backend)
     update_efield(st, 0.5 * dt); sync_guard_fields(st, E, backend)
+
+
+# --------------------------------------------------------------------------------------------------
+# MovingWindow (callback/utils.py:471-840), stage `start`
+# --------------------------------------------------------------------------------------------------
+DIR2 = [(-1, 0, 0), (1, 0, 0), (0, -1, 0), (0, 1, 0), (-1, -1, 0), (1, -1, 0), (-1, 1, 0), (1, 1, 0)]  # Boundary2D order
+
+
+def _boundary3d_dirs():
+    """Offsets in Boundary3D enum order (core/patch/patch.py:37-69): faces, xy / xz / yz edges, corners."""
+    faces = [(-1, 0, 0), (1, 0, 0), (0, -1, 0), (0, 1, 0), (0, 0, -1), (0, 0, 1)]
+    xy = [(-1, -1, 0), (-1, 1, 0)]
+    xz = [(-1, 0, -1), (-1, 0, 1)]
+    xy2 = [(1, -1, 0), (1, 1, 0)]
+    xz2 = [(1, 0, -1), (1, 0, 1)]
+    yz = [(0, -1, -1), (0, -1, 1), (0, 1, -1), (0, 1, 1)]
+    corners = [(-1, -1, -1), (-1, -1, 1), (-1, 1, -1), (-1, 1, 1), (1, -1, -1), (1, -1, 1), (1, 1, -1), (1, 1, 1)]
+    return faces + xy + xz + xy2 + xz2 + yz + corners
+
+
+class OMovingWindow:
+    """Host bookkeeping of the moving window restated on an OState.
+
+    npatch: (npx, npy[, npz]); ipatch: per patch (ix, iy, iz) at construction; periodic: per axis; density, ppc: callables
+    of the node coordinates per species (None: species is not re-loaded); rand_gen: the rank's generator AFTER the initial
+    load spawned its per-patch children (simulation.py:700-716, patch.py:864-907)."""
+
+    def __init__(self, st: OState, velocity, npatch, ipatch, periodic, Lx, density, ppc, rand_gen, start_time=None,
+                 inject_particles=True, stop_inject_time=None, density_min=0.0):
+        self.velocity, self.start_time = velocity, start_time
+        self.inject_particles, self.stop_inject_time = inject_particles, stop_inject_time
+        self.npatch, self.periodic, self.Lx = tuple(npatch), tuple(periodic), Lx
+        self.density, self.ppc, self.density_min, self.rand_gen = density, ppc, density_min, rand_gen
+        self.total_shift = self.patch_this_shift = None
+        self.num_shifts = 0
+        self.dirs = _boundary3d_dirs() if st.dim == 3 else DIR2
+        for p, ip in zip(st.patches, ipatch):
+            p.ipatch = [int(v) for v in ip]
+            p.xaxis = np.arange(st.nx) * st.dx + p.x0
+            p.yaxis = np.arange(st.ny) * st.dy + p.y0
+            p.zaxis = np.arange(st.nz) * st.dz + p.z0
+
+    def stage(self, st: OState, time: float):
+        patch_Lx = st.nx * st.dx
+        if self.start_time is None:
+            self.start_time = self.Lx / C_LIGHT
+        if self.total_shift is None:
+            self.total_shift = patch_Lx
+        if self.patch_this_shift is None:
+            self.patch_this_shift = patch_Lx
+        if time < self.start_time:
+            return
+        if self.num_shifts == 0:  # callback/utils.py:545-552: the x faces stop absorbing
+            for p in st.patches:
+                p.pml = [m for m in p.pml if m.axis != 0]
+        v = self.velocity(time) if callable(self.velocity) else self.velocity
+        self.total_shift += v * st.dt
+        self.patch_this_shift += v * st.dt
+        self.num_shifts += 1
+        if self.patch_this_shift >= patch_Lx:
+            direction = 1
+            self.patch_this_shift -= patch_Lx
+        elif self.patch_this_shift <= -patch_Lx:
+            direction = -1
+            self.patch_this_shift += patch_Lx
+        else:
+            return
+        last = self.npatch[0] - 1
+        new = []
+        for p in st.patches:  # callback/utils.py:591-646
+            if (direction > 0 and p.ipatch[0] == 0) or (direction < 0 and p.ipatch[0] == last):
+                p.ipatch[0] = last if direction > 0 else 0
+                p.x0 += direction * self.Lx
+                p.xaxis += direction * self.Lx
+                p.fields.x0 = p.fields.x0 + direction * self.Lx
+                new.append(p)
+            else:
+                p.ipatch[0] -= direction
+        self._neighbours(st)
+        self._reload(st, new, time)
+        for p in new:
+            for a in FIELD_ATTRS:
+                getattr(p.fields, a).fill(0.0)
+            for m in p.pml:
+                for nm in m.names["E"] + m.names["B"]:
+                    getattr(m, nm).fill(0.0)
+
+    def _neighbours(self, st):  # core/patch/patch.py:446-592, 641-667 (single rank: index -> list position)
+        dim = st.dim
+        where = {tuple(p.ipatch[:dim]): i for i, p in enumerate(st.patches)}
+        for p in st.patches:
+            nb = np.full(len(self.dirs), -1, dtype=np.int64)
+            for b, off in enumerate(self.dirs):
+                pos, ok = [], True
+                for a in range(dim):
+                    n = p.ipatch[a] + off[a]
+                    if n < 0 or n >= self.npatch[a]:
+                        if not self.periodic[a]:
+                            ok = False
+                            break
+                        n %= self.npatch[a]
+                    pos.append(n)
+                if ok:
+                    nb[b] = where[tuple(pos)]
+            p.neighbor_ipatch = nb
+
+    def _reload(self, st, new, time):  # callback/utils.py:718-840 + core/patch/cpu.py:6-99
+        if not new or not self.inject_particles:
+            return
+        if self.stop_inject_time is not None and time >= self.stop_inject_time:
+            return
+        dim = st.dim
+        # the loader derives the spacings from the axes of the first patch it is given (core/patch/cpu.py:23-24,70-72)
+        d = tuple(float(ax[1] - ax[0]) for ax in (new[0].xaxis, new[0].yaxis, new[0].zaxis)[:dim])
+        for s in range(st.nspec):
+            if self.density[s] is None:
+                continue
+            gens = self.rand_gen.spawn(len(new))
+            for k, p in enumerate(new):
+                axes = (p.xaxis, p.yaxis, p.zaxis)[:dim]
+                grids = np.meshgrid(*axes, indexing="ij")
+                dens = np.broadcast_to(np.asarray(self.density[s](*grids), dtype=float), grids[0].shape).ravel()
+                ppc = np.broadcast_to(np.asarray(self.ppc[s](*grids), dtype=float), grids[0].shape).astype(np.int64).ravel()
+                ppc = np.where(dens > self.density_min, ppc, 0)
+                n = int(ppc.sum())
+                part = p.particles[s]
+                # ParticlesBase.initialize (core/particles.py:118-139): fresh arrays, ids continue the patch's counter
+                part.npart = n
+                for a in PART_ATTRS:
+                    setattr(part, a, np.zeros(n))
+                part.inv_gamma[:] = 1
+                part.is_dead = np.zeros(n, dtype=bool)
+                part._id[:] = part._ids(part._npart_created, n)
+                part._npart_created += n
+                part.extended = True
+                if n == 0:
+                    continue
+                u = gens[k].random(dim * n)  # per node: ppc draws for x, then y(, then z)
+                first = np.concatenate([[0], np.cumsum(ppc)[:-1]])
+                node_of = np.repeat(np.arange(ppc.size), ppc)
+                j = np.arange(n) - first[node_of]
+                nodes = [g.ravel() for g in grids]
+                for a, name in enumerate("xyz"[:dim]):
+                    pos = dim * first[node_of] + a * ppc[node_of] + j
+                    low, rng = -d[a] / 2, d[a] / 2 - (-d[a] / 2)
+                    getattr(part, name)[:] = (low + rng * u[pos]) + nodes[a][node_of]
+                wnode = dens.copy()
+                for da in d:
+                    wnode = wnode * da
+                part.w[:] = wnode[node_of] / ppc[node_of]
+        update_lists(st)

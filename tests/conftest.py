@@ -46,3 +46,15 @@ def golden_laser3d():
 def golden_laser2d():
     import numpy as np
     return np.load(os.path.join(ROOT, "tests", "golden", "ref_laser_2d.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_mw2d():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "ref_mw_2d.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_mw3d():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "ref_mw_3d.npz"))

@@ -237,3 +237,67 @@ def test_public_api_laser_into_cpml_box_matches_reference(dim, case, nsteps, req
     st = sim.bridge.stats
     assert st["uploads"] - before["uploads"] == nsteps and st["downloads"] - before["downloads"] == nsteps  # run entry/exit only
     sim.bridge.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim,case", [(2, "golden_mw2d"), (3, "golden_mw3d")])
+def test_public_api_moving_window_matches_reference(dim, case, request):
+    """BASELINE.json configs[2] in miniature: x open with CPML until the window starts, window at c
+    from t = 0, density varying along x.  The reference recycles a column of patches at steps 0, ~11, ~22 (2D) / 0, 15
+    (3D); after each shift and at the end the whole state -- fields, slot-exact particles incl. fresh ids of the re-loaded
+    patches, origins, neighbour tables, remaining CPML faces -- must match the unmodified reference's."""
+    from lambdapic_b200 import Electron, MovingWindow, Proton, Simulation, Simulation3D, callback
+    g = request.getfixturevalue(case)
+    d, n0 = 0.8e-6 / 20, 1.742e27
+    if dim == 3:
+        sim = Simulation3D(nx=24, ny=8, nz=8, dx=d, dy=d * 1.25, dz=d * 0.8, npatch_x=3, npatch_y=1, npatch_z=1, dt_cfl=0.95,
+                           boundary_conditions=dict(xmin="pml", xmax="pml", ymin="periodic", ymax="periodic",
+                                                    zmin="periodic", zmax="periodic"), cpml_thickness=6, random_seed=4321)
+        dens = lambda x, y, z: n0 * (1.0 + x * 2.0e5)  # noqa: E731
+    else:
+        sim = Simulation(nx=32, ny=16, dx=d, dy=d * 1.25, npatch_x=4, npatch_y=2, dt_cfl=0.95,
+                         boundary_conditions=dict(xmin="pml", xmax="pml", ymin="periodic", ymax="periodic"),
+                         cpml_thickness=6, random_seed=4322)
+        dens = lambda x, y: n0 * (1.0 + x * 2.0e5)  # noqa: E731
+    sim.add_species([Electron(density=dens, ppc=2), Proton(density=dens, ppc=1)])
+    mw = MovingWindow(velocity=299792458.0, start_time=0.0)
+
+    @callback("init")
+    def seed(sim):
+        rng = np.random.default_rng(6)
+        for p in sim.patches:
+            for isp, part in enumerate(p.particles):
+                n = part.npart
+                sig = 0.3 if isp == 0 else 0.02
+                part.ux[:] = rng.normal(0.05 if isp == 0 else -0.01, sig, n)
+                part.uy[:] = rng.normal(0.0, sig, n)
+                part.uz[:] = rng.normal(0.0, sig, n)
+                part.inv_gamma[:] = 1.0 / np.sqrt(1 + part.ux**2 + part.uy**2 + part.uz**2)
+            f = p.fields
+            for a, amp in (("ex", 3e11), ("ey", -2e11), ("ez", 1e11), ("bx", 500.0), ("by", -800.0), ("bz", 300.0)):
+                arr = getattr(f, a)
+                arr[...] = amp * rng.standard_normal(arr.shape)
+    sim.initialize()
+    nsteps = int(g["meta/nsteps"])
+    dump_after = set(int(v) for v in g["meta/dump_after"])
+    shift_steps = [int(v) for v in g["meta/shift_steps"]]
+    assert len(shift_steps) >= 2
+    worst, seen_shifts = 0.0, []
+    for it in range(nsteps):
+        before = [p.x0 for p in sim.patches]
+        sim.run(nsteps=1, callbacks=[seed, mw] if it == 0 else [mw])
+        if before != [p.x0 for p in sim.patches]:
+            seen_shifts.append(it)
+        if it + 1 in dump_after:
+            tag = f"t{it + 1}"
+            assert np.array_equal(np.array([p.x0 for p in sim.patches]), g[f"{tag}/x0"]), "patch origins"
+            assert np.array_equal(np.array([p.ipatch_x for p in sim.patches]), g[f"{tag}/ipatch_x"])
+            assert np.array_equal(np.array([p.neighbor_ipatch for p in sim.patches]), g[f"{tag}/neighbor_ipatch"])
+            assert [",".join(type(m).__name__ for m in p.pml_boundary) for p in sim.patches] == list(g[f"{tag}/pml_faces"])
+            assert np.allclose([mw.total_shift, mw.patch_this_shift, mw.num_shifts], g[f"{tag}/mw"], rtol=1e-14, atol=0)
+            rtol = 1e-12 if it == 0 else 1e-10  # multi-step drift of the summation order; single steps are <= 1e-12
+            worst = max(worst, check_state_against_golden(types.SimpleNamespace(patches=sim.patches, sorters=None), g, tag,
+                                                          rtol=rtol, check_sorter=False))
+    assert seen_shifts == shift_steps
+    assert worst <= 1e-10
+    sim.bridge.close()

@@ -114,3 +114,38 @@ def test_laser_antenna_port_and_reference_extensions(case, nsteps, request):
             st = _load(g, k)
             orc.step(st, backend, laser=(_laser_sources(g, k, len(st.patches)), lp))
             assert check_state_against_golden(st, g, f"t{k + 1}", rtol=rtol, check_sorter=False) <= rtol
+
+
+@pytest.mark.parametrize("case", ["golden_mw2d", "golden_mw3d"])
+def test_moving_window_port_and_reference_extensions(case, request):
+    """MovingWindow (callback/utils.py:471-840) restated on the oracle state: patch recycling, neighbour tables, PMLX
+    removal and the re-load of the recycled patches from the reference's generator stream.  Started from the reference's
+    state at stage `init` of step 0, the whole run must reproduce every snapshot of the unmodified reference."""
+    g = request.getfixturevalue(case)
+    dim = int(g["meta/dim"])
+    n0 = 1.742e27
+    dens = (lambda x, y, z: n0 * (1.0 + x * 2.0e5)) if dim == 3 else (lambda x, y: n0 * (1.0 + x * 2.0e5))
+    ppcs = [(lambda *a: 2.0), (lambda *a: 1.0)]
+    npatch = [int(g[f"meta/npatch_{a}"]) for a in "xyz"[:dim]]
+    nsteps = int(g["meta/nsteps"])
+    dump_after = set(int(v) for v in g["meta/dump_after"])
+    # port: 17-24 steps of accumulated summation-order differences in J (single steps are <= 1e-13); ref: bit-exact
+    for backend, rtol in (("port", 1e-9), ("ref", 0.0)):
+        if backend == "ref" and not orc.have_ref():
+            continue
+        st = orc.OState.from_golden(g, "t0")
+        rand_gen = np.random.default_rng(int(g["meta/seed"])).spawn(1)[0]
+        rand_gen.spawn(len(st.patches))  # the initial load took one child per patch
+        mw = orc.OMovingWindow(st, 299792458.0, npatch, g["meta/ipatch"], g["meta/periodic"], float(g["meta/Lx"]),
+                               [dens, dens], ppcs, rand_gen, start_time=0.0)
+        for it in range(nsteps):
+            mw.stage(st, it * st.dt)
+            orc.step(st, backend)
+            if it + 1 in dump_after:
+                tag = f"t{it + 1}"
+                assert np.array_equal(np.array([p.x0 for p in st.patches]), g[f"{tag}/x0"])
+                assert np.array_equal(st.nbr, g[f"{tag}/neighbor_ipatch"])
+                assert [",".join({"xmin": "PMLXmin", "xmax": "PMLXmax", "ymin": "PMLYmin", "ymax": "PMLYmax", "zmin": "PMLZmin",
+                                  "zmax": "PMLZmax"}[m.face] for m in p.pml) for p in st.patches] == list(g[f"{tag}/pml_faces"])
+                assert check_state_against_golden(st, g, tag, rtol=rtol, check_sorter=False) <= rtol
+        assert mw.num_shifts == int(g[f"t{nsteps}/mw"][2])
