@@ -43,7 +43,6 @@ def parse():
     ap.add_argument("--cells", type=int, nargs=3, default=None, help="cells per GPU (default 256 256 256)")
     ap.add_argument("--ppc", type=int, nargs=2, default=[16, 16])
     ap.add_argument("--patch", type=int, default=16)
-    ap.add_argument("--row-tile", action="store_true", help="experimental row kernel (E/B tile in shared memory)")
     ap.add_argument("--slot-order", action="store_true", help="use the v1 particle kernel (memory order)")
     ap.add_argument("--breakdown", action="store_true", help="print per-operator CUDA-event times of one extra step to stderr")
     ap.add_argument("--no-e2e", action="store_true")
@@ -204,7 +203,6 @@ def main():
     wl = workload(args, world)
     eng = build_engine(wl, device=local, rank=rank, nranks=world)
     eng.slot_order = args.slot_order
-    eng.row_tile = args.row_tile
     if world > 1:
         from lambdapic_b200.multigpu import HaloExchanger
         eng.halo = HaloExchanger(eng, eng.grid)

@@ -35,8 +35,7 @@ enum { LPIC_P_X = 0, LPIC_P_Y, LPIC_P_Z, LPIC_P_W, LPIC_P_UX, LPIC_P_UY, LPIC_P_
 /* sorter arrays (core/sort/particle_sort.py:20-160) */
 enum { LPIC_SORT_BUCKET_COUNT = 0, LPIC_SORT_BOUND_MIN, LPIC_SORT_BOUND_MAX, LPIC_SORT_PARTICLE_INDEX };
 /* flags of lpic_push_deposit */
-enum { LPIC_PUSH_WRITE_PART = 1, LPIC_PUSH_SLOT_ORDER = 2 /* process slots in memory order (round-1 v1 kernel) */,
-       LPIC_PUSH_ROW_TILE = 4 /* experimental: one CTA per row of cells with the E/B neighbourhood staged in shared memory */ };
+enum { LPIC_PUSH_WRITE_PART = 1, LPIC_PUSH_SLOT_ORDER = 2 /* process slots in memory order (round-1 v1 kernel) */ };
 
 const char *lpic_last_error(void);
 int lpic_device_count(void);

@@ -20,7 +20,6 @@ P_IS_DEAD = len(PART_ATTRS)
 SORT_BUCKET_COUNT, SORT_BOUND_MIN, SORT_BOUND_MAX, SORT_PARTICLE_INDEX = range(4)
 PUSH_WRITE_PART = 1
 PUSH_SLOT_ORDER = 2
-PUSH_ROW_TILE = 4
 
 _i64, _dbl, _vp, _int, _u32, _u64 = C.c_int64, C.c_double, C.c_void_p, C.c_int, C.c_uint32, C.c_uint64
 

@@ -107,8 +107,6 @@ struct lpic_ctx {
     struct PmlState *pml = nullptr;   // null: no open boundaries
     struct HaloPlan *halo = nullptr;  // inter-rank exchange plan (halo.cu), null on a single rank
     cudaEvent_t *events = nullptr;  // lazily created, 4096 slots
-    int *d_rowstart = nullptr;      // (npatch, nx*ny + 1) row starts of the cell permutation (push_sorted.cu)
-    size_t rowstart_bytes = 0;
 };
 
 inline double *field_ptr(const lpic_ctx *c, int attr) { return c->fields + (size_t)attr * c->g.npatch * c->g.ncell; }

@@ -193,7 +193,7 @@ int launch_particles(lpic_ctx *c, int ispec, double dt, double q, double m, bool
 
 }  // namespace
 
-int lpic_push_deposit_sorted(lpic_ctx *c, int ispec, double dt, double q, double m, bool write_part, bool use_row_tile);
+int lpic_push_deposit_sorted(lpic_ctx *c, int ispec, double dt, double q, double m, bool write_part);
 
 extern "C" int lpic_push_deposit(lpic_ctx *c, int ispec, double dt, double q, double m, int flags) {
     const bool write_part = (flags & LPIC_PUSH_WRITE_PART) != 0;
@@ -203,7 +203,7 @@ extern "C" int lpic_push_deposit(lpic_ctx *c, int ispec, double dt, double q, do
         return -2;
     }
     if (!(flags & LPIC_PUSH_SLOT_ORDER)) {  // default: cell-ordered warp-cooperative kernel (3D), see push_sorted.cu
-        const int r = lpic_push_deposit_sorted(c, ispec, dt, q, m, write_part, (flags & LPIC_PUSH_ROW_TILE) != 0);
+        const int r = lpic_push_deposit_sorted(c, ispec, dt, q, m, write_part);
         if (r <= 0) return r;
     }
     return launch_particles<MODE_FUSED>(c, ispec, dt, q, m, write_part);

@@ -57,7 +57,6 @@ struct PermArgs {
     int *keys;     // arena scratch: cell key of every slot (-1: dead), written by the counting pass, read by the scatter pass
     int *perm;     // arena: local slot numbers of the alive particles in cell order
     i64 *nalive;   // per patch
-    int *rowstart; // (npatch, kx*ky + 1): first perm position of every (ix, iy) row of cells, or null
 };
 
 __device__ __forceinline__ int node_of(double x, double x0, double d, int n) {
@@ -115,17 +114,11 @@ __global__ void __launch_bounds__(PT) k_cell_perm(PermArgs a) {
             if (i < (tid >> 5)) add += sw[i];
             tot += sw[i];
         }
-        if (b < nkey) {
-            hist[b] = run + v + add - cnt;
-            if (a.rowstart && b % a.kz == 0) a.rowstart[(size_t)p * (a.kx * a.ky + 1) + b / a.kz] = run + v + add - cnt;
-        }
+        if (b < nkey) hist[b] = run + v + add - cnt;
         run += tot;
         __syncthreads();
     }
-    if (tid == 0) {
-        a.nalive[p] = run;
-        if (a.rowstart) a.rowstart[(size_t)p * (a.kx * a.ky + 1) + a.kx * a.ky] = run;
-    }
+    if (tid == 0) a.nalive[p] = run;
     for (int ip = tid; ip < np; ip += PT) {
         const int k = a.keys[off + ip];
         if (k >= 0) a.perm[off + atomicAdd(&hist[k], 1)] = ip;
@@ -144,50 +137,6 @@ __device__ __noinline__ void flush_red(double *dst, const int *sb, int i, int sj
     if (sb[2] < 0) return;
     const int id = wrap_once(sb[0] + i - 1, NX) * NY * NZ + wrap_once(sb[1] + sj - 1, NY) * NZ + wrap_once(sb[2] + sk - 1, NZ);
     atomicAdd(dst + id, sum);
-}
-
-// 27-point weighted sum from the shared-memory E/B tile: T points at the first stencil point, strides are
-// compile-time (x: 5*NZT, y: NZT, z: 1) so every load is an LDS with an immediate offset.  Same association as gather27.
-template <int NZT>
-__device__ __forceinline__ double gather_tile(const double *__restrict__ T, const double *fx, const double *fy, const double *fz) {
-    double az[3];
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-        double ay[3];
-#pragma unroll
-        for (int b = 0; b < 3; b++)
-            ay[b] = fx[0] * T[(0 * 5 + b) * NZT + c] + fx[1] * T[(1 * 5 + b) * NZT + c] + fx[2] * T[(2 * 5 + b) * NZT + c];
-        az[c] = fy[0] * ay[0] + fy[1] * ay[1] + fy[2] * ay[2];
-    }
-    return fz[0] * az[0] + fz[1] * az[1] + fz[2] * az[2];
-}
-
-// E and B at the particle from the tile of row (ix, iy): logical x in [ix-2, ix+2], y in [iy-2, iy+2], all z.
-// Returns false (caller falls back to the global gather) if the stencil leaves the tile, which cannot happen for
-// dt_cfl <= 1 (half-step displacement < half a cell) but is checked anyway.
-template <int NZT>
-__device__ __forceinline__ bool gather_eb_tile(const Geom &g, const double *__restrict__ tile, int tx0, int ty0, double x0,
-                                               double y0, double z0, double x, double y, double z, double *eb) {
-    const double X = (x - x0) * (1.0 / g.dx), Y = (y - y0) * (1.0 / g.dy), Z = (z - z0) * (1.0 / g.dz);
-    const double fX = floor(X), fY = floor(Y), fZ = floor(Z), rX = floor(X + 0.5), rY = floor(Y + 0.5), rZ = floor(Z + 0.5);
-    const int gi = (int)rX - 1 - tx0, hi = (int)fX - 1 - tx0, gj = (int)rY - 1 - ty0, hj = (int)fY - 1 - ty0;
-    const int gk = (int)rZ - 1 + g.ng, hk = (int)fZ - 1 + g.ng;
-    if ((unsigned)gi > 2u || (unsigned)hi > 2u || (unsigned)gj > 2u || (unsigned)hj > 2u || (unsigned)gk > (unsigned)(NZT - 3) ||
-        (unsigned)hk > (unsigned)(NZT - 3))
-        return false;
-    double gx[3], gy[3], gz[3], hx[3], hy[3], hz[3];
-    tsc3(rX - X, gx); tsc3(fX - X + 0.5, hx);
-    tsc3(rY - Y, gy); tsc3(fY - Y + 0.5, hy);
-    tsc3(rZ - Z, gz); tsc3(fZ - Z + 0.5, hz);
-    const int og = (gi * 5) * NZT, oh = (hi * 5) * NZT;
-    constexpr int CS = 25 * NZT;  // component stride
-    eb[0] = gather_tile<NZT>(tile + 0 * CS + oh + gj * NZT + gk, hx, gy, gz);
-    eb[1] = gather_tile<NZT>(tile + 1 * CS + og + hj * NZT + gk, gx, hy, gz);
-    eb[2] = gather_tile<NZT>(tile + 2 * CS + og + gj * NZT + hk, gx, gy, hz);
-    eb[3] = gather_tile<NZT>(tile + 3 * CS + og + hj * NZT + hk, gx, hy, hz);
-    eb[4] = gather_tile<NZT>(tile + 4 * CS + oh + gj * NZT + hk, hx, gy, hz);
-    eb[5] = gather_tile<NZT>(tile + 5 * CS + oh + hj * NZT + gk, hx, hy, gz);
-    return true;
 }
 
 template <typename T>
@@ -227,14 +176,12 @@ __device__ __forceinline__ void gather_eb_loop(const Geom &g, const PatchView &v
     }
 }
 
-// One warp-iteration of the fused step for the particles perm[off + t], t < n.  NZT > 0: E/B come from the
-// shared-memory tile of row (tx0 + 2, ty0 + 2); NZT == 0: from global memory through L1.
-template <bool WRITE_PART, int NZT, bool COMPACT>
+// One warp-iteration of the fused step for the particles perm[off + t], t < n.
+template <bool WRITE_PART, bool COMPACT>
 __device__ __forceinline__ void push_body(const Geom &g, double *__restrict__ F, const double *__restrict__ px0,
                                           const double *__restrict__ py0, const double *__restrict__ pz0, const Slots &s,
                                           const int *__restrict__ perm, int *__restrict__ cross, int *__restrict__ ncross,
-                                          double dt, double q, double m, int p, i64 t, i64 n, const double *__restrict__ tile,
-                                          int tx0, int ty0, const PushConst &k) {
+                                          double dt, double q, double m, int p, i64 t, i64 n, const PushConst &k) {
     const int lane = threadIdx.x & 31;
     const bool active = t < n;
     const i64 off = s.off[p];
@@ -251,9 +198,7 @@ __device__ __forceinline__ void push_body(const Geom &g, double *__restrict__ F,
         w = s.w[ip];
         x += cdt * ig * ux; y += cdt * ig * uy; z += cdt * ig * uz;
         double eb[6] = {0, 0, 0, 0, 0, 0};
-        bool got = false;
-        if (NZT > 0) got = gather_eb_tile<(NZT > 0 ? NZT : 8)>(g, tile, tx0, ty0, v.x0, v.y0, v.z0, x, y, z, eb);
-        if (!got) gather_eb_loop<COMPACT>(g, v, x, y, z, eb, k);
+        gather_eb_loop<COMPACT>(g, v, x, y, z, eb, k);
         if (WRITE_PART) {
 #pragma unroll
             for (int a = 0; a < 6; a++) s.part[a][ip] = eb[a];
@@ -400,40 +345,7 @@ __global__ void __launch_bounds__(128, 4) k_push_sorted(Geom g, double *__restri
     const i64 t = (i64)(blockIdx.x - p * blocks_per_patch) * blockDim.x + threadIdx.x;
     const i64 n = nalive[p];
     if (t - (threadIdx.x & 31) >= n) return;  // whole warp beyond the alive particles of this patch
-    push_body<WRITE_PART, 0, COMPACT>(g, F, px0, py0, pz0, s, perm, cross, ncross, dt, q, m, p, t, n, nullptr, 0, 0, k);
-}
-
-// One CTA per (patch, row of cells along z): the row's E/B neighbourhood (5 x 5 x NZ nodes x 6 components, logical
-// order) is staged in shared memory once, then the row's particles (contiguous in the cell permutation) are pushed
-// 128 at a time.  All 6 x 27 gather reads per particle become LDS with immediate offsets.
-template <bool WRITE_PART, int NZT>
-__global__ void __launch_bounds__(128, 3) k_push_rows(Geom g, double *__restrict__ F, const double *__restrict__ px0,
-                                                   const double *__restrict__ py0, const double *__restrict__ pz0, Slots s,
-                                                   const int *__restrict__ perm, const int *__restrict__ rowstart, int nrows,
-                                                   int *__restrict__ cross, int *__restrict__ ncross, double dt, double q,
-                                                   double m, PushConst k) {
-    extern __shared__ double eb_tile[];
-    const int p = blockIdx.x / nrows, r = blockIdx.x - p * nrows;
-    const int start = rowstart[(size_t)p * (nrows + 1) + r], end = rowstart[(size_t)p * (nrows + 1) + r + 1];
-    if (start == end) return;
-    const int ix = r / g.ny, iy = r - ix * g.ny;
-    const size_t stride = (size_t)g.npatch * g.ncell;
-    const double *base = F + (size_t)p * g.ncell;
-    {   // each warp copies whole z-rows (NZT contiguous doubles in the wrapped layout, except for the guard wrap)
-        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-        const int k0 = lane, k1 = lane + 32;
-        const int s0 = wrapneg(k0 - g.ng, g.NZ), s1 = wrapneg(k1 - g.ng, g.NZ);
-        for (int row = w; row < 6 * 25; row += PUSH_WARPS) {
-            const int c = row / 25, ij = row - c * 25, i5 = ij / 5, j5 = ij - i5 * 5;
-            const double *src = base + c * stride + (size_t)g.NZ * (wrapneg(iy - 2 + j5, g.NY) + g.NY * wrapneg(ix - 2 + i5, g.NX));
-            if (k0 < NZT) eb_tile[row * NZT + k0] = __ldg(src + s0);
-            if (NZT > 32 && k1 < NZT) eb_tile[row * NZT + k1] = __ldg(src + s1);
-        }
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    for (i64 t = start + threadIdx.x; t - lane < end; t += blockDim.x)
-        push_body<WRITE_PART, NZT, false>(g, F, px0, py0, pz0, s, perm, cross, ncross, dt, q, m, p, t, end, eb_tile, ix - 2, iy - 2, k);
+    push_body<WRITE_PART, COMPACT>(g, F, px0, py0, pz0, s, perm, cross, ncross, dt, q, m, p, t, n, k);
 }
 
 // general deposit for the particles that changed cell during the step
@@ -459,7 +371,7 @@ __global__ void __launch_bounds__(128) k_deposit_list(Geom g, double *__restrict
 }  // namespace
 
 // 3D fused push + deposit in cell order; returns 1 if this path does not apply (caller falls back to k_particles)
-int lpic_push_deposit_sorted(lpic_ctx *c, int ispec, double dt, double q, double m, bool write_part, bool use_row_tile) {
+int lpic_push_deposit_sorted(lpic_ctx *c, int ispec, double dt, double q, double m, bool write_part) {
     const Geom &g = c->g;
     Species &sp = c->spec[ispec];
     if (g.dim != 3) return 1;
@@ -472,7 +384,7 @@ int lpic_push_deposit_sorted(lpic_ctx *c, int ispec, double dt, double q, double
     a.cdt = LPIC_C_LIGHT * 0.5 * dt;
     a.nx = g.nx; a.ny = g.ny; a.nz = g.nz;
     static const bool no_predict = getenv("LPIC_PERM_CURRENT_CELL") != nullptr;  // tuning knob: order by the current cell
-    a.predict = !no_predict && !use_row_tile && (i64)(g.nx + 2) * (g.ny + 2) * (g.nz + 2) <= KEY_LIMIT;
+    a.predict = !no_predict && (i64)(g.nx + 2) * (g.ny + 2) * (g.nz + 2) <= KEY_LIMIT;
     if (a.predict) {
         a.kx = g.nx + 2; a.ky = g.ny + 2; a.kz = g.nz + 2;
     } else {
@@ -487,31 +399,10 @@ int lpic_push_deposit_sorted(lpic_ctx *c, int ispec, double dt, double q, double
     i64 *d_nalive = c->d_tmp64 + 64;
     int *d_ncross = (int *)(c->d_tmp64 + 64 + g.npatch);
     a.nalive = d_nalive;
-    // Optional row kernel (E/B tile in shared memory, LPIC_PUSH_ROW_TILE).  Measured SLOWER than the untiled kernel in
-    // round 1 (128^3, 16+16 ppc: 18.1 vs 14.1 ms per electron launch): a row holds ~256 particles, so the third
-    // 128-thread iteration runs mostly empty lanes and the tile load is not overlapped.  Kept opt-in for round 2
-    // (multi-row CTAs with a double-buffered TMA tile).
-    const int nrows = g.nx * g.ny;
-    const bool rows = !a.predict && a.kz == g.nz && a.ky == g.ny && g.ng >= 2 && (g.NZ == 14 || g.NZ == 22 || g.NZ == 38) &&
-                      use_row_tile;
-    a.rowstart = nullptr;
-    if (rows) {
-        const size_t need = sizeof(int) * (size_t)g.npatch * (nrows + 1);
-        if (c->rowstart_bytes < need) {
-            CUDA_TRY(cudaStreamSynchronize(c->stream));
-            cudaFree(c->d_rowstart);
-            CUDA_TRY(cudaMalloc(&c->d_rowstart, need));
-            c->rowstart_bytes = need;
-        }
-        a.rowstart = c->d_rowstart;
-    }
     const size_t smem = sizeof(int) * (size_t)a.kx * a.ky * a.kz;
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(k_cell_perm, cudaFuncAttributeMaxDynamicSharedMemorySize, KEY_LIMIT * (int)sizeof(int)));
-#define ROW_ATTR(W, N) CUDA_TRY(cudaFuncSetAttribute(k_push_rows<W, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 25 * N * 8))
-        ROW_ATTR(true, 14); ROW_ATTR(false, 14); ROW_ATTR(true, 22); ROW_ATTR(false, 22); ROW_ATTR(true, 38); ROW_ATTR(false, 38);
-#undef ROW_ATTR
         attr_set = true;
     }
     CUDA_TRY(cudaMemsetAsync(d_ncross, 0, sizeof(int) * g.npatch, c->stream));
@@ -525,22 +416,13 @@ int lpic_push_deposit_sorted(lpic_ctx *c, int ispec, double dt, double q, double
     pk.inv_dx = 1.0 / g.dx; pk.inv_dy = 1.0 / g.dy; pk.inv_dz = 1.0 / g.dz;
     pk.q_dV = q / (g.dx * g.dy * g.dz); pk.q_dydzdt = q / (g.dy * g.dz * dt);
     pk.q_dxdzdt = q / (g.dx * g.dz * dt); pk.q_dxdydt = q / (g.dx * g.dy * dt);
-    if (rows) {
-        const unsigned grid = (unsigned)((i64)nrows * g.npatch);
-#define ROW_LAUNCH(W, N)                                                                                                  \
-    k_push_rows<W, N><<<grid, B, 6 * 25 * N * 8, c->stream>>>(g, c->fields, c->d_x0, c->d_y0, c->d_z0, s, c->scr_b, c->d_rowstart, \
-                                                             nrows, c->scr_a, d_ncross, dt, q, m, pk)
-        if (g.NZ == 14) { if (write_part) ROW_LAUNCH(true, 14); else ROW_LAUNCH(false, 14); }
-        else if (g.NZ == 22) { if (write_part) ROW_LAUNCH(true, 22); else ROW_LAUNCH(false, 22); }
-        else { if (write_part) ROW_LAUNCH(true, 38); else ROW_LAUNCH(false, 38); }
-#undef ROW_LAUNCH
-    } else {
+    {
         const int bpp = (int)div_up(sp.max_npart, B);
         const unsigned grid = (unsigned)((i64)bpp * g.npatch);
         // LPIC_PUSH_COMPACT: keep the loops over components / stencil planes / source lanes rolled (2.1 k SASS instructions,
         // fits the 32 KB L1.5 instruction cache: no_instruction stall 3.9 -> 0 cycles/issue, but 35 % more instructions
         // executed; measured within 2 % of the unrolled kernel, which stays the default)
-        static const bool compact = getenv("LPIC_PUSH_COMPACT") != nullptr;
+        const bool compact = getenv("LPIC_PUSH_COMPACT") != nullptr;  // read per call: tests toggle it
 #define SORTED_LAUNCH(W, C)                                                                                                \
     k_push_sorted<W, C><<<grid, B, 0, c->stream>>>(g, c->fields, c->d_x0, c->d_y0, c->d_z0, s, c->scr_b, d_nalive, c->scr_a, \
                                                   d_ncross, bpp, dt, q, m, pk)

@@ -112,7 +112,6 @@ class DeviceEngine:
         self.rank = 0
         self.patch_index = np.arange(npatch, dtype=np.int64)
         self.x0 = self.y0 = self.z0 = None
-        self.row_tile = False    # True: experimental row kernel with the E/B neighbourhood staged in shared memory
         self.slot_order = False  # True: round-1 v1 particle kernel (memory order) instead of the cell-ordered one
 
     # ---- lifetime --------------------------------------------------------------------------------------------
@@ -263,8 +262,7 @@ class DeviceEngine:
 
     def push_deposit(self, ispec, dt, q, m, write_part=False, slot_order=None):
         slot_order = self.slot_order if slot_order is None else slot_order
-        flags = ((_lib.PUSH_WRITE_PART if write_part else 0) | (_lib.PUSH_SLOT_ORDER if slot_order else 0)
-                 | (_lib.PUSH_ROW_TILE if self.row_tile else 0))
+        flags = (_lib.PUSH_WRITE_PART if write_part else 0) | (_lib.PUSH_SLOT_ORDER if slot_order else 0)
         check(self.L.lpic_push_deposit(self.ctx, ispec, float(dt), float(q), float(m), flags))
 
     def interpolate(self, ispec):
