@@ -1,4 +1,4 @@
-// Cell-ordered, warp-cooperative version of the fused particle kernel (3D).
+// Cell-ordered, warp-cooperative version of the fused particle kernel (3D; the 2D twin k_push_sorted2d is further down).
 //
 // Same arithmetic as k_particles<3,FUSED> (particles.cu; reference: core/pusher/unified/unified_pusher_3d.c:281-431,
 // core/current/current_deposit.h:275-440) but organised for the memory system of the B200:
@@ -52,7 +52,7 @@ struct PermArgs {
     const u8 *dead;
     const i64 *off, *npart;
     const double *x0, *y0, *z0;
-    int nx, ny, nz, kx, ky, kz;  // kx,ky,kz: key grid (nz -> 1 etc. when a patch has more cells than KEY_LIMIT)
+    int dim, nx, ny, nz, kx, ky, kz;  // kx,ky,kz: key grid (nz -> 1 etc. when a patch has more cells than KEY_LIMIT; 2D: kz = 1)
     double dx, dy, dz;
     int *keys;     // arena scratch: cell key of every slot (-1: dead), written by the counting pass, read by the scatter pass
     int *perm;     // arena: local slot numbers of the alive particles in cell order
@@ -82,12 +82,12 @@ __global__ void __launch_bounds__(PT) k_cell_perm(PermArgs a) {
     const double x0 = a.x0[p], y0 = a.y0[p], z0 = a.z0[p];
     auto key_of = [&](int ip) -> int {
         if (a.dead[off + ip]) return -1;
-        const double x = a.x[off + ip], y = a.y[off + ip], z = a.z[off + ip];
+        const double x = a.x[off + ip], y = a.y[off + ip], z = a.dim == 3 ? a.z[off + ip] : 0.0;
         if (isnan(x) || isnan(y) || isnan(z)) return -1;
         if (a.predict) {
             const double h = a.cdt * a.ig[off + ip];
             const int ix = node_pad(x + h * a.ux[off + ip], x0, a.dx, a.nx), iy = node_pad(y + h * a.uy[off + ip], y0, a.dy, a.ny),
-                      iz = node_pad(z + h * a.uz[off + ip], z0, a.dz, a.nz);
+                      iz = a.dim == 3 ? node_pad(z + h * a.uz[off + ip], z0, a.dz, a.nz) : 0;
             return iz + a.kz * (iy + a.ky * ix);
         }
         const int ix = node_of(x, x0, a.dx, a.nx), iy = a.ky > 1 ? node_of(y, y0, a.dy, a.ny) : 0,
@@ -368,27 +368,171 @@ __global__ void __launch_bounds__(128) k_deposit_list(Geom g, double *__restrict
     }
 }
 
+
+// ---- 2D twin --------------------------------------------------------------------------------------------------------
+// Same organisation in two dimensions (reference: core/pusher/unified/unified_pusher_2d.c:157-330,
+// core/current/current_deposit.h:150-268): 6 x 9 gather points per particle, and the whole 3x3 stencil of a particle that
+// stays in its cell is ONE round of the [30][33] reduction tile -- rho 9 rows, jx 6 (the last x row is sum(DSx) = 0 up to
+// rounding), jy 6 (last y column likewise), jz 9.  RED address of row (i, j): wrap(bx0 + i - 1) * NY + wrap(by0 + j - 1).
+template <bool WRITE_PART>
+__global__ void __launch_bounds__(128, 6) k_push_sorted2d(Geom g, double *__restrict__ F, const double *__restrict__ px0,
+                                                       const double *__restrict__ py0, const double *__restrict__ pz0, Slots s,
+                                                       const int *__restrict__ perm, const i64 *__restrict__ nalive,
+                                                       int *__restrict__ cross, int *__restrict__ ncross, int blocks_per_patch,
+                                                       double dt, PushConst k) {
+    const int p = blockIdx.x / blocks_per_patch;
+    const i64 t = (i64)(blockIdx.x - p * blocks_per_patch) * blockDim.x + threadIdx.x;
+    const i64 n = nalive[p];
+    const int lane = threadIdx.x & 31;
+    if (t - lane >= n) return;  // whole warp beyond the alive particles of this patch
+    const bool active = t < n;
+    const i64 off = s.off[p];
+    const PatchView v = patch_view(g, F, px0, py0, pz0, p);
+    const double cdt = k.cdt;
+    double x = 0, y = 0, ux = 0, uy = 0, uz = 0, ig = 1, w = 0;
+    i64 ip = 0;
+    int local = 0;
+    if (active) {
+        local = perm[off + t];
+        ip = off + local;
+        x = s.x[ip]; y = s.y[ip];
+        ux = s.ux[ip]; uy = s.uy[ip]; uz = s.uz[ip]; ig = s.ig[ip];
+        w = s.w[ip];
+        x += cdt * ig * ux; y += cdt * ig * uy;
+        double eb[6];
+        gather_eb<2>(g, v, x, y, 0.0, eb);
+        if (WRITE_PART) {
+#pragma unroll
+            for (int a = 0; a < 6; a++) s.part[a][ip] = eb[a];
+        }
+        boris_kick(ux, uy, uz, ig, eb, k.efactor, k.bfactor);
+        s.ux[ip] = ux; s.uy[ip] = uy; s.uz[ip] = uz; s.ig[ip] = ig;
+        x += cdt * ig * ux; y += cdt * ig * uy;
+        s.x[ip] = x; s.y[ip] = y;
+    }
+    // ---- deposit set-up (current_deposit.h:196-222) ----------------------------------------------------------------
+    const double vx = ux * LPIC_C_LIGHT * ig, vy = uy * LPIC_C_LIGHT * ig, vz = uz * LPIC_C_LIGHT * ig;
+    const double X0 = (x - vx * 0.5 * dt - v.x0) / g.dx, X1 = (x + vx * 0.5 * dt - v.x0) / g.dx;
+    const double Y0 = (y - vy * 0.5 * dt - v.y0) / g.dy, Y1 = (y + vy * 0.5 * dt - v.y0) / g.dy;
+    const int ix0 = (int)floor(X0 + 0.5), iy0 = (int)floor(Y0 + 0.5);
+    const int ix1 = (int)floor(X1 + 0.5), iy1 = (int)floor(Y1 + 0.5);
+    const bool fast = active && ix1 == ix0 && iy1 == iy0;
+    {   // particles that change cell go to the general routine (k_deposit_list2d)
+        const unsigned cm = __ballot_sync(0xffffffffu, active && !fast);
+        if (cm) {
+            int basepos = 0;
+            if (lane == __ffs(cm) - 1) basepos = atomicAdd(&ncross[p], __popc(cm));
+            basepos = __shfl_sync(0xffffffffu, basepos, __ffs(cm) - 1);
+            if (active && !fast) cross[off + basepos + __popc(cm & ((1u << lane) - 1u))] = local;
+        }
+    }
+    const int bx0 = wrap_base(ix0, g.NX), by0 = wrap_base(iy0, g.NY);
+    const int key = by0 + g.NY * bx0;
+    const unsigned fm = __ballot_sync(0xffffffffu, fast);
+    const unsigned before = fm & ((1u << lane) - 1u);
+    const int pf = before ? 31 - __clz(before) : -1;
+    const int pkey = __shfl_sync(0xffffffffu, key, pf < 0 ? 0 : pf);
+    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || (fast && (pf < 0 || key != pkey)));
+    if (!fm) return;
+    double S0x[3], S0y[3], S1x[3], S1y[3], DSx[3], DSy[3];
+    shape3(ix0 - X0, S0x); shape3(iy0 - Y0, S0y);
+    shape3(ix1 - X1, S1x); shape3(iy1 - Y1, S1y);  // no cell crossing: same support as S0
+#pragma unroll
+    for (int i = 0; i < 3; i++) { DSx[i] = S1x[i] - S0x[i]; DSy[i] = S1y[i] - S0y[i]; }
+    const double wq = fast ? w : 0.0;  // lanes outside the fast path add zeros
+    const double cd = k.q_dV * wq, fdx = k.q_dydzdt * wq, fdy = k.q_dxdzdt * wq, fvz = cd * vz;  // 2D: q/(dx dy), q/(dy dt), q/(dx dt)
+    const double one_twelfth = 1.0 / 12.0;
+    __shared__ double red[PUSH_WARPS][30 * 33];
+    __shared__ int segbase[PUSH_WARPS][32][2];
+    double *rtile = red[threadIdx.x >> 5];
+    int(*sb)[2] = segbase[threadIdx.x >> 5];
+    sb[lane][0] = bx0; sb[lane][1] = fast ? by0 : -1;
+    // rows: [0,9) rho(i,j)  [9,15) jx(i<2,j)  [15,21) jy(i,j<2)  [21,30) jz(i,j)
+    double jxb[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const double a = S0x[i] + 0.5 * DSx[i], fxi = fdx * DSx[i], t12 = one_twelfth * DSx[i];
+        double jyb = 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const double b = S0y[j] + 0.5 * DSy[j];
+            rtile[(i * 3 + j) * 33 + lane] = cd * S1x[i] * S1y[j];
+            if (i < 2) {
+                jxb[j] -= fxi * b;
+                rtile[(9 + i * 3 + j) * 33 + lane] = jxb[j];
+            }
+            if (j < 2) {
+                jyb -= fdy * (DSy[j] * a);
+                rtile[(15 + i * 2 + j) * 33 + lane] = jyb;
+            }
+            rtile[(21 + i * 3 + j) * 33 + lane] = fvz * (a * b + t12 * DSy[j]);
+        }
+    }
+    __syncwarp();
+    if (lane < 30) {
+        int comp, si, sj;
+        if (lane < 9) { comp = 3; si = lane / 3; sj = lane - 3 * si; }
+        else if (lane < 15) { comp = 0; si = (lane - 9) / 3; sj = (lane - 9) - 3 * si; }
+        else if (lane < 21) { comp = 1; si = (lane - 15) >> 1; sj = (lane - 15) & 1; }
+        else { comp = 2; si = (lane - 21) / 3; sj = (lane - 21) - 3 * si; }
+        double *dst = comp == 0 ? v.jx : (comp == 1 ? v.jy : (comp == 2 ? v.jz : v.rho));
+        const double *row = rtile + lane * 33;
+        double acc = 0.0;
+        int seg = 0;  // lane index of the current segment's head
+        auto flush = [&]() {
+            if (sb[seg][1] >= 0) atomicAdd(dst + wrap_once(sb[seg][0] + si - 1, g.NX) * g.NY + wrap_once(sb[seg][1] + sj - 1, g.NY), acc);
+        };
+#pragma unroll 4
+        for (int src = 0; src < 32; src++) {
+            if (src > 0 && ((heads >> src) & 1u)) {
+                flush();
+                acc = 0.0;
+                seg = src;
+            }
+            acc += row[src];
+        }
+        flush();
+    }
+}
+
+__global__ void __launch_bounds__(128) k_deposit_list2d(Geom g, double *__restrict__ F, const double *__restrict__ px0,
+                                                        const double *__restrict__ py0, const double *__restrict__ pz0, Slots s,
+                                                        const int *__restrict__ cross, const int *__restrict__ ncross, double dt,
+                                                        double q) {
+    DepositCoef2 k;
+    k.q_dxdy = q / (g.dx * g.dy); k.q_dydt = q / (g.dy * dt); k.q_dxdt = q / (g.dx * dt); k.dt = dt;
+    for (int p = blockIdx.x; p < g.npatch; p += gridDim.x) {
+        const int n = ncross[p];
+        if (n == 0) continue;
+        const PatchView v = patch_view(g, F, px0, py0, pz0, p);
+        for (int t = threadIdx.x; t < n; t += blockDim.x) {
+            const i64 ip = s.off[p] + cross[s.off[p] + t];
+            deposit2(g, v, k, s.x[ip], s.y[ip], s.ux[ip], s.uy[ip], s.uz[ip], s.ig[ip], s.w[ip]);
+        }
+    }
+}
+
 }  // namespace
 
-// 3D fused push + deposit in cell order; returns 1 if this path does not apply (caller falls back to k_particles)
+// fused push + deposit in cell order; returns 1 if this path does not apply (caller falls back to k_particles)
 int lpic_push_deposit_sorted(lpic_ctx *c, int ispec, double dt, double q, double m, bool write_part) {
     const Geom &g = c->g;
     Species &sp = c->spec[ispec];
-    if (g.dim != 3) return 1;
     if (sp.max_npart == 0) return 0;
+    const bool three = g.dim == 3;
     if (int r = lpic_ensure_scratch(c, sp.total)) return r;
     PermArgs a;
     a.x = sp.attr[LPIC_P_X]; a.y = sp.attr[LPIC_P_Y]; a.z = sp.attr[LPIC_P_Z]; a.dead = sp.dead;
     a.off = sp.d_off; a.npart = sp.d_npart; a.x0 = c->d_x0; a.y0 = c->d_y0; a.z0 = c->d_z0;
     a.ux = sp.attr[LPIC_P_UX]; a.uy = sp.attr[LPIC_P_UY]; a.uz = sp.attr[LPIC_P_UZ]; a.ig = sp.attr[LPIC_P_INV_GAMMA];
     a.cdt = LPIC_C_LIGHT * 0.5 * dt;
-    a.nx = g.nx; a.ny = g.ny; a.nz = g.nz;
+    a.dim = g.dim; a.nx = g.nx; a.ny = g.ny; a.nz = three ? g.nz : 1;
     static const bool no_predict = getenv("LPIC_PERM_CURRENT_CELL") != nullptr;  // tuning knob: order by the current cell
-    a.predict = !no_predict && (i64)(g.nx + 2) * (g.ny + 2) * (g.nz + 2) <= KEY_LIMIT;
+    a.predict = !no_predict && (i64)(g.nx + 2) * (g.ny + 2) * (three ? g.nz + 2 : 1) <= KEY_LIMIT;
     if (a.predict) {
-        a.kx = g.nx + 2; a.ky = g.ny + 2; a.kz = g.nz + 2;
+        a.kx = g.nx + 2; a.ky = g.ny + 2; a.kz = three ? g.nz + 2 : 1;
     } else {
-        a.kx = g.nx; a.ky = g.ny; a.kz = g.nz;
+        a.kx = g.nx; a.ky = g.ny; a.kz = a.nz;
         if ((i64)a.kx * a.ky * a.kz > KEY_LIMIT) a.kz = 1;
         if ((i64)a.kx * a.ky * a.kz > KEY_LIMIT) a.ky = 1;
         if ((i64)a.kx * a.ky * a.kz > KEY_LIMIT) return 1;
@@ -416,6 +560,23 @@ int lpic_push_deposit_sorted(lpic_ctx *c, int ispec, double dt, double q, double
     pk.inv_dx = 1.0 / g.dx; pk.inv_dy = 1.0 / g.dy; pk.inv_dz = 1.0 / g.dz;
     pk.q_dV = q / (g.dx * g.dy * g.dz); pk.q_dydzdt = q / (g.dy * g.dz * dt);
     pk.q_dxdzdt = q / (g.dx * g.dz * dt); pk.q_dxdydt = q / (g.dx * g.dy * dt);
+    if (!three) {
+        pk.q_dV = q / (g.dx * g.dy); pk.q_dydzdt = q / (g.dy * dt); pk.q_dxdzdt = q / (g.dx * dt);  // DepositCoef2's q_dxdy, q_dydt, q_dxdt
+        const int bpp = (int)div_up(sp.max_npart, B);
+        const unsigned grid = (unsigned)((i64)bpp * g.npatch);
+        if (write_part)
+            k_push_sorted2d<true><<<grid, B, 0, c->stream>>>(g, c->fields, c->d_x0, c->d_y0, c->d_z0, s, c->scr_b, d_nalive, c->scr_a,
+                                                            d_ncross, bpp, dt, pk);
+        else
+            k_push_sorted2d<false><<<grid, B, 0, c->stream>>>(g, c->fields, c->d_x0, c->d_y0, c->d_z0, s, c->scr_b, d_nalive, c->scr_a,
+                                                             d_ncross, bpp, dt, pk);
+        LAUNCHED(1);
+        k_deposit_list2d<<<(unsigned)std::min<i64>(g.npatch, 148 * 8), B, 0, c->stream>>>(g, c->fields, c->d_x0, c->d_y0, c->d_z0, s,
+                                                                                        c->scr_a, d_ncross, dt, q);
+        LAUNCHED(1);
+        KERNEL_CHECK();
+        return 0;
+    }
     {
         const int bpp = (int)div_up(sp.max_npart, B);
         const unsigned grid = (unsigned)((i64)bpp * g.npatch);
