@@ -286,50 +286,48 @@ __global__ void __launch_bounds__(T) k_sort_index(SortArgs a) {
     }
 }
 
-template <typename V>
-__global__ void __launch_bounds__(256) k_sort_gather(const V *__restrict__ attr, V *__restrict__ buf, const int *__restrict__ src_of,
-                                                     const i64 *__restrict__ off, const i64 *__restrict__ nbuf, int blocks_per_patch) {
-    const int p = blockIdx.x / blocks_per_patch;
-    const i64 i = (i64)(blockIdx.x - p * blocks_per_patch) * blockDim.x + threadIdx.x;
-    if (i >= nbuf[p]) return;
-    buf[off[p] + i] = attr[off[p] + src_of[off[p] + i]];
-}
-template <typename V>
-__global__ void __launch_bounds__(256) k_sort_scatter(V *__restrict__ attr, const V *__restrict__ buf, const int *__restrict__ tgt,
-                                                      const i64 *__restrict__ off, const i64 *__restrict__ nbuf, int blocks_per_patch) {
-    const int p = blockIdx.x / blocks_per_patch;
-    const i64 i = (i64)(blockIdx.x - p * blocks_per_patch) * blockDim.x + threadIdx.x;
-    if (i >= nbuf[p]) return;
-    attr[off[p] + tgt[off[p] + i]] = buf[off[p] + i];
-}
-
 struct MoveArgs {
     double *a[LPIC_NPATTR];
-    int n;
-    u8 *dead;
+    int n;       // number of double attributes in this group
+    u8 *dead;    // moved with the group if not null
 };
-// all attributes in one launch (blockIdx.y = attribute, last = is_dead); staging buffer compact: [attr][sum of nbuf]
-__global__ void __launch_bounds__(256) k_sort_gather_all(MoveArgs A, double *__restrict__ buf, i64 cap, const int *__restrict__ src_of,
-                                                         const i64 *__restrict__ off, const i64 *__restrict__ nbuf,
-                                                         const i64 *__restrict__ poff, int blocks_per_patch) {
-    const int p = blockIdx.x / blocks_per_patch;
-    const i64 i = (i64)(blockIdx.x - p * blocks_per_patch) * blockDim.x + threadIdx.x;
-    if (i >= nbuf[p]) return;
-    const i64 src = off[p] + src_of[off[p] + i], dst = poff[p] + i;
-    const int y = blockIdx.y;
-    if (y < A.n) buf[(size_t)y * cap + dst] = A.a[y][src];
-    else ((u8 *)(buf + (size_t)A.n * cap))[dst] = A.dead[src];
+
+// Value move of the misplaced slots, all attributes of a group in one thread: thread i of the compact list
+// [0, sum nbuf) finds its patch by bisection of the prefix poff, then issues one independent load per attribute.
+// gather: staging[attr][i] = attr[src_of[i]]; scatter: attr[tgt[i]] = staging[attr][i] (staging is [attr][total]).
+__device__ __forceinline__ int patch_of(const i64 *__restrict__ poff, int npatch, i64 i) {
+    int lo = 0, hi = npatch - 1;  // last patch with poff[p] <= i
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (poff[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    return lo;
 }
-__global__ void __launch_bounds__(256) k_sort_scatter_all(MoveArgs A, const double *__restrict__ buf, i64 cap, const int *__restrict__ tgt,
-                                                          const i64 *__restrict__ off, const i64 *__restrict__ nbuf,
-                                                          const i64 *__restrict__ poff, int blocks_per_patch) {
-    const int p = blockIdx.x / blocks_per_patch;
-    const i64 i = (i64)(blockIdx.x - p * blocks_per_patch) * blockDim.x + threadIdx.x;
-    if (i >= nbuf[p]) return;
-    const i64 dst = off[p] + tgt[off[p] + i], src = poff[p] + i;
-    const int y = blockIdx.y;
-    if (y < A.n) A.a[y][dst] = buf[(size_t)y * cap + src];
-    else A.dead[dst] = ((const u8 *)(buf + (size_t)A.n * cap))[src];
+__global__ void __launch_bounds__(256) k_sort_gather_all(MoveArgs A, double *__restrict__ buf, i64 total, const int *__restrict__ src_of,
+                                                         const i64 *__restrict__ off, const i64 *__restrict__ poff, int npatch) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int p = patch_of(poff, npatch, i);
+    const i64 src = off[p] + src_of[off[p] + (i - poff[p])];
+    double v[LPIC_NPATTR];
+#pragma unroll
+    for (int y = 0; y < LPIC_NPATTR; y++)
+        if (y < A.n) v[y] = A.a[y][src];
+#pragma unroll
+    for (int y = 0; y < LPIC_NPATTR; y++)
+        if (y < A.n) buf[(size_t)y * total + i] = v[y];
+    if (A.dead) ((u8 *)(buf + (size_t)A.n * total))[i] = A.dead[src];
+}
+__global__ void __launch_bounds__(256) k_sort_scatter_all(MoveArgs A, const double *__restrict__ buf, i64 total, const int *__restrict__ tgt,
+                                                          const i64 *__restrict__ off, const i64 *__restrict__ poff, int npatch) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int p = patch_of(poff, npatch, i);
+    const i64 dst = off[p] + tgt[off[p] + (i - poff[p])];
+#pragma unroll
+    for (int y = 0; y < LPIC_NPATTR; y++)
+        if (y < A.n) A.a[y][dst] = buf[(size_t)y * total + i];
+    if (A.dead) A.dead[dst] = ((const u8 *)(buf + (size_t)A.n * total))[i];
 }
 
 __global__ void k_widen(const int *__restrict__ src, i64 *__restrict__ dst, i64 n) {
@@ -386,43 +384,35 @@ extern "C" int lpic_sort(lpic_ctx *c, int ispec, int reverse_x, int64_t nxb, int
     CUDA_TRY(cudaMemcpyAsync(h_nbuf.data(), d_nbuf, sizeof(i64) * n, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     if (g_hist) cudaFree(g_hist);
-    i64 total = 0, mx = 0;
-    for (i64 p = 0; p < n; p++) { total += h_nbuf[p]; mx = std::max(mx, h_nbuf[p]); }
+    i64 total = 0;
+    for (i64 p = 0; p < n; p++) total += h_nbuf[p];
     if (nbuf_total) *nbuf_total = total;
     if (total > 0) {
-        const int bpp = (int)div_up(mx, 256);
-        const unsigned grid = (unsigned)((i64)bpp * n);
-        MoveArgs A;
-        A.n = 0;
+        std::vector<i64> poff(n);
+        i64 run = 0;
+        for (i64 p = 0; p < n; p++) { poff[p] = run; run += h_nbuf[p]; }
+        i64 *d_poff = d_nbuf + n;
+        CUDA_TRY(cudaMemcpyAsync(d_poff, poff.data(), sizeof(i64) * n, cudaMemcpyHostToDevice, c->stream));
+        std::vector<double *> attrs;
         for (int at = 0; at < LPIC_NPATTR; at++)
-            if (sp.attr[at]) A.a[A.n++] = sp.attr[at];
-        A.dead = sp.dead;
-        if ((i64)(A.n + 1) * total <= c->scr_cap) {
-            // one gather and one scatter launch for all attributes through a compact staging buffer
-            std::vector<i64> poff(n);
-            i64 run = 0;
-            for (i64 p = 0; p < n; p++) { poff[p] = run; run += h_nbuf[p]; }
-            i64 *d_poff = d_nbuf + n;
-            CUDA_TRY(cudaMemcpyAsync(d_poff, poff.data(), sizeof(i64) * n, cudaMemcpyHostToDevice, c->stream));
-            dim3 g2(grid, A.n + 1);
-            k_sort_gather_all<<<g2, 256, 0, c->stream>>>(A, c->scr_buf, total, c->scr_b, sp.d_off, d_nbuf, d_poff, bpp);
-            k_sort_scatter_all<<<g2, 256, 0, c->stream>>>(A, c->scr_buf, total, c->scr_a, sp.d_off, d_nbuf, d_poff, bpp);
+            if (sp.attr[at]) attrs.push_back(sp.attr[at]);
+        // attribute groups sized to the staging buffer (scr_cap doubles): all at once while <= ~10 % of the slots move;
+        // the is_dead bytes ride with the last group if a row is left, else alone
+        const i64 room = std::max<i64>(1, c->scr_cap / total);
+        const unsigned grid = (unsigned)div_up(total, 256);
+        size_t a0 = 0;
+        bool dead_done = false;
+        while (a0 < attrs.size() || !dead_done) {
+            MoveArgs A;
+            A.n = 0;
+            A.dead = nullptr;
+            while (a0 < attrs.size() && A.n < room && A.n < LPIC_NPATTR) A.a[A.n++] = attrs[a0++];
+            if (a0 == attrs.size() && (A.n < room || A.n == 0)) { A.dead = sp.dead; dead_done = true; }
+            k_sort_gather_all<<<grid, 256, 0, c->stream>>>(A, c->scr_buf, total, c->scr_b, sp.d_off, d_poff, (int)n);
+            k_sort_scatter_all<<<grid, 256, 0, c->stream>>>(A, c->scr_buf, total, c->scr_a, sp.d_off, d_poff, (int)n);
             LAUNCHED(2);
-            KERNEL_CHECK();
-        } else {
-        for (int at = 0; at < LPIC_NPATTR; at++) {
-            if (!sp.attr[at]) continue;
-            k_sort_gather<double><<<grid, 256, 0, c->stream>>>(sp.attr[at], c->scr_buf, c->scr_b, sp.d_off, d_nbuf, bpp);
-            LAUNCHED(1);
-            k_sort_scatter<double><<<grid, 256, 0, c->stream>>>(sp.attr[at], c->scr_buf, c->scr_a, sp.d_off, d_nbuf, bpp);
-            LAUNCHED(1);
         }
-        k_sort_gather<u8><<<grid, 256, 0, c->stream>>>(sp.dead, (u8 *)c->scr_buf, c->scr_b, sp.d_off, d_nbuf, bpp);
-        LAUNCHED(1);
-        k_sort_scatter<u8><<<grid, 256, 0, c->stream>>>(sp.dead, (const u8 *)c->scr_buf, c->scr_a, sp.d_off, d_nbuf, bpp);
-        LAUNCHED(1);
         KERNEL_CHECK();
-        }
     }
     st.valid = true;
     return 0;
