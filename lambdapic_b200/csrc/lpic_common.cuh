@@ -41,6 +41,7 @@ struct Species {
     i64 *h_off = nullptr, *h_pcap = nullptr, *h_npart = nullptr;  // host copies (npatch)
     i64 *d_off = nullptr, *d_npart = nullptr;                     // device copies
     i64 max_npart = 0;
+    i64 max_incoming = -1;  // largest per-patch newcomer count of the last lpic_migrate_count (-1: unknown)
     double *attr[LPIC_NPATTR] = {nullptr};
     u8 *dead = nullptr;
     SortState sort;

@@ -430,10 +430,14 @@ extern "C" int lpic_migrate_count(lpic_ctx *c, int ispec, int64_t *to_extend, in
     LAUNCHED(1);
     KERNEL_CHECK();
     if (to_extend) CUDA_TRY(cudaMemcpyAsync(to_extend, sp.d_extend, sizeof(i64) * n, cudaMemcpyDeviceToHost, c->stream));
-    if (incoming) CUDA_TRY(cudaMemcpyAsync(incoming, sp.d_incoming, sizeof(i64) * n, cudaMemcpyDeviceToHost, c->stream));
+    std::vector<i64> h_in;
+    if (!incoming) { h_in.resize(n); incoming = h_in.data(); }
+    CUDA_TRY(cudaMemcpyAsync(incoming, sp.d_incoming, sizeof(i64) * n, cudaMemcpyDeviceToHost, c->stream));
     if (outgoing) CUDA_TRY(cudaMemcpyAsync(outgoing, sp.d_out, sizeof(i64) * n * c->g.nb, cudaMemcpyDeviceToHost, c->stream));
     if (alive) CUDA_TRY(cudaMemcpyAsync(alive, sp.d_alive, sizeof(i64) * n, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    sp.max_incoming = 0;  // sizes the grid of k_fill: one thread per newcomer, not per slot
+    for (i64 p = 0; p < n; p++) sp.max_incoming = std::max<i64>(sp.max_incoming, incoming[p]);
     return 0;
 }
 
@@ -446,8 +450,12 @@ extern "C" int lpic_migrate_fill(lpic_ctx *c, int ispec) {
     k_lists<<<(unsigned)n, T, 0, c->stream>>>(a);
     LAUNCHED(1);
     const int bpp = (int)div_up(sp.max_npart, T);
-    k_fill<<<(unsigned)((i64)bpp * n), T, 0, c->stream>>>(a, bpp);
-    LAUNCHED(1);
+    const int bpf = sp.max_incoming >= 0 ? (int)div_up(sp.max_incoming, T) : bpp;
+    sp.max_incoming = -1;  // valid for one fill only (remote newcomers change d_incoming through other entry points)
+    if (bpf > 0) {
+        k_fill<<<(unsigned)((i64)bpf * n), T, 0, c->stream>>>(a, bpf);
+        LAUNCHED(1);
+    }
     k_mark<<<(unsigned)((i64)bpp * n), T, 0, c->stream>>>(a, bpp);
     LAUNCHED(1);
     KERNEL_CHECK();
