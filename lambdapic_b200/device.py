@@ -19,7 +19,7 @@ from .fields import Fields2D, Fields3D
 
 
 class DeviceBridge:
-    def __init__(self, patches, n_guard, device=0, with_part=True, slack=1.5, nspec=0):
+    def __init__(self, patches, n_guard, device=0, with_part=True, slack=1.3, nspec=0):
         self.patches = patches
         dim = patches.dimension
         p0 = patches[0]
