@@ -291,6 +291,14 @@ def main():
     except Exception:
         pass
 
+    # ---- end to end through the public API with host buffers (every rank takes part) ---------------------------
+    eng.close()
+    e2e = None
+    if not args.no_e2e:
+        try:
+            e2e = e2e_public_api(args, wl, rank, world)
+        except Exception as exc:  # keep the device-resident line even if the host-side leg cannot run on this box
+            e2e = {"value": None, "unit": UNIT, "note": f"end-to-end leg failed: {type(exc).__name__}: {exc}"[:300]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -301,12 +309,8 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args, wl, world),
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "wall_ms_per_step": 1e3 * wall / args.steps}
 
-    # ---- end to end through the public API with host buffers ---------------------------------------------------
-    eng.close()
-    if not args.no_e2e and world == 1:
-        line["e2e"] = e2e_public_api(args, wl)
-    elif world > 1:
-        line["e2e"] = {"value": None, "unit": UNIT, "note": "measured at N=1 only in this round"}
+    if e2e is not None:
+        line["e2e"] = e2e
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_reference_run(args, steps=2, warmup=1)
     print(json.dumps(line), flush=True)
@@ -314,17 +318,27 @@ def main():
         dist.destroy_process_group()
 
 
-def e2e_public_api(args, wl):
+def e2e_public_api(args, wl, rank=0, world=1):
     """Same metric through the call a user makes: ``Simulation3D(...).run(nsteps=K, callbacks=[diag])`` with the whole
     state starting and ending in pinned HOST memory.  The timed region contains the H2D copy of all fields and
     particles at run() entry, K full steps each followed by a device->host read of the step's energy diagnostic
     (a `needs_host=False` callback at stage `end`), and the D2H copy of all state at run() exit."""
     import lambdapic_b200 as lp
+    if world > 1:
+        import psutil
+        import torch
+        import torch.distributed as dist
+        need = 130.0 * wl.n_particles()  # pinned mirrors (73 B per slot x 1.3 slack) + loader temporaries, all ranks on this host
+        ok = torch.tensor([float(psutil.virtual_memory().available > need)], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0.0:
+            return {"value": None, "unit": UNIT, "note": f"host memory too small for {world} ranks' pinned mirrors ({need / 1e9:.0f} GB)"}
     t_setup = time.perf_counter()
     per = {k: "periodic" for k in ("xmin", "xmax", "ymin", "ymax", "zmin", "zmax")}
     npx, npy, npz = wl.npatches
     sim = lp.Simulation3D(nx=wl.cells[0], ny=wl.cells[1], nz=wl.cells[2], dx=wl.d, dy=wl.d, dz=wl.d, npatch_x=npx, npatch_y=npy,
-                          npatch_z=npz, dt_cfl=wl.dt_cfl, boundary_conditions=per, random_seed=wl.seed, store_part_fields=False)
+                          npatch_z=npz, dt_cfl=wl.dt_cfl, boundary_conditions=per, random_seed=wl.seed, store_part_fields=False,
+                          device=int(os.environ.get("LOCAL_RANK", "0")))
     sim.add_species([lp.Electron(density=wl.density, ppc=wl.ppc[0]), lp.Proton(density=wl.density, ppc=wl.ppc[1])])
     sim.initialize()
     rng = np.random.default_rng(wl.seed + 1)
@@ -342,15 +356,25 @@ def e2e_public_api(args, wl):
     steps = max(1, args.steps)
     before = dict(sim.bridge.stats)
     n0 = sum(int((~pt.is_dead).sum()) for p in sim.patches for pt in p.particles)
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
     t0 = time.perf_counter()
     sim.run(nsteps=steps, callbacks=[diag])
     dt = time.perf_counter() - t0
     n1 = sum(int((~pt.is_dead).sum()) for p in sim.patches for pt in p.particles)
     st = sim.bridge.stats
+    h2d, d2h = st["h2d_bytes"] - before["h2d_bytes"], st["d2h_bytes"] - before["d2h_bytes"]
+    if world > 1:  # whole-job figures: particles and bytes summed over the ranks, time = slowest rank
+        v = torch.tensor([float(n0), float(n1), float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
+        tm = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(v, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        n0, n1, h2d, d2h, dt = int(v[0]), int(v[1]), int(v[2]), int(v[3]), float(tm[0])
     tot = [sum(h.values()) for h in hist]
     out = {"value": 0.5 * (n0 + n1) * steps / dt, "unit": UNIT,
-           "h2d_bytes_per_step": int((st["h2d_bytes"] - before["h2d_bytes"]) / steps),
-           "d2h_bytes_per_step": int((st["d2h_bytes"] - before["d2h_bytes"]) / steps + 8 * len(hist[0])),
+           "h2d_bytes_per_step": int(h2d / steps),
+           "d2h_bytes_per_step": int(d2h / steps + 8 * len(hist[0]) * world),
            "steps": steps, "ms_per_step": 1e3 * dt / steps, "setup_s": t_setup,
            "energy_drift_rel": abs(tot[-1] - tot[0]) / tot[0],
            "mode": "Simulation3D.run(nsteps=K): H2D of all state from pinned host mirrors at entry, K steps with a per-step "
