@@ -25,7 +25,12 @@ def _interval_triggered(sim, interval) -> bool:
     return True
 
 
-def callback(stage: Optional[str] = None, interval=1, needs_host: bool = True) -> Callable:
+def callback(stage: Optional[str] = None, interval=1, needs_host: bool = True, reads=None, writes=None) -> Callable:
+    """Extensions over the reference (mirror elision):
+      needs_host=False   the callback uses only device-side diagnostics (sim.energies()); no mirror traffic at all;
+      reads / writes     names of what the callback reads / modifies on the host mirrors -- field attributes ("ex" .. "rho"),
+                         "fields", "psi", "particles".  Only those cross PCIe before / after the stage; a read-only
+                         diagnostic (writes=()) costs no upload.  Without hints everything is synced both ways."""
     def decorator(func: Callable) -> Callable:
         _validate_interval(interval)
 
@@ -40,6 +45,8 @@ def callback(stage: Optional[str] = None, interval=1, needs_host: bool = True) -
         wrapper.stage = stage
         wrapper.interval = interval
         wrapper.needs_host = needs_host  # False: uses only device-side diagnostics, mirrors are not synced for it
+        wrapper.reads = None if reads is None else tuple(reads)
+        wrapper.writes = None if writes is None else tuple(writes)
         return wrapper
     return decorator
 
@@ -48,6 +55,8 @@ class Callback:
     interval = 1
     stage = None
     needs_host = True
+    reads = None   # see callback(): names touched on the host mirrors, None = everything
+    writes = None
 
     def __call__(self, sim):
         _validate_interval(self.interval)

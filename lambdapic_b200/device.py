@@ -142,20 +142,85 @@ class DeviceBridge:
         return False
 
     # ---- coherency ---------------------------------------------------------------------------------------------
-    def upload(self):
+    @staticmethod
+    def _selection(names):
+        """names (callback reads/writes hints) -> (field mask, psi?, particles?); None selects everything."""
+        if names is None:
+            return ALL_FIELDS, True, True
+        mask, psi, particles = 0, False, False
+        for n in names:
+            if n == "fields":
+                mask = ALL_FIELDS
+            elif n == "psi":
+                psi = True
+            elif n == "particles":
+                particles = True
+            elif n in FIELD_ATTRS:
+                mask |= 1 << FIELD_ATTRS.index(n)
+            else:
+                raise ValueError(f"unknown mirror name {n!r} (field attribute, 'fields', 'psi' or 'particles')")
+        return mask, psi, particles
+
+    def upload(self, names=None):
         ps, eng = self.patches, self.engine
+        mask, psi, particles = self._selection(names)
+        if not (mask or psi or particles):
+            return  # read-only callbacks: nothing to send back
         nspec = len(ps.species)
         if eng.nspec != nspec:
             self._recreate_engine_species()
-        else:
+            mask, psi, particles = ALL_FIELDS, True, True
+        elif particles:
             for s in range(nspec):
                 if self._layout_changed_on_host(s):
                     self._alloc_species_from_host(s)
-        eng.upload_all()
+        if names is None or (mask == ALL_FIELDS and psi and particles):
+            eng.upload_all()
+            nbytes = self.state_bytes()
+        else:
+            nbytes = 0
+            if mask:
+                eng.upload_fields(mask)
+                nbytes += bin(mask).count("1") * eng.fields_host[0].nbytes
+            if psi and getattr(eng, "psi_host", None) is not None:
+                eng.upload_psi()
+                nbytes += eng.psi_host.nbytes
+            if particles:
+                for s in range(eng.nspec):
+                    eng.upload_particles(s)
+                    m = eng.species[s]
+                    nbytes += m.total * (8 * len(m.attrs) + 1)
+            eng.sync()
         self.stats["uploads"] += 1
-        self.stats["h2d_bytes"] += self.state_bytes()
+        self.stats["h2d_bytes"] += int(nbytes)
 
-    def download(self):
+    def download(self, names=None):
+        eng = self.engine
+        mask, psi, particles = self._selection(names)
+        if not (mask or psi or particles):
+            return
+        if names is not None and not (mask == ALL_FIELDS and psi and particles):
+            nbytes = 0
+            if particles:
+                self._download_particles()
+                nbytes += sum(m.total * (8 * len(m.attrs) + 1) for m in eng.species)
+            if mask:
+                eng.download_fields(mask)
+                nbytes += bin(mask).count("1") * eng.fields_host[0].nbytes
+            if psi and getattr(eng, "psi_host", None) is not None:
+                eng.download_psi()
+                nbytes += eng.psi_host.nbytes
+            eng.sync()
+            self.stats["downloads"] += 1
+            self.stats["d2h_bytes"] += int(nbytes)
+            return
+        self._download_particles()
+        eng.download_fields(ALL_FIELDS)
+        eng.download_psi()
+        self.stats["downloads"] += 1
+        self.stats["d2h_bytes"] += self.state_bytes()
+
+    def _download_particles(self):
         eng = self.engine
         for s in range(eng.nspec):
             m = eng.species[s]
@@ -170,10 +235,6 @@ class DeviceBridge:
                     if not self.with_part:
                         self._host_only_part_fields(pt)
                 pt._npart_created = int(eng.npart_created[s][ip])
-        eng.download_fields(ALL_FIELDS)
-        eng.download_psi()
-        self.stats["downloads"] += 1
-        self.stats["d2h_bytes"] += self.state_bytes()
 
     def state_bytes(self):
         eng = self.engine

@@ -352,14 +352,18 @@ class Simulation:
         # callbacks that only use device-side diagnostics (sim.energies()) declare `needs_host = False` and run
         # without the host mirrors being refreshed (mirror elision)
         triggered = [cb for cb in cbs.stage_callbacks[stage] if _interval_triggered(self, getattr(cb, "interval", 1))]
-        was_resident = br.resident and any(getattr(cb, "needs_host", True) for cb in triggered)
+        hosted = [cb for cb in triggered if getattr(cb, "needs_host", True)]
+        was_resident = br.resident and bool(hosted)
         if was_resident:
-            br.download()
+            # declared reads / writes: only those arrays cross PCIe (a callback without hints syncs everything)
+            reads = None if any(getattr(cb, "reads", None) is None for cb in hosted) else {n for cb in hosted for n in cb.reads}
+            writes = None if any(getattr(cb, "writes", None) is None for cb in hosted) else {n for cb in hosted for n in cb.writes}
+            br.download(reads)
             br.resident = False
         with Timer(timer_name):
             cbs.run(stage)
         if was_resident:
-            br.upload()
+            br.upload(writes)
             br.resident = True
 
     def run(self, nsteps: int | None = None, sim_time: float | None = None, callbacks: Optional[Sequence[Callable]] = None,

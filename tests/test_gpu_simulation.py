@@ -301,3 +301,58 @@ def test_public_api_moving_window_matches_reference(dim, case, request):
     assert seen_shifts == shift_steps
     assert worst <= 1e-10
     sim.bridge.close()
+
+
+@pytest.mark.gpu
+def test_callback_read_write_hints_move_only_the_named_arrays():
+    """Mirror elision: a diagnostic that declares reads=("ex", "rho"), writes=() sees exactly what a
+    fully synced callback sees, downloads two field arrays per trigger and uploads nothing; a callback that declares
+    writes=("bz",) has its change picked up by the device."""
+    from lambdapic_b200 import Electron, Proton, Simulation, callback
+    d, n0 = 0.8e-6 / 20, 1.742e27
+
+    def build():
+        sim = Simulation(nx=32, ny=32, dx=d, dy=d, npatch_x=2, npatch_y=2, dt_cfl=0.95, random_seed=5,
+                         boundary_conditions={k: "periodic" for k in ("xmin", "xmax", "ymin", "ymax")})
+        sim.add_species([Electron(density=lambda x, y: n0, ppc=4), Proton(density=lambda x, y: n0, ppc=4)])
+
+        @callback("init")
+        def heat(sim):
+            rng = np.random.default_rng(3)
+            for p in sim.patches:
+                for part in p.particles:
+                    part.ux[:] = rng.normal(0.0, 0.05, part.npart)
+                    part.inv_gamma[:] = 1.0 / np.sqrt(1 + part.ux**2 + part.uy**2 + part.uz**2)
+        return sim, heat
+    seen = {"full": [], "hint": []}
+
+    def probe(tag):
+        def f(sim):
+            seen[tag].append([np.array(p.fields.ex).copy() for p in sim.patches] + [np.array(p.fields.rho).copy() for p in sim.patches])
+        return f
+    sim_a, heat_a = build()
+    sim_a.run(nsteps=4, callbacks=[heat_a, callback("end", interval=2)(probe("full"))])
+    sim_b, heat_b = build()
+    sim_b.initialize()
+    before = dict(sim_b.bridge.stats)
+    field_bytes = sim_b.bridge.engine.fields_host[0].nbytes
+
+    @callback("maxwell_1", interval=3, reads=("bz",), writes=("bz",))
+    def kick(sim):
+        for p in sim.patches:
+            p.fields.bz[...] += 1.0e6
+    sim_b.run(nsteps=4, callbacks=[heat_b, callback("end", interval=2, reads=("ex", "rho"), writes=())(probe("hint"))])
+    st = sim_b.bridge.stats
+    full = sim_b.bridge.state_bytes()
+    # run() entry/exit move everything once each; the two triggers of the diagnostic add 2 x 2 field arrays down, nothing up
+    assert st["d2h_bytes"] - before["d2h_bytes"] == full + 2 * 2 * field_bytes
+    assert st["h2d_bytes"] - before["h2d_bytes"] == full
+    assert len(seen["full"]) == len(seen["hint"]) == 2
+    for a, b in zip(seen["full"], seen["hint"]):
+        for x, y in zip(a, b):  # two separate runs: equal up to the order of the fp64 atomics
+            assert np.allclose(x, y, rtol=0.0, atol=1e-10 * max(float(np.abs(x).max()), 1e-300))
+    sim_b.run(nsteps=1, callbacks=[kick])  # itime == 4: not triggered (interval 3)
+    assert abs(np.mean([np.mean(p.fields.bz) for p in sim_b.patches])) < 1.0e5
+    sim_b.run(nsteps=2, callbacks=[kick])  # itime 5, 6: triggered at 6 -> the uniform offset written on the host reaches the device
+    assert np.mean([np.mean(p.fields.bz) for p in sim_b.patches]) > 5.0e5
+    sim_a.bridge.close(); sim_b.bridge.close()

@@ -132,3 +132,24 @@ def test_comm_shim_world_size_2_gloo(tmp_path):
                           "--master-port", "29517", str(script)], capture_output=True, text=True, env=env, timeout=240)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.count("ok") == 2
+
+
+def test_mirror_selection_of_callback_hints():
+    """reads / writes hints of @callback (mirror elision): names -> (field mask, psi, particles)."""
+    from lambdapic_b200 import callback
+    from lambdapic_b200._lib import FIELD_ATTRS
+    from lambdapic_b200.device import DeviceBridge
+    from lambdapic_b200.engine import ALL_FIELDS
+    sel = DeviceBridge._selection
+    assert sel(None) == (ALL_FIELDS, True, True)
+    assert sel(()) == (0, False, False)
+    assert sel(("ex", "rho")) == ((1 << FIELD_ATTRS.index("ex")) | (1 << FIELD_ATTRS.index("rho")), False, False)
+    assert sel(("fields", "psi")) == (ALL_FIELDS, True, False)
+    assert sel({"particles"}) == (0, False, True)
+    with pytest.raises(ValueError):
+        sel(("exx",))
+
+    @callback("end", interval=2, reads=("ex",), writes=())
+    def diag(sim):
+        pass
+    assert diag.reads == ("ex",) and diag.writes == () and diag.needs_host is True
