@@ -27,7 +27,8 @@ class DeviceBridge:
                                    p0.dx, p0.dy, getattr(p0, "dz", 0.0), nspec, device)
         self.dim = dim
         self.with_part, self.slack, self.device = with_part, slack, device
-        self.resident = False
+        self._resident = False
+        self.host_particles_valid = True  # False while the device may hold a newer particle layout than the host objects
         self.stats = dict(uploads=0, downloads=0, h2d_bytes=0, d2h_bytes=0)
         self._set_geometry()
         F = Fields3D if dim == 3 else Fields2D
@@ -49,6 +50,17 @@ class DeviceBridge:
                          ps.zmin_global or 0.0, ps.zmax_global or 0.0], dtype=float)
         rank = ps[0].rank or 0
         self.engine.set_geometry(x0, y0, z0, nbr, box, glob, rank, np.array([p.index for p in ps], dtype=np.int64))
+
+    @property
+    def resident(self):
+        """True while the device is authoritative (inside Simulation.run's loop)."""
+        return self._resident
+
+    @resident.setter
+    def resident(self, value):
+        self._resident = bool(value)
+        if value:
+            self.host_particles_valid = False  # from here on the device may re-lay-out its particle arenas
 
     def refresh_geometry(self, pml_changed=False):
         """Re-register origins, neighbour tables and particle boxes after the host objects changed them
@@ -171,6 +183,9 @@ class DeviceBridge:
             self._recreate_engine_species()
             mask, psi, particles = ALL_FIELDS, True, True
         elif particles:
+            if not self.host_particles_valid:
+                raise RuntimeError("the host particle mirrors are stale (the device moved on since the last download); "
+                                   "a callback that writes 'particles' must also read them")
             for s in range(nspec):
                 if self._layout_changed_on_host(s):
                     self._alloc_species_from_host(s)
@@ -222,6 +237,7 @@ class DeviceBridge:
 
     def _download_particles(self):
         eng = self.engine
+        self.host_particles_valid = True
         for s in range(eng.nspec):
             m = eng.species[s]
             reseat = m._host is None

@@ -354,12 +354,20 @@ class Simulation:
         triggered = [cb for cb in cbs.stage_callbacks[stage] if _interval_triggered(self, getattr(cb, "interval", 1))]
         hosted = [cb for cb in triggered if getattr(cb, "needs_host", True)]
         was_resident = br.resident and bool(hosted)
+        partial = False
         if was_resident:
             # declared reads / writes: only those arrays cross PCIe (a callback without hints syncs everything)
             reads = None if any(getattr(cb, "reads", None) is None for cb in hosted) else {n for cb in hosted for n in cb.reads}
             writes = None if any(getattr(cb, "writes", None) is None for cb in hosted) else {n for cb in hosted for n in cb.writes}
-            br.download(reads)
-            br.resident = False
+            partial = reads is not None and writes is not None
+            if partial:
+                # the device stays authoritative for everything that was not named: operator facades and
+                # sim.energies() called from these callbacks keep working on the device state
+                br.download(reads | writes)  # what is written back is read first (callbacks usually modify in place)
+            else:
+                reads = writes = None
+                br.download()
+                br.resident = False
         with Timer(timer_name):
             cbs.run(stage)
         if was_resident:

@@ -341,7 +341,13 @@ def test_callback_read_write_hints_move_only_the_named_arrays():
     def kick(sim):
         for p in sim.patches:
             p.fields.bz[...] += 1.0e6
-    sim_b.run(nsteps=4, callbacks=[heat_b, callback("end", interval=2, reads=("ex", "rho"), writes=())(probe("hint"))])
+    energies = []
+
+    @callback("end", needs_host=False)
+    def device_diag(sim):  # shares the stage with the hinted probe: must keep working on the DEVICE state (no upload)
+        energies.append(sim.energies())
+    sim_b.run(nsteps=4, callbacks=[heat_b, callback("end", interval=2, reads=("ex", "rho"), writes=())(probe("hint")), device_diag])
+    assert len(energies) == 4 and all(e["electric"] >= 0.0 for e in energies)
     st = sim_b.bridge.stats
     full = sim_b.bridge.state_bytes()
     # run() entry/exit move everything once each; the two triggers of the diagnostic add 2 x 2 field arrays down, nothing up
