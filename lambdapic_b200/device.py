@@ -29,6 +29,7 @@ class DeviceBridge:
         self.with_part, self.slack, self.device = with_part, slack, device
         self._resident = False
         self.host_particles_valid = True  # False while the device may hold a newer particle layout than the host objects
+        self.extended_particles = []  # particle objects flagged `extended` since the last Simulation.update_lists()
         self.stats = dict(uploads=0, downloads=0, h2d_bytes=0, d2h_bytes=0)
         self._set_geometry()
         F = Fields3D if dim == 3 else Fields2D
@@ -290,9 +291,10 @@ class DeviceBridge:
             for s in range(self.engine.nspec):
                 rec = self.engine.sync_particles(s)
                 total += rec["to_extend"]
-                for ip, p in enumerate(self.patches):
-                    if rec["to_extend"][ip] > 0:
-                        p.particles[s].extended = True
+                for ip in np.nonzero(rec["to_extend"] > 0)[0]:  # no per-patch Python loop on the (usual) quiet steps
+                    pt = self.patches[int(ip)].particles[s]
+                    pt.extended = True
+                    self.extended_particles.append(pt)
         return total
 
     def laser_bfields(self, laserpos, patches, ranges, ey_src, ez_src, dt):

@@ -46,7 +46,11 @@ class Laser:
         if self.side != "xmin":
             raise ValueError("Invalid side: only 'xmin' is supported.")
         laserpos = sim.cpml_thickness + 2
-        edge = [(ip, p) for ip, p in enumerate(sim.patches) if p.ipatch_x == 0]
+        ps = sim.patches
+        version = getattr(ps, "geometry_version", 0)  # bumped by MovingWindow when the columns rotate
+        if getattr(self, "_edge_cache", (None, None, None))[:2] != (id(ps), version):
+            self._edge_cache = (id(ps), version, [(ip, p) for ip, p in enumerate(ps) if p.ipatch_x == 0])
+        edge = self._edge_cache[2]
         if sum(m.face == "xmin" for _, p in edge for m in p.pml_boundary) < len(edge):
             self.disabled = True  # no PML at xmin (e.g. a moving window has started)
             return

@@ -73,6 +73,7 @@ class MovingWindow:
                 p.pml_boundary = [m for m in p.pml_boundary if m.axis != 0]
         if direction:
             new_patches = self._shift(sim, direction)
+            sim.patches.geometry_version = getattr(sim.patches, "geometry_version", 0) + 1
             self._update_patch_info(sim)
             self._fill_particles(sim, new_patches)
             for p in new_patches:  # recycled patches start from vacuum fields

@@ -265,9 +265,19 @@ class Simulation:
         pass
 
     def update_lists(self):
+        """simulation.py:781-824 re-creates the lists of extended patches; here only the flags are cleared.  The full
+        sweep over all patches runs when host code may have extended particles itself (mirrors authoritative)."""
+        br = getattr(self, "bridge", None)
+        if br is not None and br.resident:
+            for pt in br.extended_particles:
+                pt.extended = False
+            br.extended_particles.clear()
+            return
         for p in self.patches:
             for pt in p.particles:
                 pt.extended = False
+        if br is not None:
+            br.extended_particles.clear()
 
     # ---- currents (simulation.py:1143-1188) ---------------------------------------------------------------------
     def sync_currents(self):
