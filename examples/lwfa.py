@@ -46,7 +46,18 @@ def density(n0):
     return _density
 
 
-movingwindow = MovingWindow(velocity=lambda t: c + (t - Lx / c) * 0)
+class TimedMovingWindow(MovingWindow):
+    """MovingWindow that reports what a patch-recycling step costs (download, host re-load, upload)."""
+
+    def __call__(self, sim):
+        x0 = min(p.x0 for p in sim.patches)
+        t = time.perf_counter()
+        super().__call__(sim)
+        if min(p.x0 for p in sim.patches) != x0:
+            print(f"step {sim.itime:5d}  window shift took {time.perf_counter() - t:.2f} s", flush=True)
+
+
+movingwindow = TimedMovingWindow(velocity=lambda t: c + (t - Lx / c) * 0)
 laser = SimpleLaser2D(a0=2, w0=5e-6, l0=0.8e-6, ctau=5e-6)
 ne = 0.01 * nc
 sim = Simulation(nx=nx, ny=ny, dx=dx, dy=dy, npatch_x=10, npatch_y=10, dt_cfl=0.99, sim_time=args.sim_time, random_seed=2)

@@ -86,6 +86,10 @@ int lpic_download_particle_ptrs(lpic_ctx *ctx, int ispec, int attr, void *const 
  * (NaN attributes, w = 0, fresh ids starting at id_first[p]).  *relayout is set when a segment outgrew its
  * physical size and the arena was re-laid-out (host arena offsets must be re-read). */
 int lpic_species_extend(lpic_ctx *ctx, int ispec, const int64_t *ext, const uint64_t *id_first, int *relayout);
+/* Set the slot counts of every patch inside the EXISTING segments (npart[p] <= capacity[p], else error): used when the
+ * host re-initialised the particles of some patches (ParticlesBase.initialize, core/particles.py:118-139, called by
+ * MovingWindow._fill_particles, callback/utils.py:760-776) and uploads the new values next. */
+int lpic_species_set_npart(lpic_ctx *ctx, int ispec, const int64_t *npart);
 
 /* ---- Maxwell: core/maxwell/cpu.py:9-35 (2D), :83-112 (3D); facade core/maxwell/solver/solver.py:193-254 */
 int lpic_update_efield(lpic_ctx *ctx, double dt);

@@ -46,6 +46,7 @@ SIGNATURES = {
     "lpic_upload_particle_ptrs": (_int, [_vp, _int, _int, _vp]),
     "lpic_download_particle_ptrs": (_int, [_vp, _int, _int, _vp]),
     "lpic_species_extend": (_int, [_vp, _int, _vp, _vp, _vp]),
+    "lpic_species_set_npart": (_int, [_vp, _int, _vp]),
     "lpic_update_efield": (_int, [_vp, _dbl]),
     "lpic_update_bfield": (_int, [_vp, _dbl]),
     "lpic_pml_configure": (_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64]),

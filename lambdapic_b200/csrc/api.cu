@@ -453,6 +453,20 @@ extern "C" int lpic_species_extend(lpic_ctx *c, int ispec, const int64_t *ext, c
     return r;
 }
 
+// New slot counts inside the existing segments (every npart[p] <= capacity of patch p): the host re-initialised some
+// patches' particles (ParticlesBase.initialize after a MovingWindow shift) and uploads their values next.
+extern "C" int lpic_species_set_npart(lpic_ctx *c, int ispec, const int64_t *npart) {
+    REQUIRE(ispec >= 0 && ispec < c->nspec && c->spec[ispec].allocated, "species %d not allocated", ispec);
+    Species &sp = c->spec[ispec];
+    const i64 n = c->g.npatch;
+    for (i64 p = 0; p < n; p++)
+        REQUIRE(npart[p] >= 0 && npart[p] <= sp.h_pcap[p], "patch %lld: %lld slots do not fit the segment of %lld", (long long)p,
+                (long long)npart[p], (long long)sp.h_pcap[p]);
+    for (i64 p = 0; p < n; p++) sp.h_npart[p] = npart[p];
+    sp.sort.valid = false;
+    return upload_layout(c, sp);
+}
+
 int lpic_ensure_scratch(lpic_ctx *c, i64 slots) {
     if (slots <= c->scr_cap) return 0;
     CUDA_TRY(cudaStreamSynchronize(c->stream));

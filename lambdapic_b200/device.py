@@ -130,6 +130,34 @@ class DeviceBridge:
         if old_mirror is not None:
             old_mirror.free()
 
+    def _reseat_in_place(self, s) -> bool:
+        """Host code replaced some patches' particle arrays (initialize / extend / prune).  If every patch still fits its
+        device segment, keep all arenas (device and pinned host) and copy only the detached patches into their mirror
+        slices; returns False when a full re-allocation is needed."""
+        eng = self.engine
+        m = eng.species[s]
+        if m is None or m._host is None:
+            return False
+        parts = [p.particles[s] for p in self.patches]
+        npart = np.array([pt.npart for pt in parts], dtype=np.int64)
+        if (npart > m.pcap).any():
+            return False
+        changed = [ip for ip, pt in enumerate(parts) if pt._detached or pt.npart != int(m.npart[ip])]
+        old = {ip: ({a: getattr(parts[ip], a) for a in m.attrs}, parts[ip].is_dead) for ip in changed}
+        eng.set_npart(s, npart)  # keeps the arenas: off / total are unchanged
+        assert m._host is not None
+        for ip in changed:
+            pt = parts[ip]
+            vals, dead = old[ip]
+            self._seat(pt, m, ip)
+            for a in m.attrs:
+                getattr(pt, a)[...] = vals[a]
+            pt.is_dead[...] = dead
+            if not self.with_part:
+                self._host_only_part_fields(pt)
+            eng.npart_created[s][ip] = pt._npart_created
+        return True
+
     @staticmethod
     def _host_only_part_fields(pt):
         """store_part_fields=False: ex_part..bz_part are not resident on the device; the host objects expose
@@ -188,7 +216,7 @@ class DeviceBridge:
                 raise RuntimeError("the host particle mirrors are stale (the device moved on since the last download); "
                                    "a callback that writes 'particles' must also read them")
             for s in range(nspec):
-                if self._layout_changed_on_host(s):
+                if self._layout_changed_on_host(s) and not self._reseat_in_place(s):
                     self._alloc_species_from_host(s)
         if names is None or (mask == ALL_FIELDS and psi and particles):
             eng.upload_all()

@@ -244,6 +244,12 @@ class DeviceEngine:
         self.species[ispec].refresh_layout()
         return bool(moved.value)
 
+    def set_npart(self, ispec, npart):
+        """New slot counts inside the existing segments (each <= pcap); the host mirrors keep their arenas."""
+        npart = np.ascontiguousarray(npart, dtype=np.int64)
+        check(self.L.lpic_species_set_npart(self.ctx, ispec, _ptr(npart)))
+        self.species[ispec].refresh_layout()
+
     # ---- operators (one call each; names follow the reference facades) ------------------------------------------
     def update_efield(self, dt):
         check(self.L.lpic_update_efield(self.ctx, float(dt)))
