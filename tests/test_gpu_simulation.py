@@ -362,3 +362,38 @@ def test_callback_read_write_hints_move_only_the_named_arrays():
     sim_b.run(nsteps=2, callbacks=[kick])  # itime 5, 6: triggered at 6 -> the uniform offset written on the host reaches the device
     assert np.mean([np.mean(p.fields.bz) for p in sim_b.patches]) > 5.0e5
     sim_a.bridge.close(); sim_b.bridge.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim", [2, 3])
+def test_extract_species_density_conserves_the_species_charge(dim):
+    """ExtractSpeciesDensity (callback/utils.py:240-400): the density of every species, taken as the rho difference around
+    its deposit after a device-side guard reduce, integrates to the species' total weight (Esirkepov/TSC deposits are
+    charge conserving) and only the rho array crosses PCIe."""
+    from lambdapic_b200 import Electron, ExtractSpeciesDensity, Proton, Simulation, Simulation3D
+    d, n0 = 0.8e-6 / 20, 1.742e27
+    if dim == 3:
+        sim = Simulation3D(nx=16, ny=16, nz=16, dx=d, dy=d, dz=d, npatch_x=2, npatch_y=2, npatch_z=2, random_seed=11,
+                           boundary_conditions={k: "periodic" for k in ("xmin", "xmax", "ymin", "ymax", "zmin", "zmax")})
+        dens = lambda x, y, z: n0 * (1.0 + 0.5 * np.sin(x / (16 * d) * 2 * np.pi))  # noqa: E731
+    else:
+        sim = Simulation(nx=32, ny=32, dx=d, dy=d, npatch_x=2, npatch_y=2, random_seed=11,
+                         boundary_conditions={k: "periodic" for k in ("xmin", "xmax", "ymin", "ymax")})
+        dens = lambda x, y: n0 * (1.0 + 0.5 * np.sin(x / (32 * d) * 2 * np.pi))  # noqa: E731
+    ele, pro = Electron(density=dens, ppc=4), Proton(density=dens, ppc=2)
+    sim.add_species([ele, pro])
+    sim.initialize()
+    ne, npr = ExtractSpeciesDensity(sim, ele, interval=2), ExtractSpeciesDensity(sim, pro, interval=2)
+    before = dict(sim.bridge.stats)
+    sim.run(nsteps=3, callbacks=[ne, npr])
+    dV = d ** dim
+    for diag, isp in ((ne, 0), (npr, 1)):
+        total_w = sum(float(p.particles[isp].w[~np.asarray(p.particles[isp].is_dead)].sum()) for p in sim.patches)
+        assert diag.density.shape == ((16, 16, 16) if dim == 3 else (32, 32))
+        assert abs(diag.density.sum() * dV - total_w) <= 1e-10 * total_w
+        assert diag.density.min() > 0.2 * n0 and diag.density.max() < 2.5 * n0
+    st = sim.bridge.stats
+    rho_bytes = sim.bridge.engine.fields_host[0].nbytes
+    # steps 0 and 2 trigger; per trigger rho is fetched after species 0 (density of e-, previous rho of p+) and after species 1
+    assert st["d2h_bytes"] - before["d2h_bytes"] == sim.bridge.state_bytes() + 2 * 3 * rho_bytes
+    sim.bridge.close()
