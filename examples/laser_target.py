@@ -5,8 +5,8 @@
     10 particles per cell each, ~1.9e6 particles), Gaussian laser a0 = 10 from the xmin antenna, 2001 steps.
 
 Same constructor calls as the reference script; its HDF5 / plotting callbacks (outside the accelerated path) are replaced
-by a device-side energy diagnostic and one read-only field probe that uses the `reads=` hint, so the only per-step PCIe
-traffic is a handful of doubles.  Prints steps/s and particle-updates/s.
+by `ExtractSpeciesDensity`, a device-side energy diagnostic and one read-only field probe that uses the `reads=` hint, so the
+only per-step PCIe traffic is a handful of doubles.  Prints steps/s and particle-updates/s.
 
     python examples/laser_target.py [--nsteps 2001] [--nx 1024]
 """
@@ -18,7 +18,8 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from lambdapic_b200 import Electron, GaussianLaser2D, Proton, Simulation, Species, c, callback, e, epsilon_0, m_e, pi  # noqa: E402
+from lambdapic_b200 import (Electron, ExtractSpeciesDensity, GaussianLaser2D, Proton, Simulation, Species, c, callback, e,  # noqa: E402
+                            epsilon_0, m_e, pi)
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--nsteps", type=int, default=2001)
@@ -51,6 +52,7 @@ proton = Proton(density=density(10 * nc / 8 * 2), ppc=10)
 carbon = Species(name="C", charge=6, mass=12 * 1800, density=density(10 * nc / 8), ppc=10)
 sim.add_species([ele, carbon, proton])
 
+n_ele = ExtractSpeciesDensity(sim, ele, 500)  # as in the reference script; the guard reduce runs on the device, only rho is fetched
 history = []
 
 
@@ -62,7 +64,7 @@ def energies(sim):  # device-side reductions, no mirror traffic
 @callback("end", interval=500, reads=("ey",), writes=())
 def probe(sim):  # what PlotFields / SaveFieldsToHDF5 would read: one field array crosses PCIe, nothing goes back
     a0 = max(float(np.abs(p.fields.ey).max()) for p in sim.patches) * e / (m_e * c * omega0)
-    print(f"step {sim.itime:5d}  max |a_y| = {a0:.3f}", flush=True)
+    print(f"step {sim.itime:5d}  max |a_y| = {a0:.3f}  max n_e = {n_ele.density.max() / nc:.2f} n_c", flush=True)
 
 
 if __name__ == "__main__":
@@ -70,7 +72,7 @@ if __name__ == "__main__":
     sim.initialize()
     npart = sum(int((~pt.is_dead).sum()) for p in sim.patches for pt in p.particles)
     t1 = time.perf_counter()
-    sim.run(callbacks=[laser, energies, probe])
+    sim.run(callbacks=[laser, n_ele, energies, probe])
     t2 = time.perf_counter()
     n_end = sum(int((~pt.is_dead).sum()) for p in sim.patches for pt in p.particles)
     steps = sim.itime
