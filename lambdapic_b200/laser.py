@@ -36,6 +36,23 @@ class Laser:
             if m.face == "zmax": r[3] = f.nz - m.thickness
         return r
 
+    def _stacked_edge(self, edge):
+        """Virtual patch holding the transverse node coordinates of all antenna patches, stacked along y."""
+        if not edge:
+            return None
+        f0 = edge[0][1].fields
+        shape = tuple(f0.shape[1:])  # (NY,) or (NY, NZ)
+
+        class _V:  # duck-typed like Patch / Fields for _calculate_bound_fields
+            pass
+        vp, vf = _V(), _V()
+        vf.yaxis = np.concatenate([np.broadcast_to(p.fields.yaxis[0], shape) for _, p in edge])[None]
+        if len(shape) == 2:
+            vf.zaxis = np.concatenate([np.broadcast_to(p.fields.zaxis[0], shape) for _, p in edge])[None]
+        vp.fields = vf
+        vp.flat_shape = vf.yaxis.shape[1:]
+        return vp, shape, [ip for ip, _ in edge], [self._ranges(p) for _, p in edge]
+
     def __call__(self, sim):
         """laser.py:109-137"""
         if self.disabled:
@@ -48,24 +65,25 @@ class Laser:
         laserpos = sim.cpml_thickness + 2
         ps = sim.patches
         version = getattr(ps, "geometry_version", 0)  # bumped by MovingWindow when the columns rotate
-        if getattr(self, "_edge_cache", (None, None, None))[:2] != (id(ps), version):
-            self._edge_cache = (id(ps), version, [(ip, p) for ip, p in enumerate(ps) if p.ipatch_x == 0])
-        edge = self._edge_cache[2]
+        if getattr(self, "_edge_cache", (None, None))[:2] != (id(ps), version):
+            edge = [(ip, p) for ip, p in enumerate(ps) if p.ipatch_x == 0]
+            self._edge_cache = (id(ps), version, edge, self._stacked_edge(edge))
+        edge, stacked = self._edge_cache[2], self._edge_cache[3]
         if sum(m.face == "xmin" for _, p in edge for m in p.pml_boundary) < len(edge):
             self.disabled = True  # no PML at xmin (e.g. a moving window has started)
             return
-        patches, ranges, eys, ezs = [], [], [], []
-        for ip, p in edge:
-            ey_s, ez_s = self._calculate_bound_fields(sim, p)
-            if ey_s is None:
-                continue
-            shape = p.fields.shape[1:]
-            patches.append(ip)
-            ranges.append(self._ranges(p))
-            eys.append(np.broadcast_to(np.asarray(ey_s, dtype=np.float64), shape))
-            ezs.append(np.broadcast_to(np.asarray(ez_s, dtype=np.float64), shape))
-        if patches:
-            sim.bridge.laser_bfields(laserpos, patches, ranges, np.stack(eys), np.stack(ezs), sim.dt)
+        if not edge:
+            sim.mpi.comm.Barrier()
+            return
+        # ONE evaluation of the source formulas for all antenna patches: their transverse coordinates are stacked into a
+        # single virtual patch (the formulas are elementwise), instead of ~10 small numpy calls per patch and step
+        vpatch, shape, patches, ranges = stacked
+        ey_s, ez_s = self._calculate_bound_fields(sim, vpatch)
+        if ey_s is not None:
+            full = (len(edge),) + shape
+            eys = np.ascontiguousarray(np.broadcast_to(np.asarray(ey_s, dtype=np.float64), vpatch.flat_shape)).reshape(full)
+            ezs = np.ascontiguousarray(np.broadcast_to(np.asarray(ez_s, dtype=np.float64), vpatch.flat_shape)).reshape(full)
+            sim.bridge.laser_bfields(laserpos, patches, ranges, eys, ezs, sim.dt)
         sim.mpi.comm.Barrier()
 
     def __add__(self, other):
