@@ -284,6 +284,7 @@ extern "C" int lpic_upload_particles(lpic_ctx *c, int ispec, int attr, const voi
     if (int r = particle_array(c, ispec, attr, &dev, &esz)) return r;
     CUDA_TRY(cudaMemcpyAsync(dev, host, esz * c->spec[ispec].total, cudaMemcpyHostToDevice, c->stream));
     c->spec[ispec].sort.valid = false;
+    c->spec[ispec].lists_valid = false;
     return 0;
 }
 extern "C" int lpic_download_particles(lpic_ctx *c, int ispec, int attr, void *host) {
@@ -301,6 +302,7 @@ extern "C" int lpic_upload_particle_ptrs(lpic_ctx *c, int ispec, int attr, const
         if (sp.h_npart[p] > 0)
             CUDA_TRY(cudaMemcpyAsync((char *)dev + esz * sp.h_off[p], ptrs[p], esz * sp.h_npart[p], cudaMemcpyHostToDevice, c->stream));
     sp.sort.valid = false;
+    sp.lists_valid = false;
     return 0;
 }
 extern "C" int lpic_download_particle_ptrs(lpic_ctx *c, int ispec, int attr, void *const *ptrs) {
@@ -450,6 +452,7 @@ extern "C" int lpic_species_extend(lpic_ctx *c, int ispec, const int64_t *ext, c
     cudaFree(d_ext);
     cudaFree(d_attrs);
     sp.sort.valid = false;
+    sp.lists_valid = false;
     return r;
 }
 
@@ -464,10 +467,12 @@ extern "C" int lpic_species_set_npart(lpic_ctx *c, int ispec, const int64_t *npa
                 (long long)npart[p], (long long)sp.h_pcap[p]);
     for (i64 p = 0; p < n; p++) sp.h_npart[p] = npart[p];
     sp.sort.valid = false;
+    sp.lists_valid = false;
     return upload_layout(c, sp);
 }
 
 int lpic_ensure_scratch(lpic_ctx *c, i64 slots) {
+    c->scratch_epoch++;  // every caller is about to overwrite (part of) the shared lists
     if (slots <= c->scr_cap) return 0;
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     cudaFree(c->scr_a); cudaFree(c->scr_b); cudaFree(c->scr_buf);

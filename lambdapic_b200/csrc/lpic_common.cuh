@@ -41,6 +41,8 @@ struct Species {
     i64 *h_off = nullptr, *h_pcap = nullptr, *h_npart = nullptr;  // host copies (npatch)
     i64 *d_off = nullptr, *d_npart = nullptr;                     // device copies
     i64 max_npart = 0;
+    bool lists_valid = false;  // migrate.cu: la / lb / out / ndead of the last k_lists still describe the slots ...
+    unsigned long long lists_epoch = 0;  // ... and nobody else used the shared scratch lists since (lpic_ctx::scratch_epoch)
     i64 max_incoming = -1;  // largest per-patch newcomer count of the last lpic_migrate_count (-1: unknown)
     double *attr[LPIC_NPATTR] = {nullptr};
     u8 *dead = nullptr;
@@ -102,6 +104,7 @@ struct lpic_ctx {
     int *scr_a = nullptr, *scr_b = nullptr;  // int32 lists
     double *scr_buf = nullptr;               // staging for the sort's value move
     i64 scr_cap = 0;
+    unsigned long long scratch_epoch = 0;    // bumped by every user of the scratch lists (lpic_ensure_scratch)
     double *d_sort_org = nullptr;            // (3, npatch) bucket origins
     i64 *d_tmp64 = nullptr;                  // small reductions (>= 8 + npatch words)
     double *d_tmpf = nullptr;

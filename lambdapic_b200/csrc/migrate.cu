@@ -6,10 +6,11 @@
 //   incoming stream of patch p = for b in enum order (neighbour q = nbr[p][b] >= 0):
 //                                    q's alive leavers towards opposite(b), ascending slot order
 //   k-th incoming particle -> k-th dead slot of p (ascending).
-// Device plan: (1) one CTA per patch counts leavers per direction and dead slots; (2) one thread per patch
-// derives incoming / alive / npart_to_extend; [host grows the arrays: lpic_species_extend]; (3) one CTA per
-// patch lists its leavers grouped by direction (stable) and its dead slots; (4) one thread per incoming
-// particle copies every attribute; (5) out-of-box particles are killed.
+// Device plan: (1) k_lists, one CTA per patch and ONE classification pass: leavers counted per direction and listed
+// grouped by direction (stable), dead slots counted and listed; (2) k_plan, one thread per patch: incoming / alive /
+// npart_to_extend; [host grows the arrays: lpic_species_extend -- only then are the lists rebuilt]; (3) k_fill, one
+// thread per incoming particle copies every attribute; (4) k_mark kills the listed leavers (and NaNs the unfilled dead
+// slots in 3D) from the lists, without classifying again.
 #include <vector>
 #include "lpic_common.cuh"
 
@@ -68,29 +69,6 @@ __device__ __forceinline__ int block_incl_sum(int v, int *sw, int &total) {
     return v + add;
 }
 
-__global__ void __launch_bounds__(T) k_count(MigArgs a) {
-    __shared__ int s_out[32];
-    __shared__ int s_dead;
-    const int p = blockIdx.x, tid = threadIdx.x;
-    if (tid < 32) s_out[tid] = 0;
-    if (tid == 0) s_dead = 0;
-    __syncthreads();
-    const i64 off = a.off[p];
-    const int np = (int)a.npart[p];
-    const double *bx = a.box + 6 * (size_t)p;
-    int mydead = 0;
-    for (int ip = tid; ip < np; ip += T) {
-        if (a.dead[off + ip]) { mydead++; continue; }
-        const int b = classify(a, bx, off + ip);
-        if (b >= 0) atomicAdd(&s_out[b], 1);
-    }
-    mydead = __reduce_add_sync(0xffffffffu, mydead);
-    if ((tid & 31) == 0 && mydead) atomicAdd(&s_dead, mydead);
-    __syncthreads();
-    if (tid < a.nb) a.out[(size_t)p * a.nb + tid] = s_out[tid];
-    if (tid == 0) a.ndead[p] = s_dead;
-}
-
 __global__ void k_plan(MigArgs a) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.npatch) return;
@@ -106,22 +84,17 @@ __global__ void k_plan(MigArgs a) {
     a.extend[p] = incoming - ndead > 0 ? incoming - ndead + (i64)((double)npart * 0.25) : 0;
 }
 
-// leavers grouped by direction (stable, ascending slots) into lb[off ..]; dead slots ascending into la from the back
+// ONE classification pass per patch: leavers counted per direction (out), listed grouped by direction (stable, ascending
+// slots) in lb[off ..]; dead slots counted (ndead) and listed ascending in la from the back.
 __global__ void __launch_bounds__(T) k_lists(MigArgs a) {
     __shared__ int sw[T / 32];
     __shared__ int s_cur[32];
+    __shared__ int s_cnt[32];
     const int p = blockIdx.x, tid = threadIdx.x;
     const i64 off = a.off[p];
     const int np = (int)a.npart[p];
     const double *bx = a.box + 6 * (size_t)p;
-    if (tid == 0) {
-        int run = 0;
-        for (int b = 0; b < a.nb; b++) {
-            s_cur[b] = run;
-            a.dirstart[(size_t)p * a.nb + b] = run;
-            run += (int)a.out[(size_t)p * a.nb + b];
-        }
-    }
+    if (tid < 32) s_cnt[tid] = 0;
     __syncthreads();
     int nl = 0, nd = 0;
     constexpr int IT = 4;  // consecutive slots per thread and scan step
@@ -135,7 +108,11 @@ __global__ void __launch_bounds__(T) k_lists(MigArgs a) {
             isdead[j] = leaves[j] = false;
             if (ip < np) {
                 isdead[j] = a.dead[off + ip] != 0;
-                if (!isdead[j]) leaves[j] = classify(a, bx, off + ip) >= 0;
+                if (!isdead[j]) {
+                    const int b = classify(a, bx, off + ip);
+                    leaves[j] = b >= 0;
+                    if (b >= 0) atomicAdd(&s_cnt[b], 1);
+                }
             }
             cl += leaves[j];
             cd += isdead[j];
@@ -153,7 +130,18 @@ __global__ void __launch_bounds__(T) k_lists(MigArgs a) {
         }
         __syncthreads();
     }
-    if (tid == 0) a.ndead[p] = nd;  // dead slots after the host grew the arrays
+    __syncthreads();
+    if (tid == 0) {
+        a.ndead[p] = nd;
+        int run = 0;
+        for (int b = 0; b < a.nb; b++) {
+            s_cur[b] = run;
+            a.dirstart[(size_t)p * a.nb + b] = run;
+            a.out[(size_t)p * a.nb + b] = s_cnt[b];
+            run += s_cnt[b];
+        }
+    }
+    __syncthreads();
     // stable grouping by direction: warps take turns, lanes of one direction get consecutive places
     for (int base = 0; base < nl; base += T) {
         const int i = base + tid;
@@ -215,25 +203,31 @@ __global__ void __launch_bounds__(T) k_fill(MigArgs a, int blocks_per_patch) {
 }
 
 // mark_out_of_bound_as_dead (:326-346): alive outside the box -> dead with NaN position; in 3D every dead slot's
-// position is NaN'd, in 2D only the freshly killed ones (sync_particles_2d.c:185-202).
-__global__ void __launch_bounds__(T) k_mark(MigArgs a, int blocks_per_patch) {
-    const int p = blockIdx.x / blocks_per_patch;
-    const i64 t = (i64)(blockIdx.x - p * blocks_per_patch) * blockDim.x + threadIdx.x;
-    if (t >= a.npart[p]) return;
-    const i64 ip = a.off[p] + t;
-    bool out = false;
-    if (a.dead[ip]) {
-        if (a.dim != 3) return;
-        out = true;
-    } else if (classify(a, a.box + 6 * (size_t)p, ip) >= 0) {
-        out = true;
+// position is NaN'd, in 2D only the freshly killed ones (sync_particles_2d.c:185-202).  Works from the lists of k_lists
+// (leavers in lb, dead slots in la; the first min(incoming, ndead) dead slots were just filled and are alive again), so
+// nothing is classified a third time.  One CTA per patch.
+__global__ void __launch_bounds__(T) k_mark(MigArgs a) {
+    const int p = blockIdx.x;
+    const i64 off = a.off[p];
+    const int np = (int)a.npart[p];
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    int nl = 0;
+    for (int b = 0; b < a.nb; b++) nl += (int)a.out[(size_t)p * a.nb + b];
+    for (int i = threadIdx.x; i < nl; i += T) {
+        const i64 ip = off + a.lb[off + i];
         a.dead[ip] = 1;
-    }
-    if (out) {
-        const double nan = __longlong_as_double(0x7ff8000000000000ll);
         a.x[ip] = nan;
         a.y[ip] = nan;
         if (a.dim == 3) a.z[ip] = nan;
+    }
+    if (a.dim != 3) return;
+    const int nd = (int)a.ndead[p];
+    const int filled = (int)(a.incoming[p] < nd ? a.incoming[p] : nd);
+    for (int k = filled + threadIdx.x; k < nd; k += T) {
+        const i64 ip = off + a.la[off + np - 1 - k];
+        a.x[ip] = nan;
+        a.y[ip] = nan;
+        a.z[ip] = nan;
     }
 }
 
@@ -330,9 +324,8 @@ extern "C" int lpic_remote_migrate_prepare(lpic_ctx *c, int ispec, int64_t *send
     Species &sp = c->spec[ispec];
     const i64 n = c->g.npatch;
     const int nb = c->g.nb;
-    k_count<<<(unsigned)n, T, 0, c->stream>>>(a);
-    k_lists<<<(unsigned)n, T, 0, c->stream>>>(a);
-    LAUNCHED(2);
+    k_lists<<<(unsigned)n, T, 0, c->stream>>>(a);  // counts + lists in one classification pass
+    LAUNCHED(1);
     KERNEL_CHECK();
     std::vector<i64> out(n * nb);
     CUDA_TRY(cudaMemcpyAsync(out.data(), sp.d_out, sizeof(i64) * n * nb, cudaMemcpyDeviceToHost, c->stream));
@@ -379,6 +372,7 @@ extern "C" int lpic_remote_migrate_pack(lpic_ctx *c, int ispec, int slot, double
     LAUNCHED(1);
     KERNEL_CHECK();
     c->spec[ispec].sort.valid = false;
+    c->spec[ispec].lists_valid = false;
     return 0;
 }
 
@@ -415,6 +409,7 @@ extern "C" int lpic_remote_migrate_unpack(lpic_ctx *c, int ispec, const int64_t 
     KERNEL_CHECK();
     CUDA_TRY(cudaStreamSynchronize(c->stream));  // the host vectors above must outlive the copies
     c->spec[ispec].sort.valid = false;
+    c->spec[ispec].lists_valid = false;
     return 0;
 }
 
@@ -424,8 +419,10 @@ extern "C" int lpic_migrate_count(lpic_ctx *c, int ispec, int64_t *to_extend, in
     if (int r = make_args(c, ispec, a)) return r;
     Species &sp = c->spec[ispec];
     const i64 n = c->g.npatch;
-    k_count<<<(unsigned)n, T, 0, c->stream>>>(a);
+    k_lists<<<(unsigned)n, T, 0, c->stream>>>(a);  // counts + leaver / dead-slot lists in one classification pass
     LAUNCHED(1);
+    sp.lists_valid = true;  // until the arrays grow (lpic_species_extend), anything else touches the slots ...
+    sp.lists_epoch = c->scratch_epoch;  // ... or another operator uses the shared scratch lists
     k_plan<<<div_up(n, 128), 128, 0, c->stream>>>(a);
     LAUNCHED(1);
     KERNEL_CHECK();
@@ -443,12 +440,16 @@ extern "C" int lpic_migrate_count(lpic_ctx *c, int ispec, int64_t *to_extend, in
 
 extern "C" int lpic_migrate_fill(lpic_ctx *c, int ispec) {
     MigArgs a;
+    const unsigned long long epoch = c->scratch_epoch;
     if (int r = make_args(c, ispec, a)) return r;
     Species &sp = c->spec[ispec];
     const i64 n = c->g.npatch;
     if (sp.max_npart == 0) return 0;
-    k_lists<<<(unsigned)n, T, 0, c->stream>>>(a);
-    LAUNCHED(1);
+    if (!sp.lists_valid || sp.lists_epoch != epoch) {  // e.g. the host grew some patches after the count: the new (dead) slots must enter the lists
+        k_lists<<<(unsigned)n, T, 0, c->stream>>>(a);
+        LAUNCHED(1);
+    }
+    sp.lists_valid = false;
     const int bpp = (int)div_up(sp.max_npart, T);
     const int bpf = sp.max_incoming >= 0 ? (int)div_up(sp.max_incoming, T) : bpp;
     sp.max_incoming = -1;  // valid for one fill only (remote newcomers change d_incoming through other entry points)
@@ -456,9 +457,10 @@ extern "C" int lpic_migrate_fill(lpic_ctx *c, int ispec) {
         k_fill<<<(unsigned)((i64)bpf * n), T, 0, c->stream>>>(a, bpf);
         LAUNCHED(1);
     }
-    k_mark<<<(unsigned)((i64)bpp * n), T, 0, c->stream>>>(a, bpp);
+    k_mark<<<(unsigned)n, T, 0, c->stream>>>(a);
     LAUNCHED(1);
     KERNEL_CHECK();
     sp.sort.valid = false;
+    sp.lists_valid = false;
     return 0;
 }

@@ -177,6 +177,7 @@ int launch_particles(lpic_ctx *c, int ispec, double dt, double q, double m, bool
         return -2;
     }
     if (sp.max_npart == 0) return 0;
+    sp.lists_valid = false;  // positions change: the migration lists no longer describe the slots
     const Geom &g = c->g;
     const int B = 128;
     const int bpp = (int)div_up(sp.max_npart, B);
@@ -202,6 +203,7 @@ extern "C" int lpic_push_deposit(lpic_ctx *c, int ispec, double dt, double q, do
         lpic_set_error("species %d was allocated without ex_part..bz_part", ispec);
         return -2;
     }
+    c->spec[ispec].lists_valid = false;
     if (!(flags & LPIC_PUSH_SLOT_ORDER)) {  // default: cell-ordered warp-cooperative kernel (3D), see push_sorted.cu
         const int r = lpic_push_deposit_sorted(c, ispec, dt, q, m, write_part);
         if (r <= 0) return r;
@@ -255,5 +257,6 @@ extern "C" int lpic_species_init_uniform(lpic_ctx *c, int ispec, int64_t ppc, do
     LAUNCHED(1);
     KERNEL_CHECK();
     sp.sort.valid = false;
+    sp.lists_valid = false;
     return 0;
 }

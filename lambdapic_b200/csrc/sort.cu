@@ -415,6 +415,7 @@ extern "C" int lpic_sort(lpic_ctx *c, int ispec, int reverse_x, int64_t nxb, int
         KERNEL_CHECK();
     }
     st.valid = true;
+    sp.lists_valid = false;  // slots were permuted
     return 0;
 }
 
