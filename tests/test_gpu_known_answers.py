@@ -182,3 +182,40 @@ def test_sort_tables_sortedness_and_idempotence(dim):
             assert np.all(np.diff(keys[~dead]) >= 0), "alive particles are ordered by bucket after the sort"
         assert eng.sort(0, False) == 0, "a sorted species has nothing to move"
     eng.close()
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_shift_by_one_cell_migration_counts(dim):
+    """tests/mpi/test_syncparticles.py:63-116 on one rank: move every particle by +dx; each patch then sends exactly the
+    particles of its last cell column through xmax, receives as many as its xmin neighbour sent (periodic), nothing
+    crosses any other boundary, and the number of alive particles is conserved."""
+    wl = _plasma(dim, temperature_eV=1.0)
+    eng = build_engine(wl, with_part=False)
+    pg = eng.grid
+    m = eng.species[0]
+    eng.download_particles(0)
+    eng.sync()
+    alive0 = int((m.host["is_dead"] == 0).sum())
+    expect_out = np.zeros(eng.npatch, dtype=np.int64)
+    for ip in range(eng.npatch):
+        x = m.view("x", ip)
+        x += pg.dx
+        xmax_box = pg.x0[ip] + (pg.nx - 1) * pg.dx + pg.dx / 2
+        expect_out[ip] = int((x > xmax_box).sum())
+    eng.upload_particles(0)
+    rec = eng.migrate_count(0)
+    out = rec["outgoing"].reshape(eng.npatch, eng.nb)
+    assert np.array_equal(out[:, 1], expect_out) and expect_out.min() > 0      # boundary 1 = xmax
+    assert out[:, [b for b in range(eng.nb) if b != 1]].sum() == 0
+    xmin_nbr = pg.neighbor_ipatch[:, 0]                                          # boundary 0 = xmin
+    assert np.array_equal(rec["incoming"], expect_out[xmin_nbr])
+    eng.extend(0, rec["to_extend"])
+    eng.migrate_fill(0)
+    assert eng.count_alive(0) == alive0
+    eng.download_particles(0)
+    eng.sync()
+    for ip in range(eng.npatch):  # everybody is inside its patch box again (periodic wrap applied to the newcomers)
+        x, dead = m.view("x", ip), m.view("is_dead", ip).astype(bool)
+        lo, hi = pg.x0[ip] - pg.dx / 2, pg.x0[ip] + (pg.nx - 1) * pg.dx + pg.dx / 2
+        assert np.all((x[~dead] >= lo) & (x[~dead] <= hi))
+    eng.close()
