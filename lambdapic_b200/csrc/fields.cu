@@ -240,6 +240,7 @@ __device__ __forceinline__ int logical(int s, int n, int ng) { return s < n + ng
 // dst[-ng,0) <- src[n-ng,n), dst[n,n+ng) <- src[0,ng) per axis (sync_fields2d.c:191-196).  Every guard cell has
 // exactly one source, so the order of boundaries in the reference does not matter for a copy.
 struct AttrList {
+    int n;
     int a[LPIC_NFIELD];
 };
 __global__ void __launch_bounds__(256) k_sync_guard(Geom g, double *__restrict__ F, const i64 *__restrict__ nbr,
@@ -268,8 +269,15 @@ __global__ void __launch_bounds__(256) k_sync_guard(Geom g, double *__restrict__
     const int qi = li - sx * g.nx, qj = lj - sy * g.ny, qk = lk - sz * g.nz;  // interior of the neighbour
     const int src = qk + g.NZ * (qj + g.NY * qi);
     const int dst = sk + g.NZ * (sj + g.NY * si);
-    double *base = F + (size_t)attrs.a[blockIdx.y] * g.npatch * g.ncell;
-    base[(size_t)p * g.ncell + dst] = base[(size_t)q * g.ncell + src];
+    // every requested component in the same thread: the index arithmetic is paid once and the loads are independent
+    const size_t stride = (size_t)g.npatch * g.ncell, from = (size_t)q * g.ncell + src, to = (size_t)p * g.ncell + dst;
+    double v[LPIC_NFIELD];
+#pragma unroll
+    for (int ai = 0; ai < LPIC_NFIELD; ai++)
+        if (ai < attrs.n) v[ai] = F[attrs.a[ai] * stride + from];
+#pragma unroll
+    for (int ai = 0; ai < LPIC_NFIELD; ai++)
+        if (ai < attrs.n) F[attrs.a[ai] * stride + to] = v[ai];
 }
 
 // bit masks of the boundaries whose direction component along an axis is -1 / 0 / +1 (generated from kDir3 / kDir2)
@@ -449,7 +457,8 @@ extern "C" int lpic_sync_guard_fields(lpic_ctx *c, uint32_t attr_mask) {
     for (int a = 0; a < LPIC_NFIELD; a++)
         if (attr_mask & (1u << a)) attrs.a[na++] = a;
     if (!na) return 0;
-    dim3 grid(div_up((i64)g.npatch * g.ncell, 256), na);
+    attrs.n = na;
+    const unsigned grid = (unsigned)div_up((i64)g.npatch * g.ncell, 256);
     k_sync_guard<<<grid, 256, 0, c->stream>>>(g, c->fields, c->d_nbr, attrs);
     LAUNCHED(1);
     KERNEL_CHECK();
