@@ -6,8 +6,9 @@
 
 Workload (config.workload): BASELINE.json configs[4], "3D uniform thermal plasma weak scaling": periodic
 electron-proton plasma, n = n_c(0.8 um), d = lambda/20, 1 keV, 16+16 particles per cell, 16^3-cell patches,
-256^3 cells PER GPU (N = 8 is the full 512^3 box).  configs[1..3] need CPML + laser (SURVEY.md 8(f), next tier)
-and configs[0] is the reference's own CPU-sized test, used by the parity tests.
+256^3 cells PER GPU (N = 8 is the full 512^3 box).  configs[1..3] (laser / CPML / moving-window scripts) run through
+the public API in examples/ and are parity cases; configs[0] is the reference's own CPU-sized test, used by the parity
+tests.  Defaults: 20 timed steps after 5 warm-up steps.
 
 One "step" = everything simulation/simulation.py:937-1130 does between stage `start` and stage `end` for the
 periodic unified-pusher case: 4 FDTD half steps, 4 guard syncs, per-species sort, J/rho reset, fused
