@@ -104,6 +104,7 @@ struct lpic_ctx {
     int *scr_a = nullptr, *scr_b = nullptr;  // int32 lists
     double *scr_buf = nullptr;               // staging for the sort's value move
     i64 scr_cap = 0;
+    bool perm_attr_set = false;              // k_cell_perm's dynamic shared-memory limit raised on this context's device
     unsigned long long scratch_epoch = 0;    // bumped by every user of the scratch lists (lpic_ensure_scratch)
     double *d_sort_org = nullptr;            // (3, npatch) bucket origins
     i64 *d_tmp64 = nullptr;                  // small reductions (>= 8 + npatch words)

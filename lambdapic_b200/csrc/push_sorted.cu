@@ -561,10 +561,9 @@ int lpic_push_deposit_sorted(lpic_ctx *c, int ispec, double dt, double q, double
     int *d_ncross = (int *)(c->d_tmp64 + 64 + g.npatch);
     a.nalive = d_nalive;
     const size_t smem = sizeof(int) * (size_t)a.kx * a.ky * a.kz;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!c->perm_attr_set) {  // per context: function attributes are per device, and a process may drive several
         CUDA_TRY(cudaFuncSetAttribute(k_cell_perm, cudaFuncAttributeMaxDynamicSharedMemorySize, KEY_LIMIT * (int)sizeof(int)));
-        attr_set = true;
+        c->perm_attr_set = true;
     }
     CUDA_TRY(cudaMemsetAsync(d_ncross, 0, sizeof(int) * g.npatch, c->stream));
     k_cell_perm<<<g.npatch, PT, smem, c->stream>>>(a);
