@@ -27,7 +27,7 @@ namespace {
 
 constexpr int PUSH_WARPS = 4;      // warps per CTA of the particle kernel (128 threads)
 constexpr int PT = 256;          // threads of the permutation CTA
-constexpr int KEY_LIMIT = 24576;  // cells per patch that fit the shared-memory histogram (96 KB)
+constexpr int KEY_LIMIT = 57344;  // cells per patch that fit the shared-memory histogram (224 KB of the 227 KB a CTA may use)
 
 __device__ __forceinline__ int warp_incl_sum(int v) {
     const int lane = threadIdx.x & 31;
