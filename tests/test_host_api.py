@@ -153,3 +153,46 @@ def test_mirror_selection_of_callback_hints():
     def diag(sim):
         pass
     assert diag.reads == ("ex",) and diag.writes == () and diag.needs_host is True
+
+
+@pytest.mark.parametrize("dim,npatch,periodic", [(2, (4, 3, 1), (True, False, True)), (2, (3, 2, 1), (False, True, True)),
+                                                  (3, (2, 3, 2), (True, True, False)), (3, (3, 1, 2), (False, False, True))])
+def test_neighbour_tables_rebuilt_from_patch_positions_match_the_grid_builder(dim, npatch, periodic):
+    """Patches.init_rect_neighbor_index_* (used again after a MovingWindow shift, core/patch/patch.py:446-592) gives the
+    same tables as the block-partition builder for an unshifted grid, and follows the patches when a column rotates."""
+    from lambdapic_b200.patch import Patch2D, Patch3D, Patches
+    npx, npy, npz = npatch
+    bc = {f"{a}{s}": ("periodic" if periodic[i] else "pml") for i, a in enumerate("xyz"[:dim]) for s in ("min", "max")}
+    pg = make_patch_grid(dim, npx, npy, npz, 8, 8, 8 if dim == 3 else 1, 1.0, 1.0, 1.0, 3, periodic)
+    ps = Patches(dim)
+    for k, gidx in enumerate(pg.index):
+        ix, iy, iz = int(gidx % npx), int((gidx // npx) % npy), int(gidx // (npx * npy))
+        p = (Patch3D(0, int(gidx), ix, iy, iz, 0.0, 0.0, 0.0, 8, 8, 8, 1.0, 1.0, 1.0) if dim == 3
+             else Patch2D(0, int(gidx), ix, iy, 0.0, 0.0, 8, 8, 1.0, 1.0))
+        ps.append(p)
+    if dim == 3:
+        ps.init_rect_neighbor_index_3d(npx, npy, npz, boundary_conditions=bc)
+        ps.init_neighbor_ipatch_3d()
+        ps.init_neighbor_rank_3d()
+    else:
+        ps.init_rect_neighbor_index_2d(npx, npy, boundary_conditions=bc)
+        ps.init_neighbor_ipatch_2d()
+        ps.init_neighbor_rank_2d()
+    assert np.array_equal(np.stack([p.neighbor_index for p in ps]), pg.neighbor_index)
+    assert np.array_equal(np.stack([p.neighbor_ipatch for p in ps]), pg.neighbor_ipatch)
+    assert all((p.neighbor_rank == -1).all() for p in ps)
+    # rotate the columns as MovingWindow._shift does: column 0 becomes the last one
+    for p in ps:
+        p.ipatch_x = npx - 1 if p.ipatch_x == 0 else p.ipatch_x - 1
+    axes = "xyz"[:dim]
+    index_map = {tuple(getattr(p, f"ipatch_{a}") for a in axes): p.index for p in ps}
+    (ps.init_rect_neighbor_index_3d if dim == 3 else ps.init_rect_neighbor_index_2d)(
+        *npatch[:dim], boundary_conditions=bc, patch_index_map=index_map)
+    where = {p.index: p for p in ps}
+    for p in ps:
+        right = p.neighbor_index[1]  # xmax
+        if p.ipatch_x == npx - 1 and not periodic[0]:
+            assert right == -1
+        else:
+            q = where[right]
+            assert q.ipatch_x == (p.ipatch_x + 1) % npx and q.ipatch_y == p.ipatch_y
