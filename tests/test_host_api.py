@@ -196,3 +196,47 @@ def test_neighbour_tables_rebuilt_from_patch_positions_match_the_grid_builder(di
         else:
             q = where[right]
             assert q.ipatch_x == (p.ipatch_x + 1) % npx and q.ipatch_y == p.ipatch_y
+
+
+def test_stage_mirror_traffic_follows_the_callback_hints():
+    """Simulation._stage: device-side callbacks cause no mirror traffic; hinted callbacks move only the named arrays and keep
+    the device authoritative (resident stays True, so sim.energies() in the same stage works on device state); one unhinted
+    callback in the stage falls back to the full download / upload with the host authoritative in between."""
+    from lambdapic_b200.comm import default_comm
+    from lambdapic_b200.operators import SingleRankMPI
+
+    class FakeBridge:
+        def __init__(self):
+            self.resident, self.log, self.seen_resident = True, [], []
+
+        def download(self, names=None):
+            self.log.append(("down", None if names is None else frozenset(names)))
+
+        def upload(self, names=None):
+            self.log.append(("up", None if names is None else frozenset(names)))
+    d = 0.8e-6 / 20
+    sim = Simulation(nx=16, ny=16, dx=d, dy=d, npatch_x=1, npatch_y=1,
+                     boundary_conditions={k: "periodic" for k in ("xmin", "xmax", "ymin", "ymax")})
+    sim.mpi = SingleRankMPI(default_comm())
+    br = sim.bridge = FakeBridge()
+
+    def note(sim):
+        br.seen_resident.append(br.resident)
+    dev = callback("end", needs_host=False)(note)
+    hinted = callback("end", reads=("ex",), writes=("bz",))(note)
+    ro = callback("end", reads=("rho", "ex"), writes=())(note)
+    plain = callback("end")(note)
+    skipped = callback("end", interval=lambda s: False)(note)
+
+    def run(cbs):
+        br.log.clear(); br.seen_resident.clear(); br.resident = True
+        sim._stage(SimulationCallbacks(cbs, sim), "end", "end")
+        return list(br.log), list(br.seen_resident), br.resident
+    assert run([dev]) == ([], [True], True)
+    assert run([skipped, plain][:1]) == ([], [], True)  # nothing triggered: nothing moves, nothing runs
+    log, seen, after = run([dev, hinted, ro])
+    assert log == [("down", frozenset({"ex", "bz", "rho"})), ("up", frozenset({"bz"}))] and seen == [True, True, True] and after
+    log, seen, after = run([ro])
+    assert log == [("down", frozenset({"rho", "ex"})), ("up", frozenset())] and after
+    log, seen, after = run([hinted, plain])
+    assert log == [("down", None), ("up", None)] and seen == [False, False] and after
