@@ -294,14 +294,60 @@ def load_patch_particles(s: Species, p: Patch, part: ParticlesBase, gen: np.rand
     return n
 
 
+_NUMBA_CACHE: dict = {}
+
+
+def _numba_nodes(fun, axes):
+    """Evaluate a user profile node by node with numba, as the reference does (core/species.py:141-170 njit-compiles the
+    profile and core/patch/cpu.py calls it per node): same scalar code path, so also the same last bits for profiles that
+    use transcendental functions, and ~100x faster than a Python loop for profiles written with `if`.  Returns None when
+    numba is missing or cannot compile the function (the caller falls back to numpy)."""
+    key = (id(fun), len(axes))
+    if key not in _NUMBA_CACHE:
+        try:
+            import numba
+            jf = fun if isinstance(fun, numba.core.dispatcher.Dispatcher) else numba.njit(fun)
+            if len(axes) == 2:
+                @numba.njit
+                def drv(f, x, y, out):
+                    for i in range(x.size):
+                        for j in range(y.size):
+                            out[i, j] = f(x[i], y[j])
+            else:
+                @numba.njit
+                def drv(f, x, y, z, out):
+                    for i in range(x.size):
+                        for j in range(y.size):
+                            for k in range(z.size):
+                                out[i, j, k] = f(x[i], y[j], z[k])
+            probe = np.zeros(tuple(1 for _ in axes))
+            drv(jf, *[np.ascontiguousarray(a[:1], dtype=np.float64) for a in axes], probe)  # compile now, fail now
+            _NUMBA_CACHE[key] = (fun, jf, drv)  # `fun` is kept alive so that its id() stays unique
+        except Exception:
+            _NUMBA_CACHE[key] = (fun, None, None)
+    _, jf, drv = _NUMBA_CACHE[key]
+    if jf is None:
+        return None
+    out = np.empty(tuple(len(a) for a in axes))
+    drv(jf, *[np.ascontiguousarray(a, dtype=np.float64) for a in axes], out)
+    return out
+
+
 def _node_profiles(species: Species, p: Patch, dim: int):
     """density and int(ppc) on the nodes of patch p (0 where density <= density_min)."""
     axes = (p.xaxis, p.yaxis) + ((p.zaxis,) if dim == 3 else ())
     shape = tuple(len(a) for a in axes)
     dfun, pfun = species.density_jit, species.ppc_jit
-    grids = np.meshgrid(*axes, indexing="ij")
+    grids = None
 
-    def evaluate(fun):
+    def evaluate(fun, user_fun):
+        nonlocal grids
+        if callable(user_fun):  # user-written profile: the reference's numba path first
+            v = _numba_nodes(fun, axes)
+            if v is not None:
+                return v
+        if grids is None:
+            grids = np.meshgrid(*axes, indexing="ij")
         try:
             v = np.asarray(fun(*grids), dtype=float)
             if v.shape == shape:
@@ -311,7 +357,7 @@ def _node_profiles(species: Species, p: Patch, dim: int):
         except Exception:
             pass
         return np.vectorize(fun, otypes=[float])(*grids)
-    dens = evaluate(dfun)
-    ppc = evaluate(pfun).astype(np.int64)
+    dens = evaluate(dfun, species.density)
+    ppc = evaluate(pfun, species.ppc).astype(np.int64)
     ppc = np.where(dens > species.density_min, ppc, 0)
     return dens, ppc
