@@ -126,7 +126,7 @@ extern "C" void lpic_destroy(lpic_ctx *c) {
     lpic_free_peers(c);
     lpic_free_pml(c);
     cudaFree(c->fields); cudaFree(c->d_x0); cudaFree(c->d_y0); cudaFree(c->d_z0); cudaFree(c->d_nbr); cudaFree(c->d_box);
-    cudaFree(c->scr_a); cudaFree(c->scr_b); cudaFree(c->scr_buf); cudaFree(c->d_sort_org); cudaFree(c->d_tmp64); cudaFree(c->d_tmpf);
+    cudaFree(c->scr_a); cudaFree(c->scr_b); cudaFree(c->scr_buf); cudaFree(c->d_sort_org); cudaFree(c->d_tmp64); cudaFree(c->d_tmpf); cudaFree(c->d_tile_start);
     delete[] c->h_x0; delete[] c->h_y0; delete[] c->h_z0; delete[] c->h_nbr; delete[] c->h_patch_index;
     if (c->events) {
         for (int i = 0; i < 4096; i++)

@@ -11,6 +11,7 @@
 // fp64 global reductions (REDG.E.ADD.F64) that resolve in L2 because consecutive blocks work on one patch.
 // Floating-point contract: the reference is itself built with FMA contraction, so results agree to
 // <= 1e-12 of each array's max-abs (tests/test_gpu_parity.py), not bit-for-bit.
+#include <stdlib.h>
 #include "lpic_common.cuh"
 #include "particle_math.cuh"
 
@@ -195,6 +196,7 @@ int launch_particles(lpic_ctx *c, int ispec, double dt, double q, double m, bool
 }  // namespace
 
 int lpic_push_deposit_sorted(lpic_ctx *c, int ispec, double dt, double q, double m, bool write_part);
+int lpic_push_deposit_tiles(lpic_ctx *c, int ispec, double dt, double q, double m, bool write_part);
 
 extern "C" int lpic_push_deposit(lpic_ctx *c, int ispec, double dt, double q, double m, int flags) {
     const bool write_part = (flags & LPIC_PUSH_WRITE_PART) != 0;
@@ -204,8 +206,12 @@ extern "C" int lpic_push_deposit(lpic_ctx *c, int ispec, double dt, double q, do
         return -2;
     }
     c->spec[ispec].lists_valid = false;
-    if (!(flags & LPIC_PUSH_SLOT_ORDER)) {  // default: cell-ordered warp-cooperative kernel (3D), see push_sorted.cu
-        const int r = lpic_push_deposit_sorted(c, ispec, dt, q, m, write_part);
+    if (!(flags & LPIC_PUSH_SLOT_ORDER)) {
+        // default in 3D: the tile kernel (push_tile.cu); 2D, patches too large for its histogram and LPIC_PUSH_SORTED=1
+        // (A/B runs): the round-1 cell-ordered kernel (push_sorted.cu)
+        int r = getenv("LPIC_PUSH_SORTED") ? 1 : lpic_push_deposit_tiles(c, ispec, dt, q, m, write_part);
+        if (r <= 0) return r;
+        r = lpic_push_deposit_sorted(c, ispec, dt, q, m, write_part);
         if (r <= 0) return r;
     }
     return launch_particles<MODE_FUSED>(c, ispec, dt, q, m, write_part);

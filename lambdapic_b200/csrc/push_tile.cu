@@ -1,0 +1,503 @@
+// Tile kernel: the fused particle step (half push, 6 x 27-point gather, Boris, half push, Esirkepov deposit) of the 3D
+// path, organised around a CTA-owned block of cells.
+//
+// Reference behaviour restated (not copied): core/pusher/unified/unified_pusher_3d.c:281-431 (strip loop: half push,
+// interpolation, Boris, half push), core/current/current_deposit.h:275-440 (charge-conserving deposit).
+//
+//   1. k_tile_perm   one CTA per patch.  Every alive slot gets the key (tile, cell in tile) of the node nearest to its
+//                    position AFTER the first half push -- the cell it gathers from, and where its deposit starts.  Shared-
+//                    memory histogram -> block scan -> scatter gives a permutation of the slots in (tile, cell) order plus
+//                    the first position of every tile.  The slot order in memory stays the reference's (it is the
+//                    parity contract of sort and migration); only the ORDER OF PROCESSING changes.  Particles whose
+//                    nearest node lies outside the patch's own cells (a boundary layer of v dt/2) go to the patch's
+//                    list instead.
+//   2. k_push_tile   one CTA per (patch, tile of TX x TY x TZ cells).  The CTA stages the E/B values of the tile plus its
+//                    halo (6 x (TX+3)(TY+3)(TZ+3) doubles) in shared memory in LOGICAL order -- the wrapped-guard
+//                    arithmetic of the global layout is paid once per staged value instead of once per gather load --
+//                    and every gather becomes an LDS with an immediate offset.  Each warp then walks a contiguous run
+//                    of the tile's cell-ordered particles.  Deposit: for one x-plane of the 3x3x3 stencil at a time every
+//                    lane stores its 30 values as a column of a [30][33] tile, lane l then owns row l (one stencil
+//                    point of one of rho/jx/jy/jz) and adds the source lanes of a cell; the sum stays in the owner's
+//                    registers ACROSS warp iterations until the cell changes, so a cell costs 81 fp64 REDs per species
+//                    however many particles it holds.  Particles that change cell during the step are listed.
+//   3. k_list_particles  the listed particles: boundary-layer ones get the whole step with gathers from global memory,
+//                    cell-crossing ones only the general 125-point deposit.
+//
+// The Esirkepov sums are factored (jx(i,j,k) = cumx[i] * Wx[j][k] etc.), which is the reference's running sums
+// re-associated: results agree to a few ulp of each particle's largest term (parity bar 1e-12 of the array's max-abs).
+#include <stdlib.h>
+#include <algorithm>
+#include "lpic_common.cuh"
+#include "particle_math.cuh"
+#include "push_tile.cuh"
+
+namespace {
+
+constexpr int PT = 256;  // threads of the permutation CTA
+
+__device__ __forceinline__ int warp_incl_sum(int v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int n = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += n;
+    }
+    return v;
+}
+
+// Position after the first half push and its grid coordinate: explicit intrinsics, so that the permutation kernel and
+// the particle kernel agree bit for bit on the cell a particle belongs to.
+__device__ __forceinline__ double half_push(double x, double cdt, double ig, double u) { return __fma_rn(__dmul_rn(cdt, ig), u, x); }
+__device__ __forceinline__ double grid_coord(double x, double x0, double inv_d) { return __dmul_rn(__dsub_rn(x, x0), inv_d); }
+__device__ __forceinline__ double nearest(double X) { return floor(__dadd_rn(X, 0.5)); }
+
+struct TilePermArgs {
+    const double *x, *y, *z, *ux, *uy, *uz, *ig;
+    const u8 *dead;
+    const i64 *off, *npart;
+    const double *x0, *y0, *z0;
+    double cdt, inv_dx, inv_dy, inv_dz;
+    int nx, ny, nz, nty, ntz, ntile;
+    int *keys;        // arena scratch: key of every slot (-1: not in a tile)
+    int *perm;        // arena: local slot numbers in (tile, cell) order
+    int *tile_start;  // (npatch, ntile + 1)
+    int *list;        // arena: the patch's list of particles for k_list_particles
+    int *nlist;       // per patch
+};
+
+template <int TX, int TY, int TZ>
+__global__ void __launch_bounds__(PT) k_tile_perm(TilePermArgs a) {
+    extern __shared__ int hist[];
+    __shared__ int sw[PT / 32];
+    constexpr int TC = TX * TY * TZ;
+    const int p = blockIdx.x, tid = threadIdx.x;
+    const i64 off = a.off[p];
+    const int np = (int)a.npart[p];
+    const int nkey = a.ntile * TC;
+    for (int b = tid; b < nkey; b += PT) hist[b] = 0;
+    __syncthreads();
+    const double x0 = a.x0[p], y0 = a.y0[p], z0 = a.z0[p];
+    auto key_of = [&](int ip) -> int {
+        if (a.dead[off + ip]) return -1;
+        const double x = a.x[off + ip], y = a.y[off + ip], z = a.z[off + ip];
+        if (isnan(x) || isnan(y) || isnan(z)) return -1;
+        const double ig = a.ig[off + ip];
+        const int ix = (int)nearest(grid_coord(half_push(x, a.cdt, ig, a.ux[off + ip]), x0, a.inv_dx));
+        const int iy = (int)nearest(grid_coord(half_push(y, a.cdt, ig, a.uy[off + ip]), y0, a.inv_dy));
+        const int iz = (int)nearest(grid_coord(half_push(z, a.cdt, ig, a.uz[off + ip]), z0, a.inv_dz));
+        if ((unsigned)ix >= (unsigned)a.nx || (unsigned)iy >= (unsigned)a.ny || (unsigned)iz >= (unsigned)a.nz) return -2;
+        const int tx = ix / TX, ty = iy / TY, tz = iz / TZ;
+        return ((tx * a.nty + ty) * a.ntz + tz) * TC + ((ix - tx * TX) * TY + (iy - ty * TY)) * TZ + (iz - tz * TZ);
+    };
+    // four slots per thread and iteration: the loads of the four are independent and in flight together
+    for (int base = 0; base < np; base += 4 * PT) {
+        int k[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int ip = base + u * PT + tid;
+            k[u] = ip < np ? key_of(ip) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int ip = base + u * PT + tid;
+            if (ip < np) a.keys[off + ip] = k[u];
+            if (k[u] >= 0) atomicAdd(&hist[k[u]], 1);
+            if (k[u] == -2) a.list[off + atomicAdd(&a.nlist[p], 1)] = ip | LIST_WHOLE_STEP;
+        }
+    }
+    __syncthreads();
+    // exclusive scan of the histogram in place
+    int run = 0;
+    for (int base = 0; base < nkey; base += PT) {
+        const int b = base + tid;
+        const int cnt = b < nkey ? hist[b] : 0;
+        int v = warp_incl_sum(cnt);
+        if ((tid & 31) == 31) sw[tid >> 5] = v;
+        __syncthreads();
+        int add = 0, tot = 0;
+#pragma unroll
+        for (int i = 0; i < PT / 32; i++) {
+            if (i < (tid >> 5)) add += sw[i];
+            tot += sw[i];
+        }
+        if (b < nkey) hist[b] = run + v + add - cnt;
+        run += tot;
+        __syncthreads();
+    }
+    int *ts = a.tile_start + (size_t)p * (a.ntile + 1);
+    for (int t = tid; t < a.ntile; t += PT) ts[t] = hist[t * TC];
+    if (tid == 0) ts[a.ntile] = run;
+    __syncthreads();
+    for (int base = 0; base < np; base += 4 * PT) {
+        int k[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int ip = base + u * PT + tid;
+            k[u] = ip < np ? a.keys[off + ip] : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (k[u] >= 0) a.perm[off + atomicAdd(&hist[k[u]], 1)] = base + u * PT + tid;
+    }
+}
+
+struct TileArgs {
+    Geom g;
+    double *F;
+    const double *px0, *py0, *pz0;
+    Slots s;
+    const int *perm, *tile_start;
+    int *list, *nlist;
+    int nty, ntz, ntile;
+    double dt, cdt, efactor, bfactor, inv_dx, inv_dy, inv_dz, q_dV, q_dydzdt, q_dxdzdt, q_dxdydt;
+};
+
+__device__ __forceinline__ void spline3(double d, double &a, double &b, double &c) {  // quadratic spline at offsets -1, 0, +1
+    const double d2 = d * d;
+    a = 0.5 * (0.25 + d2 + d);
+    b = 0.75 - d2;
+    c = 0.5 * (0.25 + d2 - d);
+}
+
+// 27-point weighted sum from the staged tile: immediate offsets, nesting z(y(x)) as interp_field_safe_3d
+// (unified_pusher_3d.c:79-106)
+template <int SX, int SY>
+__device__ __forceinline__ double gather_tile(const double *__restrict__ t, double fx0, double fx1, double fx2, double fy0,
+                                              double fy1, double fy2, double fz0, double fz1, double fz2) {
+    double az[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        double ay[3];
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+            const double *r = t + b * SY + c;
+            ay[b] = fx0 * r[0] + fx1 * r[SX] + fx2 * r[2 * SX];
+        }
+        az[c] = fy0 * ay[0] + fy1 * ay[1] + fy2 * ay[2];
+    }
+    return fz0 * az[0] + fz1 * az[1] + fz2 * az[2];
+}
+
+// What an owner lane needs to turn (cell inside the tile, x-plane) into the address of its stencil point
+struct RowOwner {
+    double *dst;     // this patch's jx / jy / jz / rho block
+    int ax, ay, az;  // tile origin + the owner's stencil offset - 1 (ax is advanced by one per x-plane)
+    int NX, NY, NZ;
+};
+
+// one RED for a finished cell (code = cell inside the tile; -1: nothing carried yet)
+template <int TY, int TZ>
+__device__ __forceinline__ void flush_cell(const RowOwner &o, int code, double sum) {
+    if (code < 0) return;
+    const int lz = code % TZ, ly = (code / TZ) % TY, lx = code / (TZ * TY);
+    const int id = (wrapneg(o.ax + lx, o.NX) * o.NY + wrapneg(o.ay + ly, o.NY)) * o.NZ + wrapneg(o.az + lz, o.NZ);
+    atomicAdd(o.dst + id, sum);
+}
+
+// Owner lane: add this iteration's 32 source lanes of one row to the running sum of the current cell; a set bit in
+// `heads` marks a source lane that starts a new cell: the finished cell is flushed and the sum restarts.  One copy of
+// this in the instruction stream serves the three x-planes.
+template <int TY, int TZ>
+__device__ __noinline__ double row_sum(double acc, unsigned heads, const double *__restrict__ row, const int *__restrict__ codes,
+                                       int cur, RowOwner o) {
+    if (heads == 0u) {
+        double t[8];
+#pragma unroll
+        for (int g4 = 0; g4 < 8; g4++) t[g4] = (row[4 * g4] + row[4 * g4 + 1]) + (row[4 * g4 + 2] + row[4 * g4 + 3]);
+        return acc + (((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7])));
+    }
+    int s = 0;
+    for (;;) {
+        const int e = heads ? __ffs(heads) - 1 : 32;
+        for (; s + 4 <= e; s += 4) acc += (row[s] + row[s + 1]) + (row[s + 2] + row[s + 3]);
+        for (; s < e; s++) acc += row[s];
+        if (e == 32) return acc;
+        heads &= heads - 1u;
+        flush_cell<TY, TZ>(o, cur, acc);
+        acc = 0.0;
+        cur = codes[e];
+    }
+}
+
+template <int TX, int TY, int TZ, int NW, bool WRITE_PART>
+__global__ void __launch_bounds__(NW * 32, TILE_MIN_CTAS) k_push_tile(const TileArgs a) {
+    constexpr int EX = TX + 3, EY = TY + 3, EZ = TZ + 3, EN = EX * EY * EZ;
+    constexpr int SX = EY * EZ, SY = EZ;  // strides (in doubles) of the staged tile
+    extern __shared__ double smem[];
+    double *eb = smem;                                            // [6][EX][EY][EZ]
+    double *red = smem + 6 * EN + (threadIdx.x >> 5) * (30 * 33);  // this warp's [30][33] reduction tile
+    int *codes = (int *)(smem + 6 * EN + NW * 30 * 33) + (threadIdx.x >> 5) * 32;
+    const Geom &g = a.g;
+    const int p = blockIdx.x / a.ntile, tile = blockIdx.x - p * a.ntile;
+    const int *ts = a.tile_start + (size_t)p * (a.ntile + 1) + tile;
+    const int first = ts[0], last = ts[1];
+    if (first == last) return;
+    const int tz = tile % a.ntz, ty = (tile / a.ntz) % a.nty, tx = tile / (a.ntz * a.nty);
+    const int ox = tx * TX, oy = ty * TY, oz = tz * TZ;
+    const size_t stride = (size_t)g.npatch * g.ncell;
+    double *Fp = a.F + (size_t)p * g.ncell;
+    // ---- stage E/B of the tile and its halo: nodes [o-2, o+T] per axis, logical order --------------------------------
+    for (int idx = threadIdx.x; idx < EN; idx += NW * 32) {
+        const int lz = idx % EZ, ly = (idx / EZ) % EY, lx = idx / (EZ * EY);
+        const int gx = ox - 2 + lx, gy = oy - 2 + ly, gz = oz - 2 + lz;
+        if (gx < g.nx + g.ng && gy < g.ny + g.ng && gz < g.nz + g.ng) {  // (the low side is always inside: ng >= 2)
+            const double *src = Fp + (wrapneg(gx, g.NX) * g.NY + wrapneg(gy, g.NY)) * g.NZ + wrapneg(gz, g.NZ);
+#pragma unroll
+            for (int c = 0; c < 6; c++) eb[c * EN + idx] = __ldg(src + c * stride);
+        }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int per = ((last - first + NW * 32 - 1) / (NW * 32)) * 32;  // particles per warp, a multiple of 32
+    const int wfirst = first + warp * per, wlast = min(last, wfirst + per);
+    if (wfirst >= wlast) return;
+    const i64 off = a.s.off[p];
+    const double x0 = a.px0[p], y0 = a.py0[p], z0 = a.pz0[p];
+    // which row of the reduction tile does this lane own?  [0,9) rho(j,k)  [9,15) jy(j<2,k)  [15,21) jz(j,k<2)  [21,30) jx(j,k)
+    int comp, sj, sk;
+    if (lane < 9) { comp = LPIC_RHO; sj = lane / 3; sk = lane - 3 * sj; }
+    else if (lane < 15) { comp = LPIC_JY; sj = (lane - 9) / 3; sk = (lane - 9) - 3 * sj; }
+    else if (lane < 21) { comp = LPIC_JZ; sj = (lane - 15) >> 1; sk = (lane - 15) & 1; }
+    else { comp = LPIC_JX; sj = (lane - 21) / 3; sk = (lane - 21) - 3 * sj; }
+    RowOwner own;
+    own.dst = Fp + comp * stride;
+    own.ax = ox - 1; own.ay = oy + sj - 1; own.az = oz + sk - 1;
+    own.NX = g.NX; own.NY = g.NY; own.NZ = g.NZ;
+    const double *row = red + lane * 33;
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;  // the owner's running sums of the current cell, one per x-plane
+    int ccode = -1;                             // that cell (-1: none yet)
+    for (int t0 = wfirst; t0 < wlast; t0 += 32) {
+        const bool active = t0 + lane < wlast;
+        double x = 0, y = 0, z = 0, ux = 0, uy = 0, uz = 0, ig = 1, w = 0;
+        int local = 0, cx = 0, cy = 0, cz = 0;
+        if (active) {
+            local = a.perm[off + t0 + lane];
+            const i64 ip = off + local;
+            x = a.s.x[ip]; y = a.s.y[ip]; z = a.s.z[ip];
+            ux = a.s.ux[ip]; uy = a.s.uy[ip]; uz = a.s.uz[ip]; ig = a.s.ig[ip];
+            w = a.s.w[ip];
+            x = half_push(x, a.cdt, ig, ux); y = half_push(y, a.cdt, ig, uy); z = half_push(z, a.cdt, ig, uz);
+            const double X = grid_coord(x, x0, a.inv_dx), Y = grid_coord(y, y0, a.inv_dy), Z = grid_coord(z, z0, a.inv_dz);
+            const double rX = nearest(X), rY = nearest(Y), rZ = nearest(Z), fX = floor(X), fY = floor(Y), fZ = floor(Z);
+            cx = (int)rX; cy = (int)rY; cz = (int)rZ;
+            double gx0, gx1, gx2, gy0, gy1, gy2, gz0, gz1, gz2, hx0, hx1, hx2, hy0, hy1, hy2, hz0, hz1, hz2;
+            spline3(rX - X, gx0, gx1, gx2); spline3(fX - X + 0.5, hx0, hx1, hx2);
+            spline3(rY - Y, gy0, gy1, gy2); spline3(fY - Y + 0.5, hy0, hy1, hy2);
+            spline3(rZ - Z, gz0, gz1, gz2); spline3(fZ - Z + 0.5, hz0, hz1, hz2);
+            // staged index of the first stencil node: node-centred (g) r-1 -> r-1-(o-2), cell-centred (h) f-1 -> f-1-(o-2)
+            const int bgx = (cx - ox + 1) * SX, bhx = ((int)fX - ox + 1) * SX;
+            const int bgy = (cy - oy + 1) * SY, bhy = ((int)fY - oy + 1) * SY;
+            const int bgz = cz - oz + 1, bhz = (int)fZ - oz + 1;
+            // ex(h,g,g) ey(g,h,g) ez(g,g,h) bx(g,h,h) by(h,g,h) bz(h,h,g)  (unified_pusher_3d.c:190-195)
+            double f[6];
+            f[0] = gather_tile<SX, SY>(eb + 0 * EN + bhx + bgy + bgz, hx0, hx1, hx2, gy0, gy1, gy2, gz0, gz1, gz2);
+            f[1] = gather_tile<SX, SY>(eb + 1 * EN + bgx + bhy + bgz, gx0, gx1, gx2, hy0, hy1, hy2, gz0, gz1, gz2);
+            f[2] = gather_tile<SX, SY>(eb + 2 * EN + bgx + bgy + bhz, gx0, gx1, gx2, gy0, gy1, gy2, hz0, hz1, hz2);
+            f[3] = gather_tile<SX, SY>(eb + 3 * EN + bgx + bhy + bhz, gx0, gx1, gx2, hy0, hy1, hy2, hz0, hz1, hz2);
+            f[4] = gather_tile<SX, SY>(eb + 4 * EN + bhx + bgy + bhz, hx0, hx1, hx2, gy0, gy1, gy2, hz0, hz1, hz2);
+            f[5] = gather_tile<SX, SY>(eb + 5 * EN + bhx + bhy + bgz, hx0, hx1, hx2, hy0, hy1, hy2, gz0, gz1, gz2);
+            if (WRITE_PART) {
+#pragma unroll
+                for (int c = 0; c < 6; c++) a.s.part[c][ip] = f[c];
+            }
+            boris_kick(ux, uy, uz, ig, f, a.efactor, a.bfactor);
+            a.s.ux[ip] = ux; a.s.uy[ip] = uy; a.s.uz[ip] = uz; a.s.ig[ip] = ig;
+            x += a.cdt * ig * ux; y += a.cdt * ig * uy; z += a.cdt * ig * uz;
+            a.s.x[ip] = x; a.s.y[ip] = y; a.s.z[ip] = z;
+        }
+        // ---- deposit set-up (current_deposit.h:341-373): the path from x - v dt/2 to x + v dt/2 ------------------------
+        const double hvx = ux * ig * (LPIC_C_LIGHT * 0.5) * a.dt, hvy = uy * ig * (LPIC_C_LIGHT * 0.5) * a.dt,
+                     hvz = uz * ig * (LPIC_C_LIGHT * 0.5) * a.dt;
+        const double X0 = (x - hvx - x0) * a.inv_dx, X1 = (x + hvx - x0) * a.inv_dx;
+        const double Y0 = (y - hvy - y0) * a.inv_dy, Y1 = (y + hvy - y0) * a.inv_dy;
+        const double Z0 = (z - hvz - z0) * a.inv_dz, Z1 = (z + hvz - z0) * a.inv_dz;
+        const double rX0 = floor(X0 + 0.5), rY0 = floor(Y0 + 0.5), rZ0 = floor(Z0 + 0.5);
+        // fast: the nearest node does not change along the path AND it is the node the particle was keyed by (recomputing
+        // the start from the end position can round to the other side of a cell boundary)
+        const bool fast = active && floor(X1 + 0.5) == rX0 && floor(Y1 + 0.5) == rY0 && floor(Z1 + 0.5) == rZ0 &&
+                          (int)rX0 == cx && (int)rY0 == cy && (int)rZ0 == cz;
+        {   // everything else takes the general deposit (k_list_particles); one warp-aggregated append
+            const unsigned cm = __ballot_sync(0xffffffffu, active && !fast);
+            if (cm) {
+                int basepos = 0;
+                if (lane == __ffs(cm) - 1) basepos = atomicAdd(&a.nlist[p], __popc(cm));
+                basepos = __shfl_sync(0xffffffffu, basepos, __ffs(cm) - 1);
+                if (active && !fast) a.list[off + basepos + __popc(cm & ((1u << lane) - 1u))] = local;
+            }
+        }
+        // cells = runs of consecutive fast lanes with the same code; lanes outside the fast path add zeros and never
+        // start a run; the first fast lane continues the run carried over from the previous iteration if the cell matches
+        const int code = fast ? ((cx - ox) * TY + (cy - oy)) * TZ + (cz - oz) : -1;
+        const unsigned fm = __ballot_sync(0xffffffffu, fast);
+        if (fm == 0u) continue;
+        const unsigned before = fm & ((1u << lane) - 1u);
+        const int pf = before ? 31 - __clz(before) : 0;
+        int pcode = __shfl_sync(0xffffffffu, code, pf);
+        if (!before) pcode = ccode;
+        const unsigned heads = __ballot_sync(0xffffffffu, fast && code != pcode);
+        codes[lane] = code;
+        const int lastcode = __shfl_sync(0xffffffffu, code, 31 - __clz(fm));
+        // shape factors at the start (S0) and their change (DS); no cell crossing: both live on the same 3 nodes
+        double S0x[3], S0y[3], S0z[3], DSx[3], DSy[3], DSz[3];
+        {
+            double s1[3];
+            spline3(rX0 - X0, S0x[0], S0x[1], S0x[2]); spline3(rX0 - X1, s1[0], s1[1], s1[2]);
+#pragma unroll
+            for (int i = 0; i < 3; i++) DSx[i] = s1[i] - S0x[i];
+            spline3(rY0 - Y0, S0y[0], S0y[1], S0y[2]); spline3(rY0 - Y1, s1[0], s1[1], s1[2]);
+#pragma unroll
+            for (int i = 0; i < 3; i++) DSy[i] = s1[i] - S0y[i];
+            spline3(rZ0 - Z0, S0z[0], S0z[1], S0z[2]); spline3(rZ0 - Z1, s1[0], s1[1], s1[2]);
+#pragma unroll
+            for (int i = 0; i < 3; i++) DSz[i] = s1[i] - S0z[i];
+        }
+        const double wq = fast ? w : 0.0;
+        const double cd = a.q_dV * wq, fdx = a.q_dydzdt * wq, fdy = a.q_dxdzdt * wq, fdz = a.q_dxdydt * wq;
+        // running sums of the reference's jyb / jzb loops, factored: jy(i,j,k) = cumy[j] * Wy_i[k], jz(i,j,k) = cumz[k] * Tz_i[j]
+        const double cumy0 = -fdy * DSy[0], cumy1 = cumy0 - fdy * DSy[1];
+        const double cumz0 = -fdz * DSz[0], cumz1 = cumz0 - fdz * DSz[1];
+        double cumx = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const double ax = S0x[i] + 0.5 * DSx[i], cxx = 0.5 * S0x[i] + LPIC_ONE_THIRD * DSx[i];
+            const double rx = cd * (S0x[i] + DSx[i]);
+            cumx -= fdx * DSx[i];
+            double wy[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) wy[k] = ax * S0z[k] + cxx * DSz[k];
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const double rxy = rx * (S0y[j] + DSy[j]);
+                const double tzj = ax * S0y[j] + cxx * DSy[j];
+                const double ay = S0y[j] + 0.5 * DSy[j], cyy = 0.5 * S0y[j] + LPIC_ONE_THIRD * DSy[j];
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    red[(j * 3 + k) * 33 + lane] = rxy * (S0z[k] + DSz[k]);
+                    if (i < 2) red[(21 + j * 3 + k) * 33 + lane] = cumx * (ay * S0z[k] + cyy * DSz[k]);
+                    if (j < 2) red[(9 + j * 3 + k) * 33 + lane] = (j == 0 ? cumy0 : cumy1) * wy[k];
+                    if (k < 2) red[(15 + j * 2 + k) * 33 + lane] = (k == 0 ? cumz0 : cumz1) * tzj;
+                }
+            }
+            __syncwarp();
+            if (lane < (i < 2 ? 30 : 21)) {
+                RowOwner o = own;
+                o.ax += i;
+                const double acc = row_sum<TY, TZ>(i == 0 ? acc0 : (i == 1 ? acc1 : acc2), heads, row, codes, ccode, o);
+                if (i == 0) acc0 = acc; else if (i == 1) acc1 = acc; else acc2 = acc;
+            }
+            __syncwarp();
+        }
+        ccode = lastcode;
+    }
+    flush_cell<TY, TZ>(own, ccode, acc0);
+    own.ax++;
+    flush_cell<TY, TZ>(own, ccode, acc1);
+    own.ax++;
+    if (lane < 21) flush_cell<TY, TZ>(own, ccode, acc2);
+}
+
+// The listed particles of every patch: entries tagged LIST_WHOLE_STEP get the whole step with gathers from global memory
+// (they sit in the boundary layer outside the tiles), the others were pushed by k_push_tile and only need the general
+// deposit.  Persistent grid: CTAs stride over the patches, threads over each patch's (short) list.
+template <bool WRITE_PART>
+__global__ void __launch_bounds__(128) k_list_particles(Geom g, double *__restrict__ F, const double *__restrict__ px0,
+                                                        const double *__restrict__ py0, const double *__restrict__ pz0, Slots s,
+                                                        const int *__restrict__ list, const int *__restrict__ nlist, double dt,
+                                                        double q, double m) {
+    DepositCoef3 k;
+    k.q_dV = q / (g.dx * g.dy * g.dz); k.q_dydzdt = q / (g.dy * g.dz * dt);
+    k.q_dxdzdt = q / (g.dx * g.dz * dt); k.q_dxdydt = q / (g.dx * g.dy * dt); k.dt = dt;
+    const double cdt = LPIC_C_LIGHT * 0.5 * dt, efactor = q * dt / (2 * m * LPIC_C_LIGHT), bfactor = q * dt / (2 * m);
+    for (int p = blockIdx.x; p < g.npatch; p += gridDim.x) {
+        const int n = nlist[p];
+        if (n == 0) continue;
+        const PatchView v = patch_view(g, F, px0, py0, pz0, p);
+        for (int t = threadIdx.x; t < n; t += blockDim.x) {
+            const int e = list[s.off[p] + t];
+            const i64 ip = s.off[p] + (e & ~LIST_WHOLE_STEP);
+            double x = s.x[ip], y = s.y[ip], z = s.z[ip], ux = s.ux[ip], uy = s.uy[ip], uz = s.uz[ip], ig = s.ig[ip];
+            if (e & LIST_WHOLE_STEP) {
+                x = half_push(x, cdt, ig, ux); y = half_push(y, cdt, ig, uy); z = half_push(z, cdt, ig, uz);
+                double eb[6];
+                gather_eb<3>(g, v, x, y, z, eb);
+                if (WRITE_PART) {
+#pragma unroll
+                    for (int c = 0; c < 6; c++) s.part[c][ip] = eb[c];
+                }
+                boris_kick(ux, uy, uz, ig, eb, efactor, bfactor);
+                s.ux[ip] = ux; s.uy[ip] = uy; s.uz[ip] = uz; s.ig[ip] = ig;
+                x += cdt * ig * ux; y += cdt * ig * uy; z += cdt * ig * uz;
+                s.x[ip] = x; s.y[ip] = y; s.z[ip] = z;
+            }
+            deposit3(g, v, k, x, y, z, ux, uy, uz, ig, s.w[ip]);
+        }
+    }
+}
+
+template <int TX, int TY, int TZ, int NW>
+int launch_tiles(lpic_ctx *c, Species &sp, double dt, double q, double m, bool write_part) {
+    const Geom &g = c->g;
+    constexpr int TC = TX * TY * TZ;
+    const int ntx = (g.nx + TX - 1) / TX, nty = (g.ny + TY - 1) / TY, ntz = (g.nz + TZ - 1) / TZ;
+    const int ntile = ntx * nty * ntz;
+    const size_t perm_smem = sizeof(int) * (size_t)ntile * TC;
+    if (perm_smem > TILE_PERM_SMEM_LIMIT) return 1;
+    if (g.ng < 2) return 1;  // the staged halo reaches node -2
+    if (int r = lpic_ensure_scratch(c, sp.total)) return r;
+    const size_t need = (size_t)g.npatch * (ntile + 1);
+    if (need > c->tile_start_cap) {
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_tile_start);
+        c->d_tile_start = nullptr; c->tile_start_cap = 0;
+        CUDA_TRY(cudaMalloc(&c->d_tile_start, sizeof(int) * need));
+        c->tile_start_cap = need;
+    }
+    int *d_nlist = (int *)(c->d_tmp64 + 64 + g.npatch);
+    TilePermArgs pa;
+    pa.x = sp.attr[LPIC_P_X]; pa.y = sp.attr[LPIC_P_Y]; pa.z = sp.attr[LPIC_P_Z];
+    pa.ux = sp.attr[LPIC_P_UX]; pa.uy = sp.attr[LPIC_P_UY]; pa.uz = sp.attr[LPIC_P_UZ]; pa.ig = sp.attr[LPIC_P_INV_GAMMA];
+    pa.dead = sp.dead; pa.off = sp.d_off; pa.npart = sp.d_npart; pa.x0 = c->d_x0; pa.y0 = c->d_y0; pa.z0 = c->d_z0;
+    pa.cdt = LPIC_C_LIGHT * 0.5 * dt; pa.inv_dx = 1.0 / g.dx; pa.inv_dy = 1.0 / g.dy; pa.inv_dz = 1.0 / g.dz;
+    pa.nx = g.nx; pa.ny = g.ny; pa.nz = g.nz; pa.nty = nty; pa.ntz = ntz; pa.ntile = ntile;
+    pa.keys = (int *)c->scr_buf;  // the sort's staging buffer is idle during the push
+    pa.perm = c->scr_b; pa.tile_start = c->d_tile_start; pa.list = c->scr_a; pa.nlist = d_nlist;
+    constexpr size_t push_smem = sizeof(double) * (6 * (TX + 3) * (TY + 3) * (TZ + 3) + NW * 30 * 33) + sizeof(int) * NW * 32;
+    if (!c->tile_attr_set) {  // per context: function attributes are per device, and a process may drive several
+        CUDA_TRY(cudaFuncSetAttribute(k_tile_perm<TX, TY, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_PERM_SMEM_LIMIT));
+        CUDA_TRY(cudaFuncSetAttribute(k_push_tile<TX, TY, TZ, NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)push_smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_push_tile<TX, TY, TZ, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)push_smem));
+        c->tile_attr_set = true;
+    }
+    CUDA_TRY(cudaMemsetAsync(d_nlist, 0, sizeof(int) * g.npatch, c->stream));
+    k_tile_perm<TX, TY, TZ><<<g.npatch, PT, perm_smem, c->stream>>>(pa);
+    LAUNCHED(1);
+    TileArgs ta;
+    ta.g = g; ta.F = c->fields; ta.px0 = c->d_x0; ta.py0 = c->d_y0; ta.pz0 = c->d_z0; ta.s = make_slots(sp);
+    ta.perm = c->scr_b; ta.tile_start = c->d_tile_start; ta.list = c->scr_a; ta.nlist = d_nlist;
+    ta.nty = nty; ta.ntz = ntz; ta.ntile = ntile;
+    ta.dt = dt; ta.cdt = pa.cdt; ta.efactor = q * dt / (2 * m * LPIC_C_LIGHT); ta.bfactor = q * dt / (2 * m);
+    ta.inv_dx = pa.inv_dx; ta.inv_dy = pa.inv_dy; ta.inv_dz = pa.inv_dz;
+    ta.q_dV = q / (g.dx * g.dy * g.dz); ta.q_dydzdt = q / (g.dy * g.dz * dt);
+    ta.q_dxdzdt = q / (g.dx * g.dz * dt); ta.q_dxdydt = q / (g.dx * g.dy * dt);
+    const unsigned grid = (unsigned)((i64)g.npatch * ntile);
+    if (write_part) k_push_tile<TX, TY, TZ, NW, true><<<grid, NW * 32, push_smem, c->stream>>>(ta);
+    else k_push_tile<TX, TY, TZ, NW, false><<<grid, NW * 32, push_smem, c->stream>>>(ta);
+    LAUNCHED(1);
+    const unsigned lgrid = (unsigned)std::min<i64>(g.npatch, 148 * 8);
+    if (write_part) k_list_particles<true><<<lgrid, 128, 0, c->stream>>>(g, c->fields, c->d_x0, c->d_y0, c->d_z0, ta.s, c->scr_a, d_nlist, dt, q, m);
+    else k_list_particles<false><<<lgrid, 128, 0, c->stream>>>(g, c->fields, c->d_x0, c->d_y0, c->d_z0, ta.s, c->scr_a, d_nlist, dt, q, m);
+    LAUNCHED(1);
+    KERNEL_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+// fused push + deposit, tile kernel (3D); returns 1 if this path does not apply (caller falls back)
+int lpic_push_deposit_tiles(lpic_ctx *c, int ispec, double dt, double q, double m, bool write_part) {
+    const Geom &g = c->g;
+    Species &sp = c->spec[ispec];
+    if (g.dim != 3) return 1;
+    if (sp.max_npart == 0) return 0;
+    return launch_tiles<4, 4, 16, 8>(c, sp, dt, q, m, write_part);
+}

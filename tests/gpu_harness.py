@@ -182,3 +182,75 @@ def engine_from_pml_golden(g, tag, with_part=True):
     eng.upload_all()
     meta = dict(dt=float(g["meta/dt"]), q=[float(v) for v in g["meta/q"]], m=[float(v) for v in g["meta/m"]], dim=dim)
     return eng, meta
+
+
+class _Synthetic(dict):
+    """A golden-format snapshot built on the fly (same keys as tests/golden/ref_step_*.npz)."""
+
+    @property
+    def files(self):
+        return list(self.keys())
+
+
+def synthetic_snapshot(wl, field_amp=1.0, seed=5):
+    """A periodic thermal plasma of `wl` (lambdapic_b200.workloads.ThermalPlasma) as a golden-format snapshot `t0`: particles
+    loaded cell by cell as the reference loader does, Maxwellian momenta, smooth random E/B including guards.  Feeds both
+    `engine_from_golden` and `oracle.OState.from_golden`, so the CUDA path and the oracle start from identical bits."""
+    from lambdapic_b200._lib import PART_ATTRS as PA
+    pg = wl.grid()
+    dim = wl.dim
+    g = _Synthetic()
+    for k, v in dict(dim=dim, nx=pg.nx, ny=pg.ny, nz=pg.nz, n_guard=pg.n_guard, dx=pg.dx, dy=pg.dy, dz=pg.dz if dim == 3 else 0.0,
+                     dt=wl.dt, nspec=len(wl.ppc), npatch_x=pg.npx, npatch_y=pg.npy, npatch_z=pg.npz).items():
+        g[f"meta/{k}"] = np.asarray(v)
+    g["meta/q"], g["meta/m"] = np.array(wl.q), np.array(wl.m)
+    g["meta/x0"], g["meta/y0"], g["meta/z0"] = pg.x0.astype(float), pg.y0.astype(float), pg.z0.astype(float)
+    g["meta/neighbor_ipatch"] = pg.neighbor_ipatch
+    g["meta/bounds_global"] = pg.glob
+    rng = np.random.default_rng(seed)
+    shape = (pg.nx + 2 * pg.n_guard, pg.ny + 2 * pg.n_guard) + ((pg.nz + 2 * pg.n_guard,) if dim == 3 else ())
+    amps = dict(ex=3e10, ey=-2e10, ez=1e10, bx=50.0, by=-80.0, bz=30.0)
+    idx = np.meshgrid(*[np.arange(n) for n in ((pg.nx, pg.ny, pg.nz) if dim == 3 else (pg.nx, pg.ny))], indexing="ij")
+    for ip in range(pg.npatch):
+        for a in FIELD_ATTRS:
+            g[f"t0/f/{ip}/{a}"] = field_amp * amps[a] * rng.standard_normal(shape) if a in amps else np.zeros(shape)
+        for s, ppc in enumerate(wl.ppc):
+            n = idx[0].size * ppc
+            d = {a: np.zeros(n) for a in PA}
+            d["x"] = pg.x0[ip] + (np.repeat(idx[0].ravel(), ppc) + rng.random(n) - 0.5) * pg.dx
+            d["y"] = pg.y0[ip] + (np.repeat(idx[1].ravel(), ppc) + rng.random(n) - 0.5) * pg.dy
+            if dim == 3:
+                d["z"] = pg.z0[ip] + (np.repeat(idx[2].ravel(), ppc) + rng.random(n) - 0.5) * pg.dz
+            for a in ("ux", "uy", "uz"):
+                d[a] = rng.normal(0.0, wl.uth[s], n)
+            d["inv_gamma"] = 1.0 / np.sqrt(1 + d["ux"]**2 + d["uy"]**2 + d["uz"]**2)
+            d["w"] = np.full(n, wl.weights[s])
+            d["_id"] = ((np.uint64(ip) << np.uint64(32)) | np.arange(n, dtype=np.uint64)).view(np.float64)
+            for a in PA:
+                g[f"t0/p/{ip}/{s}/{a}"] = d[a]
+            g[f"t0/p/{ip}/{s}/is_dead"] = np.zeros(n, dtype=bool)
+    return g
+
+
+def compare_with_oracle(eng, ost, nbuf=None, rtol=1e-12, part_fields=True):
+    """Device state (through host_view) against an oracle OState: integers bit-exact, floats <= rtol of each array's max-abs."""
+    from tests.parity import PART_FLOAT_ATTRS, rel_err
+    st = host_view(eng, nbuf, with_sorter=False)
+    worst = {}
+    for ip, p in enumerate(ost.patches):
+        for a in FIELD_ATTRS:
+            e = rel_err(getattr(st.patches[ip].fields, a), getattr(p.fields, a))
+            worst[a] = max(worst.get(a, 0.0), e)
+            assert e <= rtol, f"field {a} patch {ip}: rel err {e:.3e}"
+        for s in range(ost.nspec):
+            ref, got = p.particles[s], st.patches[ip].particles[s]
+            assert np.array_equal(np.asarray(got.is_dead).astype(bool), ref.is_dead), f"is_dead / capacity patch {ip} spec {s}"
+            assert np.array_equal(np.asarray(got._id).view(np.uint64), ref._id.view(np.uint64)), f"slot permutation patch {ip} spec {s}"
+            alive = ~ref.is_dead
+            for a in PART_FLOAT_ATTRS:
+                if (eng.dim == 2 and a == "z") or (a.endswith("_part") and (not part_fields or getattr(got, a) is None)):
+                    continue
+                e = rel_err(np.asarray(getattr(got, a))[alive], getattr(ref, a)[alive])
+                worst[a] = max(worst.get(a, 0.0), e)
+                assert e <= rtol, f"particle {a} patch {ip} spec {s}: rel err {e:.3e}"
+    return worst
