@@ -4,11 +4,14 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path on the host cores
 
-Workload (config.workload): BASELINE.json configs[4], "3D uniform thermal plasma weak scaling": periodic
-electron-proton plasma, n = n_c(0.8 um), d = lambda/20, 1 keV, 16+16 particles per cell, 16^3-cell patches,
-256^3 cells PER GPU (N = 8 is the full 512^3 box).  configs[1..3] (laser / CPML / moving-window scripts) run through
-the public API in examples/ and are parity cases; configs[0] is the reference's own CPU-sized test, used by the parity
-tests.  Defaults: 20 timed steps after 5 warm-up steps.
+Workload (config.workload): BASELINE.json configs[4], "3D uniform thermal plasma weak/strong scaling sweep (512^3 cells,
+8-64 ppc)": periodic electron-proton plasma, n = n_c(0.8 um), d = lambda/20, 1 keV, 16^3-cell patches, fp64.
+  --scaling weak (default): 256^3 cells and 32+32 particles per cell PER GPU = 1.07e9 particles per GPU (SURVEY.md 8(d)-5's
+                            weak shape; N = 8 is the full 512^3 box at 64 ppc)
+  --scaling strong:         the 512^3 box at 4+4 ppc (1.07e9 particles in total) split over the N GPUs
+configs[1..3] (laser / CPML / moving-window scripts) run through the public API in examples/ and are parity cases;
+configs[0] is the reference's own CPU-sized test, used by the parity tests.  Defaults: 20 timed steps after 5 warm-up steps.
+For N > 1 a multi-rank parity self-check runs before the timed region (key "multirank_parity").
 
 One "step" = everything simulation/simulation.py:937-1130 does between stage `start` and stage `end` for the
 periodic unified-pusher case: 4 FDTD half steps, 4 guard syncs, per-species sort, J/rho reset, fused
@@ -41,19 +44,26 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cells", type=int, nargs=3, default=None, help="cells per GPU (default 256 256 256)")
-    ap.add_argument("--ppc", type=int, nargs=2, default=[16, 16])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--cells", type=int, nargs=3, default=None, help="weak: cells per GPU (default 256^3); strong: global cells (default 512^3)")
+    ap.add_argument("--ppc", type=int, nargs=2, default=None, help="default 32 32 (weak) / 4 4 (strong)")
     ap.add_argument("--patch", type=int, default=16)
     ap.add_argument("--slot-order", action="store_true", help="use the v1 particle kernel (memory order)")
     ap.add_argument("--breakdown", action="store_true", help="print per-operator CUDA-event times of one extra step to stderr")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-cells", type=int, default=64, help="edge of the CPU sample box (cells)")
-    return ap.parse_args()
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the multi-rank parity self-check (N > 1)")
+    args = ap.parse_args()
+    if args.ppc is None:
+        args.ppc = [32, 32] if args.scaling == "weak" else [4, 4]
+    return args
 
 
 def workload(args, nranks):
     from lambdapic_b200.workloads import ThermalPlasma
+    if args.scaling == "strong":  # fixed global box, block-partitioned over the ranks
+        return ThermalPlasma(dim=3, cells=tuple(args.cells) if args.cells else (512, 512, 512), patch=(args.patch,) * 3, ppc=tuple(args.ppc))
     per_gpu = tuple(args.cells) if args.cells else (256, 256, 256)
     # weak scaling: the global box doubles along z, then y, then x as ranks double (8 ranks: 2x2x2 blocks)
     mult = [1, 1, 1]
@@ -139,8 +149,15 @@ def cpu_reference_run(args, steps, warmup):
     """Times `steps` full PIC steps of the reference's CPU path on a bounded sample of the workload."""
     from lambdapic_b200.workloads import ThermalPlasma
     from oracle import oracle as orc
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: override it (the reference arm uses all host threads it can), and
+    # also tell an OpenMP runtime that was already initialised by an earlier import
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    try:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(cores))
+    except OSError:
+        pass
     orc.lib()
     kind = "reference" if orc.have_ref() else "port"
     backend = "ref" if kind == "reference" else "port"
@@ -157,9 +174,9 @@ def cpu_reference_run(args, steps, warmup):
     dt = time.perf_counter() - t0
     sample = (f"{e}^3 cells, {args.ppc[0]}+{args.ppc[1]} ppc, {args.patch}^3 patches ({wl_small.n_particles()} particles), "
               f"{steps} steps after {max(warmup, 1)} warm-up; pusher/sort/sync = the reference's C extensions "
-              f"(OpenMP, {cores} threads), FDTD = C restatement (serial)" if kind == "reference" else
+              f"(OpenMP, {cores} threads), FDTD = C restatement, OpenMP over patches" if kind == "reference" else
               f"{e}^3 cells, oracle C port, serial")
-    return {"value": n_upd / dt, "unit": UNIT, "cores": cores if kind == "reference" else 1, "kind": kind,
+    return {"value": n_upd / dt, "unit": UNIT, "cores": cores if kind == "reference" else 1, "omp_threads": cores, "kind": kind,
             "sample": sample, "ms_per_step": 1e3 * dt / steps}
 
 
@@ -172,19 +189,95 @@ def run_reference(args):
     wl = workload(args, args.gpus)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(args, wl, args.gpus), "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 def config_dict(args, wl, nranks):
-    return {"workload": "BASELINE.json configs[4]: 3D uniform thermal e-/p+ plasma, periodic, weak scaling "
+    return {"workload": f"BASELINE.json configs[4]: 3D uniform thermal e-/p+ plasma, periodic, {args.scaling} scaling "
                         f"({wl.cells[0]}x{wl.cells[1]}x{wl.cells[2]} cells on {nranks} GPU(s), "
                         f"{args.ppc[0]}+{args.ppc[1]} ppc, {args.patch}^3-cell patches, 1 keV, fp64)",
             "cells_global": list(wl.cells), "particles_global": wl.n_particles(), "patch_cells": args.patch,
             "ppc": list(args.ppc), "n_guard": 3, "parallelism": f"patch blocks over {nranks} GPU(s)",
             "l2_policy": "inputs larger than L2 (particle arenas are tens of GB; no flush needed)"}
+
+
+def multirank_parity_check(args, rank, world, local, nsteps=3, rtol=1e-11):
+    """N ranks against 1 rank on the same global patch grid, before the timed region: 64^3 cells in 16^3 patches, 2+2 ppc,
+    20 keV (particles cross patch and rank boundaries every step).  Every rank runs `nsteps` steps of its block through
+    the NCCL path; rank 0 also runs the whole box on its own GPU through the single-rank path.  Compared per global patch:
+    E, B, J, rho (<= rtol of each array's max-abs), the SET of alive particle ids (exact) and their positions / momenta
+    (<= rtol).  A mismatch makes every rank exit non-zero."""
+    import torch
+    import torch.distributed as dist
+    from lambdapic_b200._lib import FIELD_ATTRS
+    from lambdapic_b200.multigpu import HaloExchanger
+    from lambdapic_b200.workloads import ThermalPlasma, build_engine
+    wl = ThermalPlasma(dim=3, cells=(64, 64, 64), patch=(16, 16, 16), ppc=(2, 2), temperature_eV=2.0e4)
+    rev = [False, False]
+
+    def snapshot(eng):
+        eng.download_all()
+        out = {}
+        for k, gp in enumerate(eng.grid.index):
+            d = {a: eng.field_view(a, k).copy() for a in FIELD_ATTRS}
+            for s in range(eng.nspec):
+                m = eng.species[s]
+                alive = ~m.view("is_dead", k)
+                ids = m.view("_id", k).view(np.uint64)[alive] & np.uint64((1 << 50) - 1)  # drop the rank bits
+                o = np.argsort(ids)
+                d[f"ids{s}"] = ids[o]
+                for a in ("x", "y", "z", "ux", "uy", "uz", "w"):
+                    d[f"{a}{s}"] = m.view(a, k)[alive][o]
+            out[int(gp)] = d
+        return out
+
+    eng = build_engine(wl, device=local, rank=rank, nranks=world)
+    halo = HaloExchanger(eng, eng.grid)
+    for _ in range(nsteps):
+        halo.step(wl.dt, wl.q, wl.m, rev)
+    mine = snapshot(eng)
+    eng.close()
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(mine, gathered, dst=0)
+    result = [None]
+    if rank == 0:
+        ref_eng = build_engine(wl, device=local, rank=0, nranks=1)
+        for _ in range(nsteps):
+            ref_eng.step(wl.dt, wl.q, wl.m, rev)
+        ref = snapshot(ref_eng)
+        ref_eng.close()
+        worst, bad, npatch = 0.0, [], 0
+        for part in gathered:
+            for gp, d in part.items():
+                npatch += 1
+                r = ref[gp]
+                for key, got in d.items():
+                    if key.startswith("ids"):
+                        if got.size != r[key].size or not np.array_equal(got, r[key]):
+                            bad.append(f"patch {gp} {key}: particle sets differ")
+                        continue
+                    if got.shape != r[key].shape:
+                        continue  # reported through the ids
+                    scale = float(np.abs(r[key]).max()) if r[key].size else 0.0
+                    e = float(np.abs(got - r[key]).max()) / scale if scale > 0 else 0.0
+                    worst = max(worst, e)
+                    if e > rtol:
+                        bad.append(f"patch {gp} {key}: rel err {e:.3e}")
+        if npatch != len(ref):
+            bad.append(f"{npatch} patches gathered, {len(ref)} expected")
+        result[0] = {"ok": not bad, "max_rel": worst, "rtol": rtol, "steps": nsteps, "ranks": world,
+                     "case": "64^3 cells, 16^3 patches, 2+2 ppc, 20 keV: N-rank NCCL path vs 1-rank path on rank 0's GPU",
+                     "errors": bad[:5]}
+    dist.broadcast_object_list(result, src=0)
+    if not result[0]["ok"]:
+        if rank == 0:
+            print(json.dumps({"multirank_parity": result[0]}), flush=True)
+        dist.destroy_process_group()
+        sys.exit(3)
+    return result[0]
 
 
 def main():
@@ -202,7 +295,10 @@ def main():
     from lambdapic_b200 import _lib
     from lambdapic_b200.workloads import build_engine
     wl = workload(args, world)
-    eng = build_engine(wl, device=local, rank=rank, nranks=world)
+    parity = None
+    if world > 1 and not args.no_parity_check:
+        parity = multirank_parity_check(args, rank, world, local)
+    eng = build_engine(wl, device=local, rank=rank, nranks=world, slack=1.4 if args.scaling == "weak" else 1.3)
     eng.slot_order = args.slot_order
     if world > 1:
         from lambdapic_b200.multigpu import HaloExchanger
@@ -281,10 +377,16 @@ def main():
     bytes_launch = 121.0 * n_local + (48.0 + 64.0) * cells_local
     avg_push_ms = float(np.mean(push_ms))
     achieved = bytes_launch / (avg_push_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "lpic_push_deposit = k_cell_perm + k_push_sorted<3> (gather+Boris+Esirkepov, cell-ordered, warp-cooperative) + k_deposit_list" if not args.slot_order else "k_particles<3,FUSED> (slot order)", "achieved": achieved, "peak": peak,
+    fp64_peak = _lib.C.c_double(0)
+    _lib.check(L.lpic_fp64_peak(eng.ctx, _lib.C.byref(fp64_peak)))
+    FLOP_PER_UPDATE = 1.4e3  # gather 6x27 FMA, Boris, 27..125-point Esirkepov deposit
+    fp64_achieved = FLOP_PER_UPDATE * n_local / (avg_push_ms * 1e-3) / 1e12
+    roofline = {"bound": "hbm", "kernel": "lpic_push_deposit = k_tile_perm + k_push_tile<4,4,16> (E/B tile staged in shared memory, gather+Boris+Esirkepov, per-cell carried sums) + k_list_particles" if not args.slot_order else "k_particles<3,FUSED> (slot order)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6.65 TB/s",
                 "avg_launch_ms": avg_push_ms, "algorithmic_bytes_per_launch": bytes_launch,
-                "share_of_step": eng.nspec * avg_push_ms / (ms.value / args.steps)}
+                "share_of_step": eng.nspec * avg_push_ms / (ms.value / args.steps),
+                "fp64": {"achieved_tflops": fp64_achieved, "peak_tflops": fp64_peak.value, "frac": fp64_achieved / max(fp64_peak.value, 1e-9),
+                         "flop_per_update": FLOP_PER_UPDATE, "peak_source": "measured by lpic_fp64_peak (DFMA chains, this device, this run)"}}
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         roofline["traffic"] = prof.get("bytes_per_particle") * n_local if prof.get("bytes_per_particle") else None
@@ -306,14 +408,16 @@ def main():
         return
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args, wl, world),
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "wall_ms_per_step": 1e3 * wall / args.steps}
 
+    if parity is not None:
+        line["multirank_parity"] = parity
     if e2e is not None:
         line["e2e"] = e2e
     if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_reference_run(args, steps=2, warmup=1)
+        line["cpu_baseline"] = cpu_reference_run(args, steps=10, warmup=1)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

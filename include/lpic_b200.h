@@ -187,6 +187,27 @@ int lpic_remote_migrate_unpack(lpic_ctx *ctx, int ispec, const int64_t *recv_cou
 int lpic_event_record(lpic_ctx *ctx, int slot);                              /* slot in [0, 4096) */
 int lpic_event_elapsed_ms(lpic_ctx *ctx, int slot_a, int slot_b, double *ms); /* synchronises on slot_b */
 int64_t lpic_launch_count(void);
+/* ---- inter-rank transport inside the library (comm.cu): NCCL point-to-point on its own stream, ordered against the compute
+ * stream with events.  Replaces core/mpi/mpi_manager.py:9-298 and the start/wait pairs of core/mpi/sync_fields{2,3}d.c
+ * (:713-866 currents, :883-996 guards) and core/mpi/sync_particles_{2,3}d.c:413-745.  Call order: lpic_halo_plan ->
+ * lpic_comm_unique_id on one rank, id passed to the others by the host (MPI_Bcast / torch.distributed) -> lpic_comm_init
+ * on every rank (collective).  peer_rank[s] = rank of the plan's peer slot s. */
+int lpic_comm_unique_id(void *id128);
+int lpic_comm_nccl_version(void);
+int lpic_comm_init(lpic_ctx *ctx, const void *id128, int rank, int nranks, const int64_t *peer_rank);
+int64_t lpic_comm_bytes_sent(const lpic_ctx *ctx);
+/* pack + ncclSend/ncclRecv per peer, asynchronous; run the intra-rank lpic_sync_guard_fields / lpic_sync_currents between
+ * start and wait (simulation/simulation.py:948-952); wait = compute stream waits for the receive, then one unpack kernel */
+int lpic_halo_start(lpic_ctx *ctx, uint32_t attr_mask, int reduce);
+int lpic_halo_wait(lpic_ctx *ctx);
+/* particles: classification, counts exchanged device to device, ONE host synchronisation for the message sizes, payload
+ * exchange overlapped with the intra-rank fill.  Returns 1 when some patch has to grow first: call lpic_species_extend with
+ * to_extend, then again with resume = 1.  info[4] = sent, received, largest per-patch remote / intra-rank arrival count.
+ * The call pair performs the WHOLE migration of the species (other ranks and intra-rank). */
+int lpic_migrate_remote_start(lpic_ctx *ctx, int ispec, int resume, int64_t *to_extend, int64_t *info);
+int lpic_migrate_remote_wait(lpic_ctx *ctx, int ispec);
+/* measured fp64 FMA throughput of the context's device in TFLOP/s (bench.py's roofline.fp64 co-bound; no reference counterpart) */
+int lpic_fp64_peak(lpic_ctx *ctx, double *tflops);
 
 void *lpic_stream(lpic_ctx *ctx); /* cudaStream_t of the context (for event timing by the host) */
 

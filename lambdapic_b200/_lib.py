@@ -83,6 +83,15 @@ SIGNATURES = {
     "lpic_event_record": (_int, [_vp, _int]),
     "lpic_event_elapsed_ms": (_int, [_vp, _int, _int, _vp]),
     "lpic_launch_count": (_i64, []),
+    "lpic_fp64_peak": (_int, [_vp, _vp]),
+    "lpic_comm_unique_id": (_int, [_vp]),
+    "lpic_comm_nccl_version": (_int, []),
+    "lpic_comm_init": (_int, [_vp, _vp, _int, _int, _vp]),
+    "lpic_comm_bytes_sent": (_i64, [_vp]),
+    "lpic_halo_start": (_int, [_vp, _u32, _int]),
+    "lpic_halo_wait": (_int, [_vp]),
+    "lpic_migrate_remote_start": (_int, [_vp, _int, _int, _vp, _vp]),
+    "lpic_migrate_remote_wait": (_int, [_vp, _int]),
     "lpic_stream": (_vp, [_vp]),
 }
 

@@ -140,6 +140,7 @@ extern "C" void lpic_destroy(lpic_ctx *c) {
 extern "C" int lpic_set_patch_geometry(lpic_ctx *c, const double *x0, const double *y0, const double *z0,
                                        const int64_t *nbr, const double *box, const double *glob, int64_t rank,
                                        const int64_t *patch_index) {
+    DeviceGuard dg(c);
     const Geom &g = c->g;
     const i64 n = g.npatch;
     std::vector<double> zeros(n, 0.0);
@@ -160,11 +161,14 @@ extern "C" int lpic_set_patch_geometry(lpic_ctx *c, const double *x0, const doub
 }
 
 extern "C" int lpic_sync(lpic_ctx *c) {
+    DeviceGuard dg(c);
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return 0;
 }
-extern "C" void *lpic_stream(lpic_ctx *c) { return (void *)c->stream; }
-extern "C" int64_t lpic_field_cells(const lpic_ctx *c) { return c->g.ncell; }
+extern "C" void *lpic_stream(lpic_ctx *c) {
+    DeviceGuard dg(c); return (void *)c->stream; }
+extern "C" int64_t lpic_field_cells(const lpic_ctx *c) {
+    DeviceGuard dg(c); return c->g.ncell; }
 
 // ---- fields --------------------------------------------------------------------------------------------------
 static int copy_fields(lpic_ctx *c, uint32_t mask, double *host, bool up) {
@@ -182,10 +186,13 @@ static int copy_fields(lpic_ctx *c, uint32_t mask, double *host, bool up) {
     if (!up) CUDA_TRY(cudaStreamSynchronize(c->stream));
     return 0;
 }
-extern "C" int lpic_upload_fields(lpic_ctx *c, uint32_t mask, const double *host) { return copy_fields(c, mask, (double *)host, true); }
-extern "C" int lpic_download_fields(lpic_ctx *c, uint32_t mask, double *host) { return copy_fields(c, mask, host, false); }
+extern "C" int lpic_upload_fields(lpic_ctx *c, uint32_t mask, const double *host) {
+    DeviceGuard dg(c); return copy_fields(c, mask, (double *)host, true); }
+extern "C" int lpic_download_fields(lpic_ctx *c, uint32_t mask, double *host) {
+    DeviceGuard dg(c); return copy_fields(c, mask, host, false); }
 
 extern "C" int lpic_upload_field_ptrs(lpic_ctx *c, int attr, const double *const *ptrs) {
+    DeviceGuard dg(c);
     REQUIRE(attr >= 0 && attr < LPIC_NFIELD, "bad field attribute %d", attr);
     for (int p = 0; p < c->g.npatch; p++)
         CUDA_TRY(cudaMemcpyAsync(field_ptr(c, attr) + (size_t)p * c->g.ncell, ptrs[p], sizeof(double) * c->g.ncell,
@@ -193,6 +200,7 @@ extern "C" int lpic_upload_field_ptrs(lpic_ctx *c, int attr, const double *const
     return 0;
 }
 extern "C" int lpic_download_field_ptrs(lpic_ctx *c, int attr, double *const *ptrs) {
+    DeviceGuard dg(c);
     REQUIRE(attr >= 0 && attr < LPIC_NFIELD, "bad field attribute %d", attr);
     for (int p = 0; p < c->g.npatch; p++)
         CUDA_TRY(cudaMemcpyAsync(ptrs[p], field_ptr(c, attr) + (size_t)p * c->g.ncell, sizeof(double) * c->g.ncell,
@@ -223,6 +231,7 @@ static int upload_layout(lpic_ctx *c, Species &sp) {
 
 extern "C" int lpic_species_alloc(lpic_ctx *c, int ispec, const int64_t *npart, double slack, int64_t min_extra,
                                   int with_part) {
+    DeviceGuard dg(c);
     REQUIRE(ispec >= 0 && ispec < c->nspec, "bad species %d", ispec);
     Species &sp = c->spec[ispec];
     const i64 n = c->g.npatch;
@@ -259,6 +268,7 @@ extern "C" int lpic_species_alloc(lpic_ctx *c, int ispec, const int64_t *npart, 
 }
 
 extern "C" int lpic_species_layout(const lpic_ctx *c, int ispec, int64_t *off, int64_t *pcap, int64_t *npart, int64_t *total) {
+    DeviceGuard dg(c);
     REQUIRE(ispec >= 0 && ispec < c->nspec && c->spec[ispec].allocated, "species %d not allocated", ispec);
     const Species &sp = c->spec[ispec];
     const i64 n = c->g.npatch;
@@ -280,6 +290,7 @@ static int particle_array(lpic_ctx *c, int ispec, int attr, void **dev, size_t *
 }
 
 extern "C" int lpic_upload_particles(lpic_ctx *c, int ispec, int attr, const void *host) {
+    DeviceGuard dg(c);
     void *dev; size_t esz;
     if (int r = particle_array(c, ispec, attr, &dev, &esz)) return r;
     CUDA_TRY(cudaMemcpyAsync(dev, host, esz * c->spec[ispec].total, cudaMemcpyHostToDevice, c->stream));
@@ -288,6 +299,7 @@ extern "C" int lpic_upload_particles(lpic_ctx *c, int ispec, int attr, const voi
     return 0;
 }
 extern "C" int lpic_download_particles(lpic_ctx *c, int ispec, int attr, void *host) {
+    DeviceGuard dg(c);
     void *dev; size_t esz;
     if (int r = particle_array(c, ispec, attr, &dev, &esz)) return r;
     CUDA_TRY(cudaMemcpyAsync(host, dev, esz * c->spec[ispec].total, cudaMemcpyDeviceToHost, c->stream));
@@ -295,6 +307,7 @@ extern "C" int lpic_download_particles(lpic_ctx *c, int ispec, int attr, void *h
     return 0;
 }
 extern "C" int lpic_upload_particle_ptrs(lpic_ctx *c, int ispec, int attr, const void *const *ptrs) {
+    DeviceGuard dg(c);
     void *dev; size_t esz;
     if (int r = particle_array(c, ispec, attr, &dev, &esz)) return r;
     Species &sp = c->spec[ispec];
@@ -306,6 +319,7 @@ extern "C" int lpic_upload_particle_ptrs(lpic_ctx *c, int ispec, int attr, const
     return 0;
 }
 extern "C" int lpic_download_particle_ptrs(lpic_ctx *c, int ispec, int attr, void *const *ptrs) {
+    DeviceGuard dg(c);
     void *dev; size_t esz;
     if (int r = particle_array(c, ispec, attr, &dev, &esz)) return r;
     Species &sp = c->spec[ispec];
@@ -355,6 +369,7 @@ __global__ void __launch_bounds__(256) k_relayout(const T *__restrict__ src, T *
 }
 
 extern "C" int lpic_species_extend(lpic_ctx *c, int ispec, const int64_t *ext, const uint64_t *id_first, int *relayout) {
+    DeviceGuard dg(c);
     REQUIRE(ispec >= 0 && ispec < c->nspec && c->spec[ispec].allocated, "species %d not allocated", ispec);
     Species &sp = c->spec[ispec];
     const i64 n = c->g.npatch;
@@ -459,6 +474,7 @@ extern "C" int lpic_species_extend(lpic_ctx *c, int ispec, const int64_t *ext, c
 // New slot counts inside the existing segments (every npart[p] <= capacity of patch p): the host re-initialised some
 // patches' particles (ParticlesBase.initialize after a MovingWindow shift) and uploads their values next.
 extern "C" int lpic_species_set_npart(lpic_ctx *c, int ispec, const int64_t *npart) {
+    DeviceGuard dg(c);
     REQUIRE(ispec >= 0 && ispec < c->nspec && c->spec[ispec].allocated, "species %d not allocated", ispec);
     Species &sp = c->spec[ispec];
     const i64 n = c->g.npatch;
@@ -486,8 +502,51 @@ int lpic_ensure_scratch(lpic_ctx *c, i64 slots) {
 }
 
 
+// fp64 FMA peak of this device, measured: the co-bound of the fused particle kernel next to the HBM copy bandwidth
+// (SURVEY.md 8(d)).  8 independent DFMA chains per thread, 148 x 8 CTAs of 256 threads, best of 5 launches.
+__global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters, double a, double b) {
+    double v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = threadIdx.x + j;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = __fma_rn(v[j], a, b);
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) sum += v[j];
+    if (sum == 12345.678) out[0] = sum;  // never true: keeps the chains alive
+}
+extern "C" int lpic_fp64_peak(lpic_ctx *c, double *tflops) {
+    DeviceGuard dg(c);
+    const int iters = 4096, grid = 148 * 8;
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; rep++) {
+        CUDA_TRY(cudaEventRecord(e0, c->stream));
+        k_fp64_peak<<<grid, 256, 0, c->stream>>>(c->d_tmpf, iters, 0.999999, 1e-9);
+        CUDA_TRY(cudaEventRecord(e1, c->stream));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 32.0 * iters * 256.0 * grid;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    LAUNCHED(6);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
+    return 0;
+}
+
 static const int kEventSlots = 4096;
 extern "C" int lpic_event_record(lpic_ctx *c, int slot) {
+    DeviceGuard dg(c);
     REQUIRE(slot >= 0 && slot < kEventSlots, "event slot %d out of range", slot);
     if (!c->events) c->events = new cudaEvent_t[kEventSlots]();
     if (!c->events[slot]) CUDA_TRY(cudaEventCreate(&c->events[slot]));
@@ -495,6 +554,7 @@ extern "C" int lpic_event_record(lpic_ctx *c, int slot) {
     return 0;
 }
 extern "C" int lpic_event_elapsed_ms(lpic_ctx *c, int a, int b, double *ms) {
+    DeviceGuard dg(c);
     REQUIRE(c->events && a >= 0 && b >= 0 && a < kEventSlots && b < kEventSlots && c->events[a] && c->events[b], "events not recorded");
     CUDA_TRY(cudaEventSynchronize(c->events[b]));
     float f = 0.f;

@@ -417,6 +417,7 @@ static int pml_advance(lpic_ctx *c, int is_b, double dt) {
 }
 
 extern "C" int lpic_update_efield(lpic_ctx *c, double dt) {
+    DeviceGuard dg(c);
     const Geom &g = c->g;
     const i64 n = (i64)g.npatch * g.nx * g.ny * g.nz;
     // bfactor = dt*c**2, jfactor = dt/epsilon_0 (core/maxwell/cpu.py:90-91)
@@ -435,6 +436,7 @@ extern "C" int lpic_update_efield(lpic_ctx *c, double dt) {
 }
 
 extern "C" int lpic_update_bfield(lpic_ctx *c, double dt) {
+    DeviceGuard dg(c);
     const Geom &g = c->g;
     const i64 n = (i64)g.npatch * g.nx * g.ny * g.nz;
     const PmlState *pm = c->pml;
@@ -451,6 +453,7 @@ extern "C" int lpic_update_bfield(lpic_ctx *c, double dt) {
 }
 
 extern "C" int lpic_sync_guard_fields(lpic_ctx *c, uint32_t attr_mask) {
+    DeviceGuard dg(c);
     const Geom &g = c->g;
     AttrList attrs;
     int na = 0;
@@ -466,6 +469,7 @@ extern "C" int lpic_sync_guard_fields(lpic_ctx *c, uint32_t attr_mask) {
 }
 
 extern "C" int lpic_sync_currents(lpic_ctx *c) {
+    DeviceGuard dg(c);
     const Geom &g = c->g;
     dim3 grid(div_up((i64)g.npatch * g.nx * g.ny * g.nz, 256), 4);
     k_sync_currents<<<grid, 256, 0, c->stream>>>(g, c->fields, c->d_nbr);
@@ -476,12 +480,14 @@ extern "C" int lpic_sync_currents(lpic_ctx *c) {
 }
 
 extern "C" int lpic_reset_currents(lpic_ctx *c) {
+    DeviceGuard dg(c);
     const Geom &g = c->g;
     CUDA_TRY(cudaMemsetAsync(field_ptr(c, LPIC_JX), 0, sizeof(double) * 4 * (size_t)g.npatch * g.ncell, c->stream));
     return 0;
 }
 
 extern "C" int lpic_field_energy_sums(lpic_ctx *c, double *out2) {
+    DeviceGuard dg(c);
     const Geom &g = c->g;
     CUDA_TRY(cudaMemsetAsync(c->d_tmpf, 0, 2 * sizeof(double), c->stream));
     k_field_energy<<<148 * 4, 256, 0, c->stream>>>(g, c->fields, c->d_tmpf);
@@ -503,6 +509,7 @@ void lpic_free_pml(lpic_ctx *c) {
 
 extern "C" int lpic_pml_configure(lpic_ctx *c, int64_t ninst, const int64_t *inst_patch, const int64_t *inst_axis,
                                   const int64_t *inst_slot, const int64_t *ranges, const double *profiles, int64_t nmax) {
+    DeviceGuard dg(c);
     const Geom &g = c->g;
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     lpic_free_pml(c);
@@ -559,13 +566,16 @@ extern "C" int lpic_pml_configure(lpic_ctx *c, int64_t ninst, const int64_t *ins
     return 0;
 }
 
-extern "C" int64_t lpic_pml_psi_words(const lpic_ctx *c) { return c->pml ? c->pml->ninst * 4 * c->pml->ncint : 0; }
+extern "C" int64_t lpic_pml_psi_words(const lpic_ctx *c) {
+    DeviceGuard dg(c); return c->pml ? c->pml->ninst * 4 * c->pml->ncint : 0; }
 extern "C" int lpic_pml_upload_psi(lpic_ctx *c, const double *host) {
+    DeviceGuard dg(c);
     if (!c->pml) return 0;
     CUDA_TRY(cudaMemcpyAsync(c->pml->d_psi, host, sizeof(double) * (size_t)lpic_pml_psi_words(c), cudaMemcpyHostToDevice, c->stream));
     return 0;
 }
 extern "C" int lpic_pml_download_psi(lpic_ctx *c, double *host) {
+    DeviceGuard dg(c);
     if (!c->pml) return 0;
     CUDA_TRY(cudaMemcpyAsync(host, c->pml->d_psi, sizeof(double) * (size_t)lpic_pml_psi_words(c), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -574,6 +584,7 @@ extern "C" int lpic_pml_download_psi(lpic_ctx *c, double *host) {
 
 extern "C" int lpic_laser_bfields(lpic_ctx *c, int64_t laserpos, int64_t n, const int64_t *patches, const int64_t *ranges,
                                   const double *ey_src, const double *ez_src, double dt) {
+    DeviceGuard dg(c);
     const Geom &g = c->g;
     if (n <= 0) return 0;
     REQUIRE(laserpos >= 1 && laserpos < g.nx + g.ng, "laserpos %lld outside the padded patch", (long long)laserpos);

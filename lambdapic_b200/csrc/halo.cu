@@ -145,11 +145,13 @@ AttrList attr_list(uint32_t mask) {
 
 }  // namespace
 
+void lpic_free_comm(lpic_ctx *c);
 void lpic_free_peers(lpic_ctx *c) {
+    lpic_free_comm(c);  // the communicator's staging buffers are sized by the plan
     HaloPlan *h = c->halo;
     if (!h) return;
     delete[] h->h_send_patch; delete[] h->h_send_b; delete[] h->h_recv_patch; delete[] h->h_recv_b; delete[] h->h_mig_send_cnt;
-    cudaFree(h->d_send_patch); cudaFree(h->d_send_b); cudaFree(h->d_send_woff); cudaFree(h->d_recv_peer); cudaFree(h->d_recv_woff);
+    cudaFree(h->d_send_patch); cudaFree(h->d_send_b); cudaFree(h->d_recv_patch); cudaFree(h->d_recv_b); cudaFree(h->d_send_woff); cudaFree(h->d_recv_peer); cudaFree(h->d_recv_woff);
     cudaFree(h->d_mig_send_cnt); cudaFree(h->d_mig_send_poff); cudaFree(h->d_mig_recv_cnt); cudaFree(h->d_mig_recv_poff);
     cudaFree(h->d_mig_incoming);
     delete h;
@@ -158,6 +160,7 @@ void lpic_free_peers(lpic_ctx *c) {
 
 extern "C" int lpic_halo_plan(lpic_ctx *c, int npeers, const int64_t *nsend, const int64_t *send_patch, const int64_t *send_b,
                               const int64_t *nrecv, const int64_t *recv_patch, const int64_t *recv_b) {
+    DeviceGuard dg(c);
     REQUIRE(npeers >= 0 && npeers <= LPIC_MAX_PEERS, "at most %d peer ranks are supported", LPIC_MAX_PEERS);
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     lpic_free_peers(c);
@@ -174,7 +177,7 @@ extern "C" int lpic_halo_plan(lpic_ctx *c, int npeers, const int64_t *nsend, con
     h->h_send_patch = new int[h->nsend_total + 1]; h->h_send_b = new int[h->nsend_total + 1];
     h->h_recv_patch = new int[h->nrecv_total + 1]; h->h_recv_b = new int[h->nrecv_total + 1];
     h->h_mig_send_cnt = new i64[h->nsend_total + 1];
-    std::vector<int> sp(h->nsend_total), sb(h->nsend_total), rpeer((size_t)g.npatch * g.nb, -1);
+    std::vector<int> sp(h->nsend_total), sb(h->nsend_total), rpeer((size_t)g.npatch * g.nb, -1), rp(h->nrecv_total), rb(h->nrecv_total);
     std::vector<i64> swoff(h->nsend_total), rwoff((size_t)g.npatch * g.nb, 0);
     for (int s = 0; s < npeers; s++) {
         i64 w = 0;
@@ -189,8 +192,8 @@ extern "C" int lpic_halo_plan(lpic_ctx *c, int npeers, const int64_t *nsend, con
         w = 0;
         for (i64 e = h->recv_first[s]; e < h->recv_first[s + 1]; e++) {
             REQUIRE(recv_patch[e] >= 0 && recv_patch[e] < g.npatch && recv_b[e] >= 0 && recv_b[e] < g.nb, "bad recv entry");
-            h->h_recv_patch[e] = (int)recv_patch[e];
-            h->h_recv_b[e] = (int)recv_b[e];
+            rp[e] = h->h_recv_patch[e] = (int)recv_patch[e];
+            rb[e] = h->h_recv_b[e] = (int)recv_b[e];
             const size_t key = (size_t)recv_patch[e] * g.nb + recv_b[e];
             REQUIRE(rpeer[key] < 0, "boundary listed twice in the receive plan");
             rpeer[key] = s;
@@ -200,6 +203,7 @@ extern "C" int lpic_halo_plan(lpic_ctx *c, int npeers, const int64_t *nsend, con
         h->recv_words[s] = w;
     }
     if (to_device(&h->d_send_patch, sp) || to_device(&h->d_send_b, sb) || to_device(&h->d_send_woff, swoff) ||
+        to_device(&h->d_recv_patch, rp) || to_device(&h->d_recv_b, rb) ||
         to_device(&h->d_recv_peer, rpeer) || to_device(&h->d_recv_woff, rwoff))
         return -1;
     CUDA_TRY(cudaMalloc(&h->d_mig_send_cnt, sizeof(i64) * (h->nsend_total + 1)));
@@ -211,11 +215,17 @@ extern "C" int lpic_halo_plan(lpic_ctx *c, int npeers, const int64_t *nsend, con
 }
 
 extern "C" int64_t lpic_halo_words(lpic_ctx *c, int slot, int recv) {
+    DeviceGuard dg(c);
     if (!c->halo || slot < 0 || slot >= c->halo->npeers) return -1;
     return recv ? c->halo->recv_words[slot] : c->halo->send_words[slot];
 }
 
+int lpic_halo_pack_to(lpic_ctx *c, int slot, uint32_t mask, int reduce, double *dev_send);
 extern "C" int lpic_halo_pack(lpic_ctx *c, int slot, uint32_t mask, int reduce, double *dev_send) {
+    DeviceGuard dg(c);
+    return lpic_halo_pack_to(c, slot, mask, reduce, dev_send);
+}
+int lpic_halo_pack_to(lpic_ctx *c, int slot, uint32_t mask, int reduce, double *dev_send) {
     HaloPlan *h = c->halo;
     REQUIRE(h && slot >= 0 && slot < h->npeers, "no exchange plan / bad peer slot");
     const i64 ne = h->send_first[slot + 1] - h->send_first[slot];
@@ -231,7 +241,12 @@ extern "C" int lpic_halo_pack(lpic_ctx *c, int slot, uint32_t mask, int reduce, 
     return 0;
 }
 
+int lpic_halo_unpack_from(lpic_ctx *c, uint32_t mask, int reduce, const double *const *dev_recv, cudaStream_t st);
 extern "C" int lpic_halo_unpack(lpic_ctx *c, uint32_t mask, int reduce, const double *const *dev_recv) {
+    DeviceGuard dg(c);
+    return lpic_halo_unpack_from(c, mask, reduce, dev_recv, c->stream);
+}
+int lpic_halo_unpack_from(lpic_ctx *c, uint32_t mask, int reduce, const double *const *dev_recv, cudaStream_t st) {
     HaloPlan *h = c->halo;
     REQUIRE(h, "no exchange plan");
     if (h->nrecv_total == 0) return 0;
@@ -241,10 +256,10 @@ extern "C" int lpic_halo_unpack(lpic_ctx *c, uint32_t mask, int reduce, const do
     const AttrList attrs = attr_list(mask);
     if (reduce) {
         dim3 grid(div_up((i64)g.npatch * g.nx * g.ny * g.nz, 256), attrs.n);
-        k_halo_unpack_reduce<<<grid, 256, 0, c->stream>>>(g, c->fields, h->d_recv_peer, h->d_recv_woff, attrs, bufs);
+        k_halo_unpack_reduce<<<grid, 256, 0, st>>>(g, c->fields, h->d_recv_peer, h->d_recv_woff, attrs, bufs);
     } else {
         dim3 grid(div_up((i64)g.npatch * g.ncell, 256), attrs.n);
-        k_halo_unpack_copy<<<grid, 256, 0, c->stream>>>(g, c->fields, h->d_recv_peer, h->d_recv_woff, attrs, bufs);
+        k_halo_unpack_copy<<<grid, 256, 0, st>>>(g, c->fields, h->d_recv_peer, h->d_recv_woff, attrs, bufs);
     }
     LAUNCHED(1);
     KERNEL_CHECK();

@@ -62,6 +62,7 @@ struct HaloPlan {
     i64 send_words[LPIC_MAX_PEERS] = {0}, recv_words[LPIC_MAX_PEERS] = {0};          // fp64 words per grid attribute
     int *h_send_patch = nullptr, *h_send_b = nullptr, *h_recv_patch = nullptr, *h_recv_b = nullptr;
     int *d_send_patch = nullptr, *d_send_b = nullptr;
+    int *d_recv_patch = nullptr, *d_recv_b = nullptr;  // receive entries in plan order (comm.cu: counts arrive in this order)
     i64 *d_send_woff = nullptr;                        // word offset of each send entry inside its peer's buffer
     int *d_recv_peer = nullptr;                        // (npatch, nb): peer slot the boundary receives from, or -1
     i64 *d_recv_woff = nullptr;                        // (npatch, nb): word offset inside that peer's buffer
@@ -114,7 +115,24 @@ struct lpic_ctx {
     double *d_tmpf = nullptr;
     struct PmlState *pml = nullptr;   // null: no open boundaries
     struct HaloPlan *halo = nullptr;  // inter-rank exchange plan (halo.cu), null on a single rank
+    const i64 *comm_remote_in = nullptr;  // comm.cu: per-patch remote arrival counts of the exchange in flight
+    struct CommState *comm = nullptr;  // NCCL communicator, comm stream, staging buffers (comm.cu), null until lpic_comm_init
     cudaEvent_t *events = nullptr;  // lazily created, 4096 slots
+};
+
+// Every entry point runs on its context's device whatever device is current in the calling thread (a process may hold
+// contexts on several GPUs, and torch may have switched the current device between two calls).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(const lpic_ctx *c) {
+        if (c && cudaGetDevice(&prev) == cudaSuccess && prev != c->device) switched = cudaSetDevice(c->device) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
 };
 
 inline double *field_ptr(const lpic_ctx *c, int attr) { return c->fields + (size_t)attr * c->g.npatch * c->g.ncell; }

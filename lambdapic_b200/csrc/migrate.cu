@@ -11,6 +11,7 @@
 // npart_to_extend; [host grows the arrays: lpic_species_extend -- only then are the lists rebuilt]; (3) k_fill, one
 // thread per incoming particle copies every attribute; (4) k_mark kills the listed leavers (and NaNs the unfilled dead
 // slots in 3D) from the lists, without classifying again.
+#include <algorithm>
 #include <vector>
 #include "lpic_common.cuh"
 
@@ -25,6 +26,7 @@ struct MigArgs {
     double *x, *y, *z;
     u8 *dead;
     i64 *out, *ndead, *incoming, *extend, *alive;  // per patch (out: per patch x boundary)
+    const i64 *remote_in;                          // per patch: arrivals from other ranks take the first dead slots (null: none)
     int *la, *lb;                                  // arena-sized int lists
     int *dirstart;                                 // (npatch, nb)
     double *attrs[LPIC_NPATTR];
@@ -170,7 +172,8 @@ __global__ void __launch_bounds__(T) k_lists(MigArgs a) {
 __global__ void __launch_bounds__(T) k_fill(MigArgs a, int blocks_per_patch) {
     const int p = blockIdx.x / blocks_per_patch;
     const i64 k = (i64)(blockIdx.x - p * blocks_per_patch) * blockDim.x + threadIdx.x;
-    if (k >= a.incoming[p] || k >= a.ndead[p]) return;
+    const i64 skip = a.remote_in ? a.remote_in[p] : 0;  // dead slots already promised to arrivals from other ranks
+    if (k >= a.incoming[p] || k + skip >= a.ndead[p]) return;
     // which boundary does the k-th newcomer arrive through?  (fill_boundary_particles_to_buffer, :302-323)
     i64 run = 0;
     i64 q = -1;
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(T) k_fill(MigArgs a, int blocks_per_patch) {
     if (q < 0) return;
     const i64 src = a.off[q] + a.lb[a.off[q] + a.dirstart[(size_t)q * a.nb + ob] + r];
     const i64 np = a.npart[p];
-    const i64 dst = a.off[p] + a.la[a.off[p] + np - 1 - k];
+    const i64 dst = a.off[p] + a.la[a.off[p] + np - 1 - (k + skip)];
     const double *bx = a.box + 6 * (size_t)p;
     for (int t = 0; t < a.nattr; t++) {
         double v = a.attrs[t][src];
@@ -222,7 +225,8 @@ __global__ void __launch_bounds__(T) k_mark(MigArgs a) {
     }
     if (a.dim != 3) return;
     const int nd = (int)a.ndead[p];
-    const int filled = (int)(a.incoming[p] < nd ? a.incoming[p] : nd);
+    const i64 arrivals = a.incoming[p] + (a.remote_in ? a.remote_in[p] : 0);
+    const int filled = (int)(arrivals < nd ? arrivals : nd);
     for (int k = filled + threadIdx.x; k < nd; k += T) {
         const i64 ip = off + a.la[off + np - 1 - k];
         a.x[ip] = nan;
@@ -241,6 +245,7 @@ int make_args(lpic_ctx *c, int ispec, MigArgs &a) {
     a.x = sp.attr[LPIC_P_X]; a.y = sp.attr[LPIC_P_Y]; a.z = sp.attr[LPIC_P_Z]; a.dead = sp.dead;
     a.out = sp.d_out; a.ndead = sp.d_ndead; a.incoming = sp.d_incoming; a.extend = sp.d_extend; a.alive = sp.d_alive;
     a.la = c->scr_a; a.lb = c->scr_b;
+    a.remote_in = nullptr;
     a.dirstart = (int *)(c->d_tmp64 + 64);  // npatch*nb ints <= 4*npatch i64 words (26 ints = 13 words): checked below
     a.nattr = 0; a.ia_x = a.ia_y = a.ia_z = -1;
     for (int t = 0; t < LPIC_NPATTR; t++) {
@@ -311,12 +316,14 @@ __global__ void __launch_bounds__(T) k_remote_unpack(MigArgs a, const int *__res
 }  // namespace
 
 extern "C" int lpic_particle_record_words(lpic_ctx *c, int ispec) {
+    DeviceGuard dg(c);
     MigArgs a;
     if (make_args(c, ispec, a)) return -1;
     return a.nattr;
 }
 
 extern "C" int lpic_remote_migrate_prepare(lpic_ctx *c, int ispec, int64_t *send_counts, int64_t *ndead) {
+    DeviceGuard dg(c);
     HaloPlan *h = c->halo;
     REQUIRE(h, "no exchange plan");
     MigArgs a;
@@ -349,6 +356,7 @@ extern "C" int lpic_remote_migrate_prepare(lpic_ctx *c, int ispec, int64_t *send
 }
 
 extern "C" int lpic_remote_migrate_relist(lpic_ctx *c, int ispec) {
+    DeviceGuard dg(c);
     MigArgs a;
     if (int r = make_args(c, ispec, a)) return r;
     k_lists<<<(unsigned)c->g.npatch, T, 0, c->stream>>>(a);
@@ -358,6 +366,7 @@ extern "C" int lpic_remote_migrate_relist(lpic_ctx *c, int ispec) {
 }
 
 extern "C" int lpic_remote_migrate_pack(lpic_ctx *c, int ispec, int slot, double *dev_send, int64_t *nparticles) {
+    DeviceGuard dg(c);
     HaloPlan *h = c->halo;
     REQUIRE(h && slot >= 0 && slot < h->npeers, "no exchange plan / bad peer slot");
     MigArgs a;
@@ -377,6 +386,7 @@ extern "C" int lpic_remote_migrate_pack(lpic_ctx *c, int ispec, int slot, double
 }
 
 extern "C" int lpic_remote_migrate_unpack(lpic_ctx *c, int ispec, const int64_t *recv_counts, const double *const *dev_recv) {
+    DeviceGuard dg(c);
     HaloPlan *h = c->halo;
     REQUIRE(h, "no exchange plan");
     MigArgs a;
@@ -413,8 +423,79 @@ extern "C" int lpic_remote_migrate_unpack(lpic_ctx *c, int ispec, const int64_t 
     return 0;
 }
 
+// ---- pieces of the in-library NCCL path (comm.cu) -------------------------------------------------------------------------
+// classification pass + intra-rank plan; the lists stay valid until the arrays grow
+int lpic_mig_classify(lpic_ctx *c, int ispec, const i64 *) {
+    MigArgs a;
+    if (int r = make_args(c, ispec, a)) return r;
+    Species &sp = c->spec[ispec];
+    k_lists<<<(unsigned)c->g.npatch, T, 0, c->stream>>>(a);
+    k_plan<<<div_up(c->g.npatch, 128), 128, 0, c->stream>>>(a);
+    LAUNCHED(2);
+    KERNEL_CHECK();
+    sp.lists_valid = true;
+    sp.lists_epoch = c->scratch_epoch;
+    return 0;
+}
+
+int lpic_mig_pack(lpic_ctx *c, int ispec, int slot, i64 max_entry, double *dev_send) {
+    HaloPlan *h = c->halo;
+    MigArgs a;
+    const unsigned long long epoch = c->scratch_epoch;
+    if (int r = make_args(c, ispec, a)) return r;
+    REQUIRE(c->spec[ispec].lists_valid && c->spec[ispec].lists_epoch == epoch, "lpic_mig_pack: the leaver lists are stale");
+    c->spec[ispec].lists_epoch = c->scratch_epoch;
+    dim3 grid(div_up(std::max<i64>(max_entry, 1), T), (unsigned)(h->send_first[slot + 1] - h->send_first[slot]));
+    k_remote_pack<<<grid, T, 0, c->stream>>>(a, h->d_send_patch, h->d_send_b, h->d_mig_send_cnt, h->d_mig_send_poff,
+                                             h->send_first[slot], dev_send);
+    LAUNCHED(1);
+    KERNEL_CHECK();
+    return 0;
+}
+
+int lpic_mig_local_fill(lpic_ctx *c, int ispec, i64 max_local) {
+    MigArgs a;
+    const unsigned long long epoch = c->scratch_epoch;
+    if (int r = make_args(c, ispec, a)) return r;
+    REQUIRE(c->spec[ispec].lists_valid && c->spec[ispec].lists_epoch == epoch, "lpic_mig_local_fill: the lists are stale");
+    c->spec[ispec].lists_epoch = c->scratch_epoch;
+    a.remote_in = c->comm_remote_in;
+    const int bpf = (int)div_up(max_local, T);
+    if (bpf > 0) {
+        k_fill<<<(unsigned)((i64)bpf * c->g.npatch), T, 0, c->stream>>>(a, bpf);
+        LAUNCHED(1);
+        KERNEL_CHECK();
+    }
+    return 0;
+}
+
+int lpic_mig_unpack_mark(lpic_ctx *c, int ispec, const double *const *dev_recv, i64 max_remote, const i64 *d_remote_in) {
+    HaloPlan *h = c->halo;
+    MigArgs a;
+    const unsigned long long epoch = c->scratch_epoch;
+    if (int r = make_args(c, ispec, a)) return r;
+    Species &sp = c->spec[ispec];
+    REQUIRE(sp.lists_valid && sp.lists_epoch == epoch, "lpic_mig_unpack_mark: the lists are stale");
+    a.remote_in = d_remote_in;
+    if (max_remote > 0) {
+        PeerRecs bufs;
+        for (int s = 0; s < h->npeers; s++) bufs.p[s] = dev_recv[s];
+        const int bpp = (int)div_up(max_remote, T);
+        k_remote_unpack<<<(unsigned)((i64)bpp * c->g.npatch), T, 0, c->stream>>>(a, h->d_recv_peer, h->d_mig_recv_cnt, h->d_mig_recv_poff,
+                                                                               d_remote_in, bufs, bpp);
+        LAUNCHED(1);
+    }
+    k_mark<<<(unsigned)c->g.npatch, T, 0, c->stream>>>(a);
+    LAUNCHED(1);
+    KERNEL_CHECK();
+    sp.sort.valid = false;
+    sp.lists_valid = false;
+    return 0;
+}
+
 extern "C" int lpic_migrate_count(lpic_ctx *c, int ispec, int64_t *to_extend, int64_t *incoming, int64_t *outgoing,
                                   int64_t *alive) {
+    DeviceGuard dg(c);
     MigArgs a;
     if (int r = make_args(c, ispec, a)) return r;
     Species &sp = c->spec[ispec];
@@ -439,6 +520,7 @@ extern "C" int lpic_migrate_count(lpic_ctx *c, int ispec, int64_t *to_extend, in
 }
 
 extern "C" int lpic_migrate_fill(lpic_ctx *c, int ispec) {
+    DeviceGuard dg(c);
     MigArgs a;
     const unsigned long long epoch = c->scratch_epoch;
     if (int r = make_args(c, ispec, a)) return r;

@@ -199,6 +199,7 @@ int lpic_push_deposit_sorted(lpic_ctx *c, int ispec, double dt, double q, double
 int lpic_push_deposit_tiles(lpic_ctx *c, int ispec, double dt, double q, double m, bool write_part);
 
 extern "C" int lpic_push_deposit(lpic_ctx *c, int ispec, double dt, double q, double m, int flags) {
+    DeviceGuard dg(c);
     const bool write_part = (flags & LPIC_PUSH_WRITE_PART) != 0;
     REQUIRE(ispec >= 0 && ispec < c->nspec && c->spec[ispec].allocated, "species %d not allocated", ispec);
     if (write_part && !c->spec[ispec].with_part) {
@@ -216,14 +217,18 @@ extern "C" int lpic_push_deposit(lpic_ctx *c, int ispec, double dt, double q, do
     }
     return launch_particles<MODE_FUSED>(c, ispec, dt, q, m, write_part);
 }
-extern "C" int lpic_interpolate(lpic_ctx *c, int ispec) { return launch_particles<MODE_GATHER>(c, ispec, 0.0, 0.0, 1.0, false); }
+extern "C" int lpic_interpolate(lpic_ctx *c, int ispec) {
+    DeviceGuard dg(c); return launch_particles<MODE_GATHER>(c, ispec, 0.0, 0.0, 1.0, false); }
 extern "C" int lpic_push_momentum(lpic_ctx *c, int ispec, double dt, double q, double m) {
+    DeviceGuard dg(c);
     return launch_particles<MODE_BORIS>(c, ispec, dt, q, m, false);
 }
 extern "C" int lpic_push_position(lpic_ctx *c, int ispec, double dt) {
+    DeviceGuard dg(c);
     return launch_particles<MODE_POSITION>(c, ispec, dt, 0.0, 1.0, false);
 }
 extern "C" int lpic_deposit(lpic_ctx *c, int ispec, double dt, double q) {
+    DeviceGuard dg(c);
     return launch_particles<MODE_DEPOSIT>(c, ispec, dt, q, 1.0, false);
 }
 
@@ -244,11 +249,15 @@ static int reduce_species(lpic_ctx *c, int ispec, int which, double *outf, int n
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return 0;
 }
-extern "C" int lpic_weighted_drift(lpic_ctx *c, int ispec, double *out2) { return reduce_species(c, ispec, 0, out2, 2, nullptr); }
-extern "C" int lpic_kinetic_sum(lpic_ctx *c, int ispec, double *out) { return reduce_species(c, ispec, 1, out, 1, nullptr); }
-extern "C" int lpic_count_alive(lpic_ctx *c, int ispec, int64_t *out) { return reduce_species(c, ispec, 2, nullptr, 0, out); }
+extern "C" int lpic_weighted_drift(lpic_ctx *c, int ispec, double *out2) {
+    DeviceGuard dg(c); return reduce_species(c, ispec, 0, out2, 2, nullptr); }
+extern "C" int lpic_kinetic_sum(lpic_ctx *c, int ispec, double *out) {
+    DeviceGuard dg(c); return reduce_species(c, ispec, 1, out, 1, nullptr); }
+extern "C" int lpic_count_alive(lpic_ctx *c, int ispec, int64_t *out) {
+    DeviceGuard dg(c); return reduce_species(c, ispec, 2, nullptr, 0, out); }
 
 extern "C" int lpic_species_init_uniform(lpic_ctx *c, int ispec, int64_t ppc, double weight, double uth, uint64_t seed) {
+    DeviceGuard dg(c);
     REQUIRE(ispec >= 0 && ispec < c->nspec && c->spec[ispec].allocated, "species %d not allocated", ispec);
     Species &sp = c->spec[ispec];
     const Geom &g = c->g;

@@ -50,6 +50,12 @@ __device__ __forceinline__ int warp_incl_sum(int v) {
 __device__ __forceinline__ double half_push(double x, double cdt, double ig, double u) { return __fma_rn(__dmul_rn(cdt, ig), u, x); }
 __device__ __forceinline__ double grid_coord(double x, double x0, double inv_d) { return __dmul_rn(__dsub_rn(x, x0), inv_d); }
 __device__ __forceinline__ double nearest(double X) { return floor(__dadd_rn(X, 0.5)); }
+// n / d from the rounded reciprocal r = 1/d plus one correction step: the correctly rounded quotient (Markstein) at 3 FMA-pipe
+// operations instead of the ~25-instruction division sequence
+__device__ __forceinline__ double div_rn(double n, double d, double r) {
+    const double q = __dmul_rn(n, r);
+    return __fma_rn(__fma_rn(-q, d, n), r, q);
+}
 
 struct TilePermArgs {
     const double *x, *y, *z, *ux, *uy, *uz, *ig;
@@ -159,23 +165,42 @@ __device__ __forceinline__ void spline3(double d, double &a, double &b, double &
     c = 0.5 * (0.25 + d2 - d);
 }
 
-// 27-point weighted sum from the staged tile: immediate offsets, nesting z(y(x)) as interp_field_safe_3d
-// (unified_pusher_3d.c:79-106)
+// 27-point weighted sum from the staged tile.  The three z-neighbours of every (x, y) stencil row are fetched as one aligned
+// 16-byte pair plus a single: a broadcast-style LDS.128 costs 1.07 crossbar cycles per double against 1.52 for an LDS.64
+// (profiles/microbench/lds_bench.cu).  tp = address of the pair, ts = address of the single, (wp0, wp1, ws) the z-weights
+// in that order (see ZSplit).  Same 27 products as interp_field_safe_3d (unified_pusher_3d.c:79-106), summed z first.
 template <int SX, int SY>
-__device__ __forceinline__ double gather_tile(const double *__restrict__ t, double fx0, double fx1, double fx2, double fy0,
-                                              double fy1, double fy2, double fz0, double fz1, double fz2) {
-    double az[3];
+__device__ __forceinline__ double gather_tile(const double *__restrict__ tp, const double *__restrict__ ts, double fx0, double fx1,
+                                              double fx2, double fy0, double fy1, double fy2, double wp0, double wp1, double ws) {
+    double ax[3];
 #pragma unroll
-    for (int c = 0; c < 3; c++) {
+    for (int a = 0; a < 3; a++) {
         double ay[3];
 #pragma unroll
         for (int b = 0; b < 3; b++) {
-            const double *r = t + b * SY + c;
-            ay[b] = fx0 * r[0] + fx1 * r[SX] + fx2 * r[2 * SX];
+            const double2 v = *reinterpret_cast<const double2 *>(tp + a * SX + b * SY);
+            ay[b] = wp0 * v.x + wp1 * v.y + ws * ts[a * SX + b * SY];
         }
-        az[c] = fy0 * ay[0] + fy1 * ay[1] + fy2 * ay[2];
+        ax[a] = fy0 * ay[0] + fy1 * ay[1] + fy2 * ay[2];
     }
-    return fz0 * az[0] + fz1 * az[1] + fz2 * az[2];
+    return fx0 * ax[0] + fx1 * ax[1] + fx2 * ax[2];
+}
+
+// z-stencil starting at staged index bz (weights w0, w1, w2 for bz, bz+1, bz+2): even start -> pair (bz, bz+1) + single bz+2,
+// odd start -> single bz + pair (bz+1, bz+2).  The staged rows have an even length, so the parity is that of bz alone.
+struct ZSplit {
+    int pair, single;    // offsets relative to the row's first staged z index
+    double wp0, wp1, ws;
+};
+__device__ __forceinline__ ZSplit zsplit(int bz, double w0, double w1, double w2) {
+    ZSplit z;
+    const bool odd = bz & 1;
+    z.pair = bz + (odd ? 1 : 0);
+    z.single = bz + (odd ? 0 : 2);
+    z.wp0 = odd ? w1 : w0;
+    z.wp1 = odd ? w2 : w1;
+    z.ws = odd ? w0 : w2;
+    return z;
 }
 
 // What an owner lane needs to turn (cell inside the tile, x-plane) into the address of its stencil point
@@ -185,45 +210,60 @@ struct RowOwner {
     int NX, NY, NZ;
 };
 
+// fp64 reduction into global memory without a return value.  Spelled as PTX: inside a non-inlined function the compiler
+// no longer knows that the pointer is a global one and emits a generic ATOM with a shared-memory CAS fallback.
+__device__ __forceinline__ void red_add(double *p, double v) {
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "d"(v) : "memory");
+}
+
 // one RED for a finished cell (code = cell inside the tile; -1: nothing carried yet)
 template <int TY, int TZ>
 __device__ __forceinline__ void flush_cell(const RowOwner &o, int code, double sum) {
     if (code < 0) return;
     const int lz = code % TZ, ly = (code / TZ) % TY, lx = code / (TZ * TY);
     const int id = (wrapneg(o.ax + lx, o.NX) * o.NY + wrapneg(o.ay + ly, o.NY)) * o.NZ + wrapneg(o.az + lz, o.NZ);
-    atomicAdd(o.dst + id, sum);
+    red_add(o.dst + id, sum);
 }
 
 // Owner lane: add this iteration's 32 source lanes of one row to the running sum of the current cell; a set bit in
 // `heads` marks a source lane that starts a new cell: the finished cell is flushed and the sum restarts.  One copy of
-// this in the instruction stream serves the three x-planes.
+// this in the instruction stream serves the three x-planes.  Straight-line per group of four source lanes; a group
+// that contains a head splits its four values around it.
 template <int TY, int TZ>
 __device__ __noinline__ double row_sum(double acc, unsigned heads, const double *__restrict__ row, const int *__restrict__ codes,
                                        int cur, RowOwner o) {
-    if (heads == 0u) {
-        double t[8];
 #pragma unroll
-        for (int g4 = 0; g4 < 8; g4++) t[g4] = (row[4 * g4] + row[4 * g4 + 1]) + (row[4 * g4 + 2] + row[4 * g4 + 3]);
-        return acc + (((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7])));
+    for (int g4 = 0; g4 < 32; g4 += 4) {
+        const unsigned mm = (heads >> g4) & 0xFu;
+        const double v0 = row[g4], v1 = row[g4 + 1], v2 = row[g4 + 2], v3 = row[g4 + 3];
+        if (mm == 0u) {
+            acc += (v0 + v1) + (v2 + v3);
+        } else if ((mm & (mm - 1u)) == 0u) {  // one head, at position t: sources before it close the current cell
+            const int t = __ffs(mm) - 1;
+            const double lo = (t > 0 ? v0 : 0.0) + (t > 1 ? v1 : 0.0) + (t > 2 ? v2 : 0.0);
+            flush_cell<TY, TZ>(o, cur, acc + lo);
+            cur = codes[g4 + t];
+            acc = ((t > 0 ? 0.0 : v0) + (t > 1 ? 0.0 : v1)) + ((t > 2 ? 0.0 : v2) + v3);
+        } else {  // several cells start inside the group (fewer than 4 particles per cell): rolled, re-reads the row
+#pragma unroll 1
+            for (int t = 0; t < 4; t++) {
+                if ((mm >> t) & 1u) {
+                    flush_cell<TY, TZ>(o, cur, acc);
+                    acc = 0.0;
+                    cur = codes[g4 + t];
+                }
+                acc += row[g4 + t];
+            }
+        }
     }
-    int s = 0;
-    for (;;) {
-        const int e = heads ? __ffs(heads) - 1 : 32;
-        for (; s + 4 <= e; s += 4) acc += (row[s] + row[s + 1]) + (row[s + 2] + row[s + 3]);
-        for (; s < e; s++) acc += row[s];
-        if (e == 32) return acc;
-        heads &= heads - 1u;
-        flush_cell<TY, TZ>(o, cur, acc);
-        acc = 0.0;
-        cur = codes[e];
-    }
+    return acc;
 }
 
 template <int TX, int TY, int TZ, int NW, bool WRITE_PART>
 __global__ void __launch_bounds__(NW * 32, TILE_MIN_CTAS) k_push_tile(const TileArgs a) {
-    constexpr int EX = TX + 3, EY = TY + 3, EZ = TZ + 3, EN = EX * EY * EZ;
+    constexpr int EX = TX + 3, EY = TY + 3, EZ = TZ + 4, EN = EX * EY * EZ;  // EZ: TZ + 3 nodes, padded to an even row length
     constexpr int SX = EY * EZ, SY = EZ;  // strides (in doubles) of the staged tile
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     double *eb = smem;                                            // [6][EX][EY][EZ]
     double *red = smem + 6 * EN + (threadIdx.x >> 5) * (30 * 33);  // this warp's [30][33] reduction tile
     int *codes = (int *)(smem + 6 * EN + NW * 30 * 33) + (threadIdx.x >> 5) * 32;
@@ -238,7 +278,7 @@ __global__ void __launch_bounds__(NW * 32, TILE_MIN_CTAS) k_push_tile(const Tile
     double *Fp = a.F + (size_t)p * g.ncell;
     // ---- stage E/B of the tile and its halo: nodes [o-2, o+T] per axis, logical order --------------------------------
     for (int idx = threadIdx.x; idx < EN; idx += NW * 32) {
-        const int lz = idx % EZ, ly = (idx / EZ) % EY, lx = idx / (EZ * EY);
+        const int lz = idx % EZ, ly = (idx / EZ) % EY, lx = idx / (EZ * EY);  // (the pad column lz = TZ + 3 is loaded too: one more guard node)
         const int gx = ox - 2 + lx, gy = oy - 2 + ly, gz = oz - 2 + lz;
         if (gx < g.nx + g.ng && gy < g.ny + g.ng && gz < g.nz + g.ng) {  // (the low side is always inside: ng >= 2)
             const double *src = Fp + (wrapneg(gx, g.NX) * g.NY + wrapneg(gy, g.NY)) * g.NZ + wrapneg(gz, g.NZ);
@@ -287,15 +327,16 @@ __global__ void __launch_bounds__(NW * 32, TILE_MIN_CTAS) k_push_tile(const Tile
             // staged index of the first stencil node: node-centred (g) r-1 -> r-1-(o-2), cell-centred (h) f-1 -> f-1-(o-2)
             const int bgx = (cx - ox + 1) * SX, bhx = ((int)fX - ox + 1) * SX;
             const int bgy = (cy - oy + 1) * SY, bhy = ((int)fY - oy + 1) * SY;
-            const int bgz = cz - oz + 1, bhz = (int)fZ - oz + 1;
+            const ZSplit zg = zsplit(cz - oz + 1, gz0, gz1, gz2), zh = zsplit((int)fZ - oz + 1, hz0, hz1, hz2);
             // ex(h,g,g) ey(g,h,g) ez(g,g,h) bx(g,h,h) by(h,g,h) bz(h,h,g)  (unified_pusher_3d.c:190-195)
             double f[6];
-            f[0] = gather_tile<SX, SY>(eb + 0 * EN + bhx + bgy + bgz, hx0, hx1, hx2, gy0, gy1, gy2, gz0, gz1, gz2);
-            f[1] = gather_tile<SX, SY>(eb + 1 * EN + bgx + bhy + bgz, gx0, gx1, gx2, hy0, hy1, hy2, gz0, gz1, gz2);
-            f[2] = gather_tile<SX, SY>(eb + 2 * EN + bgx + bgy + bhz, gx0, gx1, gx2, gy0, gy1, gy2, hz0, hz1, hz2);
-            f[3] = gather_tile<SX, SY>(eb + 3 * EN + bgx + bhy + bhz, gx0, gx1, gx2, hy0, hy1, hy2, hz0, hz1, hz2);
-            f[4] = gather_tile<SX, SY>(eb + 4 * EN + bhx + bgy + bhz, hx0, hx1, hx2, gy0, gy1, gy2, hz0, hz1, hz2);
-            f[5] = gather_tile<SX, SY>(eb + 5 * EN + bhx + bhy + bgz, hx0, hx1, hx2, hy0, hy1, hy2, gz0, gz1, gz2);
+            const double *t;
+            t = eb + 0 * EN + bhx + bgy; f[0] = gather_tile<SX, SY>(t + zg.pair, t + zg.single, hx0, hx1, hx2, gy0, gy1, gy2, zg.wp0, zg.wp1, zg.ws);
+            t = eb + 1 * EN + bgx + bhy; f[1] = gather_tile<SX, SY>(t + zg.pair, t + zg.single, gx0, gx1, gx2, hy0, hy1, hy2, zg.wp0, zg.wp1, zg.ws);
+            t = eb + 2 * EN + bgx + bgy; f[2] = gather_tile<SX, SY>(t + zh.pair, t + zh.single, gx0, gx1, gx2, gy0, gy1, gy2, zh.wp0, zh.wp1, zh.ws);
+            t = eb + 3 * EN + bgx + bhy; f[3] = gather_tile<SX, SY>(t + zh.pair, t + zh.single, gx0, gx1, gx2, hy0, hy1, hy2, zh.wp0, zh.wp1, zh.ws);
+            t = eb + 4 * EN + bhx + bgy; f[4] = gather_tile<SX, SY>(t + zh.pair, t + zh.single, hx0, hx1, hx2, gy0, gy1, gy2, zh.wp0, zh.wp1, zh.ws);
+            t = eb + 5 * EN + bhx + bhy; f[5] = gather_tile<SX, SY>(t + zg.pair, t + zg.single, hx0, hx1, hx2, hy0, hy1, hy2, zg.wp0, zg.wp1, zg.ws);
             if (WRITE_PART) {
 #pragma unroll
                 for (int c = 0; c < 6; c++) a.s.part[c][ip] = f[c];
@@ -306,11 +347,12 @@ __global__ void __launch_bounds__(NW * 32, TILE_MIN_CTAS) k_push_tile(const Tile
             a.s.x[ip] = x; a.s.y[ip] = y; a.s.z[ip] = z;
         }
         // ---- deposit set-up (current_deposit.h:341-373): the path from x - v dt/2 to x + v dt/2 ------------------------
-        const double hvx = ux * ig * (LPIC_C_LIGHT * 0.5) * a.dt, hvy = uy * ig * (LPIC_C_LIGHT * 0.5) * a.dt,
-                     hvz = uz * ig * (LPIC_C_LIGHT * 0.5) * a.dt;
-        const double X0 = (x - hvx - x0) * a.inv_dx, X1 = (x + hvx - x0) * a.inv_dx;
-        const double Y0 = (y - hvy - y0) * a.inv_dy, Y1 = (y + hvy - y0) * a.inv_dy;
-        const double Z0 = (z - hvz - z0) * a.inv_dz, Z1 = (z + hvz - z0) * a.inv_dz;
+        // Same expressions as the reference (and k_particles): a slow particle's current is proportional to X1 - X0, the
+        // difference of two separately rounded coordinates, so the quotients have to round the way a division does.
+        const double vx = ux * LPIC_C_LIGHT * ig, vy = uy * LPIC_C_LIGHT * ig, vz = uz * LPIC_C_LIGHT * ig;
+        const double X0 = div_rn(x - vx * 0.5 * a.dt - x0, g.dx, a.inv_dx), X1 = div_rn(x + vx * 0.5 * a.dt - x0, g.dx, a.inv_dx);
+        const double Y0 = div_rn(y - vy * 0.5 * a.dt - y0, g.dy, a.inv_dy), Y1 = div_rn(y + vy * 0.5 * a.dt - y0, g.dy, a.inv_dy);
+        const double Z0 = div_rn(z - vz * 0.5 * a.dt - z0, g.dz, a.inv_dz), Z1 = div_rn(z + vz * 0.5 * a.dt - z0, g.dz, a.inv_dz);
         const double rX0 = floor(X0 + 0.5), rY0 = floor(Y0 + 0.5), rZ0 = floor(Z0 + 0.5);
         // fast: the nearest node does not change along the path AND it is the node the particle was keyed by (recomputing
         // the start from the end position can round to the other side of a cell boundary)
@@ -461,7 +503,7 @@ int launch_tiles(lpic_ctx *c, Species &sp, double dt, double q, double m, bool w
     pa.nx = g.nx; pa.ny = g.ny; pa.nz = g.nz; pa.nty = nty; pa.ntz = ntz; pa.ntile = ntile;
     pa.keys = (int *)c->scr_buf;  // the sort's staging buffer is idle during the push
     pa.perm = c->scr_b; pa.tile_start = c->d_tile_start; pa.list = c->scr_a; pa.nlist = d_nlist;
-    constexpr size_t push_smem = sizeof(double) * (6 * (TX + 3) * (TY + 3) * (TZ + 3) + NW * 30 * 33) + sizeof(int) * NW * 32;
+    constexpr size_t push_smem = sizeof(double) * (6 * (TX + 3) * (TY + 3) * (TZ + 4) + NW * 30 * 33) + sizeof(int) * NW * 32;
     if (!c->tile_attr_set) {  // per context: function attributes are per device, and a process may drive several
         CUDA_TRY(cudaFuncSetAttribute(k_tile_perm<TX, TY, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_PERM_SMEM_LIMIT));
         CUDA_TRY(cudaFuncSetAttribute(k_push_tile<TX, TY, TZ, NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)push_smem));

@@ -340,6 +340,7 @@ __global__ void k_widen(const int *__restrict__ src, i64 *__restrict__ dst, i64 
 extern "C" int lpic_sort(lpic_ctx *c, int ispec, int reverse_x, int64_t nxb, int64_t nyb, int64_t nzb, double dxb,
                          double dyb, double dzb, const double *x0s, const double *y0s, const double *z0s,
                          int64_t *nbuf_total) {
+    DeviceGuard dg(c);
     REQUIRE(ispec >= 0 && ispec < c->nspec && c->spec[ispec].allocated, "species %d not allocated", ispec);
     Species &sp = c->spec[ispec];
     const Geom &g = c->g;
@@ -420,6 +421,7 @@ extern "C" int lpic_sort(lpic_ctx *c, int ispec, int reverse_x, int64_t nxb, int
 }
 
 extern "C" int lpic_sort_download(lpic_ctx *c, int ispec, int which, int64_t *out) {
+    DeviceGuard dg(c);
     REQUIRE(ispec >= 0 && ispec < c->nspec && c->spec[ispec].allocated, "species %d not allocated", ispec);
     Species &sp = c->spec[ispec];
     SortState &st = sp.sort;

@@ -326,6 +326,11 @@ def _advance_psi(st, p, which, dt):
 def update_efield(st: OState, dt: float):
     L = lib()
     bfac, jfac = dt * C_LIGHT**2, dt / EPSILON_0
+    if st.dim == 3 and not any(p.pml for p in st.patches):  # all patches in one call, OpenMP over patches
+        ptrs = _pp([getattr(p.fields, n) for p in st.patches for n in FIELD_ATTRS[:9]])
+        L.orc_update_efield_3d_all(ptrs, _c_i64(len(st.patches)), _c_i64(st.nx), _c_i64(st.ny), _c_i64(st.nz), _c_i64(st.ng),
+                                   _c_dbl(st.dx), _c_dbl(st.dy), _c_dbl(st.dz), _c_dbl(bfac), _c_dbl(jfac))
+        return
     for p in st.patches:
         f = p.fields
         a = [_p(getattr(f, n)) for n in FIELD_ATTRS[:9]]
@@ -349,6 +354,11 @@ def update_efield(st: OState, dt: float):
 
 def update_bfield(st: OState, dt: float):
     L = lib()
+    if st.dim == 3 and not any(p.pml for p in st.patches):
+        ptrs = _pp([getattr(p.fields, n) for p in st.patches for n in FIELD_ATTRS[:6]])
+        L.orc_update_bfield_3d_all(ptrs, _c_i64(len(st.patches)), _c_i64(st.nx), _c_i64(st.ny), _c_i64(st.nz), _c_i64(st.ng),
+                                   _c_dbl(st.dx), _c_dbl(st.dy), _c_dbl(st.dz), _c_dbl(dt))
+        return
     for p in st.patches:
         f = p.fields
         a = [_p(getattr(f, n)) for n in FIELD_ATTRS[:6]]

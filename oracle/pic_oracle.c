@@ -90,6 +90,25 @@ void orc_update_bfield_3d(const double *ex, const double *ey, const double *ez, 
             }
 }
 
+/* All patches of a rank in one call, OpenMP over patches as the reference's numba kernels run them
+ * (update_efield_patches_3d / update_bfield_patches_3d, core/maxwell/cpu.py:37-158: prange over patches).
+ * f = npatch x 9 (E) or npatch x 6 (B) array pointers in FIELD_ATTRS order; same per-patch arithmetic as above. */
+void orc_update_efield_3d_all(double **f, i64 npatch, i64 nx, i64 ny, i64 nz, i64 ng, double dx, double dy, double dz,
+                              double bfactor, double jfactor) {
+#pragma omp parallel for schedule(static)
+    for (i64 p = 0; p < npatch; p++) {
+        double **a = f + 9 * p;
+        orc_update_efield_3d(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], nx, ny, nz, ng, dx, dy, dz, bfactor, jfactor);
+    }
+}
+void orc_update_bfield_3d_all(double **f, i64 npatch, i64 nx, i64 ny, i64 nz, i64 ng, double dx, double dy, double dz, double dt) {
+#pragma omp parallel for schedule(static)
+    for (i64 p = 0; p < npatch; p++) {
+        double **a = f + 6 * p;
+        orc_update_bfield_3d(a[0], a[1], a[2], a[3], a[4], a[5], nx, ny, nz, ng, dx, dy, dz, dt);
+    }
+}
+
 #define IX2(i, j) (wrapneg(j, NY) + wrapneg(i, NX) * NY)
 
 void orc_update_efield_2d(double *ex, double *ey, double *ez, const double *bx, const double *by, const double *bz,
