@@ -346,6 +346,27 @@ def main():
             _lib.check(L.lpic_event_elapsed_ms(eng.ctx, 2 + 4 * k + 2 * s, 3 + 4 * k + 2 * s, _lib.C.byref(e)))
             push_ms.append(e.value)
     alive1 = sum(eng.count_alive(s) for s in range(eng.nspec))
+    if args.breakdown and world > 1 and not eng.halo.host_driven:  # per-phase CUDA-event times of one extra step, every rank
+        names, slot = [], [3000]
+
+        def mark(name):
+            eng.record_event(slot[0])
+            names.append(name)
+            slot[0] += 1
+        mark("begin")
+        eng.halo.step(dt, q, m, rev, marks=mark)
+        eng.sync()
+        tms = []
+        for i in range(1, len(names)):
+            e = _lib.C.c_double(0)
+            _lib.check(L.lpic_event_elapsed_ms(eng.ctx, 3000 + i - 1, 3000 + i, _lib.C.byref(e)))
+            tms.append(e.value)
+        tt = torch.tensor(tms, dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            for name, t in zip(names[1:], tt.tolist()):
+                print(f"  {name:44s} {t:9.3f} ms (max over ranks)", file=sys.stderr)
+            print(f"  {'TOTAL':44s} {sum(tt.tolist()):9.3f} ms", file=sys.stderr)
     if args.breakdown and world == 1:
         bd = eng.step_profiled(dt, q, m, rev)
         tot = sum(t for _, t in bd)

@@ -293,6 +293,7 @@ extern "C" int lpic_migrate_remote_start(lpic_ctx *c, int ispec, int resume, int
     PeerRanges rg;
     for (int s = 0; s <= h->npeers; s++) { rg.send_first[s] = h->send_first[s]; rg.recv_first[s] = h->recv_first[s]; }
     const unsigned pgrid = div_up(std::max(h->npeers, 1), 32);
+    const int nw = lpic_particle_record_words(c, ispec);  // (before the classification: it touches the shared scratch epoch)
     if (!resume) {
         CUDA_TRY(cudaMemsetAsync(m->d_remote_in, 0, sizeof(i64) * n, c->stream));
         if (int r = lpic_mig_classify(c, ispec, nullptr)) return r;  // lists + out + ndead + local incoming (k_plan)
@@ -337,7 +338,6 @@ extern "C" int lpic_migrate_remote_start(lpic_ctx *c, int ispec, int resume, int
     }
     i64 sent = 0, recvd = 0, max_remote = 0, max_local = 0;
     for (i64 p = 0; p < n; p++) { max_remote = std::max(max_remote, m->h_patch[p]); max_local = std::max(max_local, m->h_patch[n + p]); }
-    const int nw = lpic_particle_record_words(c, ispec);
     for (int s = 0; s < h->npeers; s++) {
         const i64 ns = m->h_peer_tot[s], nr = m->h_peer_tot[LPIC_MAX_PEERS + s];
         sent += ns; recvd += nr;

@@ -316,8 +316,12 @@ class DeviceBridge:
     def sync_particles(self):
         total = np.zeros(self.patches.npatches, dtype=np.int64)
         with self.coherent():
+            xch = getattr(self.engine, "comm_exchange", None)
             for s in range(self.engine.nspec):
-                rec = self.engine.sync_particles(s)
+                if xch is not None and s in xch.migrated:  # sim.mpi.sync_particles_start already did the whole migration
+                    rec = {"to_extend": xch.migrated.pop(s)}
+                else:
+                    rec = self.engine.sync_particles(s)
                 total += rec["to_extend"]
                 for ip in np.nonzero(rec["to_extend"] > 0)[0]:  # no per-patch Python loop on the (usual) quiet steps
                     pt = self.patches[int(ip)].particles[s]

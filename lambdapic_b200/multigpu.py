@@ -7,6 +7,16 @@ Replaces core/mpi/mpi_manager.py + core/mpi/sync_{fields,particles}_{2d,3d}.c of
 step is the reference's (simulation/simulation.py:937-1130): E guards, B guards, [particles pushed], local current
 reduce then remote current reduce, remote migration then local migration, B guards, E guards.
 
+Two transports share the exchange plan and the pack / unpack kernels:
+
+* :class:`NcclExchange` -- the production path.  NCCL lives INSIDE the library (csrc/comm.cu: ``lpic_comm_init``,
+  ``lpic_halo_start/wait``, ``lpic_migrate_remote_start/wait``): a dedicated comm stream, CUDA events instead of host
+  synchronisation, persistent staging buffers, counts exchanged device to device.  ``*_start`` returns at once and the
+  intra-rank guard copy / current reduce / particle fill run between start and wait (simulation/simulation.py:948-952).
+* :class:`RankProgram` -- the same step as a generator whose yields are the exchange phases, driven either in-process
+  (all emulated ranks on ONE GPU, used by the single-GPU tests: no kernel ever waits on another rank) or by
+  ``torch.distributed`` send/recv (``LPIC_HOST_EXCHANGE=1``).
+
 The per-rank step is written once as a generator (:class:`RankProgram`) that yields its outgoing buffers and is
 resumed with the incoming ones, so the same code runs under the NCCL driver (one rank per process) and under the
 in-process driver used by the single-GPU tests (all ranks' programs advanced in lockstep, buffers handed over by
@@ -51,6 +61,101 @@ def build_plan(grid):
     return peers, s, v
 
 
+def register_plan(eng, grid):
+    """Build the exchange plan and hand it to the library (lpic_halo_plan); returns (peers, send, recv, nsend, nrecv)."""
+    peers, send, recv = build_plan(grid)
+    i64 = lambda a: np.ascontiguousarray(a, dtype=np.int64)  # noqa: E731
+    nsend = i64([len(send[r]) for r in peers])
+    nrecv = i64([len(recv[r]) for r in peers])
+    sp = i64([e[0] for r in peers for e in send[r]])
+    sb = i64([e[1] for r in peers for e in send[r]])
+    rp = i64([e[0] for r in peers for e in recv[r]])
+    rb = i64([e[1] for r in peers for e in recv[r]])
+    P = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
+    check(eng.L.lpic_halo_plan(eng.ctx, len(peers), P(nsend), P(sp), P(sb), P(nrecv), P(rp), P(rb)))
+    return peers, send, recv, nsend, nrecv
+
+
+class NcclExchange:
+    """Inter-rank exchange through the library's own NCCL transport (csrc/comm.cu).  `bcast(obj, root)` carries the NCCL
+    unique id from rank 0 to the other ranks (torch.distributed / sim.mpi.comm); nothing else goes through the host."""
+
+    def __init__(self, eng, grid, bcast):
+        self.eng, self.grid, self.L = eng, grid, eng.L
+        self.peers, self.send_entries, self.recv_entries, self.nsend, self.nrecv = register_plan(eng, grid)
+        buf = C.create_string_buffer(128)
+        if grid.rank == 0:
+            check(self.L.lpic_comm_unique_id(buf))
+        ident = bcast(bytes(buf.raw), 0)
+        peer_rank = np.ascontiguousarray(self.peers if self.peers else [0], dtype=np.int64)
+        check(self.L.lpic_comm_init(eng.ctx, C.create_string_buffer(ident, 128), int(grid.rank), int(grid.nranks),
+                                    C.c_void_p(peer_rank.ctypes.data)))
+        self.migrated = {}  # species -> per-patch extension of the migration this object has already completed
+
+    @property
+    def bytes_sent(self):
+        return int(self.L.lpic_comm_bytes_sent(self.eng.ctx))
+
+    # ---- fields ------------------------------------------------------------------------------------------------------
+    def halo_start(self, mask, reduce):
+        check(self.L.lpic_halo_start(self.eng.ctx, int(mask), int(reduce)))
+
+    def halo_wait(self):
+        check(self.L.lpic_halo_wait(self.eng.ctx))
+
+    def sync_guard_fields(self, mask):
+        self.halo_start(mask, 0)
+        self.eng.sync_guard_fields(mask)   # intra-rank neighbours while the messages are on the wire
+        self.halo_wait()
+
+    def sync_currents(self):
+        self.halo_start(J_MASK, 1)         # packs (and zeroes) the guards facing other ranks ...
+        self.eng.sync_currents()           # ... the intra-rank reduce touches the others
+        self.halo_wait()                   # remote contributions are added after the local ones, as the reference does
+
+    # ---- particles ---------------------------------------------------------------------------------------------------
+    def sync_particles(self, ispec):
+        """Whole migration of one species: other ranks and intra-rank (core/mpi/sync_particles_3d.c + core/patch/patch.py:705-764)."""
+        eng = self.eng
+        ext = np.zeros(eng.npatch, dtype=np.int64)
+        info = np.zeros(4, dtype=np.int64)
+        r = self.L.lpic_migrate_remote_start(eng.ctx, ispec, 0, C.c_void_p(ext.ctypes.data), C.c_void_p(info.ctypes.data))
+        moved = False
+        if r == 1:  # some patch has to grow first
+            moved = eng.extend(ispec, ext)
+            r = self.L.lpic_migrate_remote_start(eng.ctx, ispec, 1, None, C.c_void_p(info.ctypes.data))
+        check(r)
+        check(self.L.lpic_migrate_remote_wait(eng.ctx, ispec))
+        return dict(sent=int(info[0]), received=int(info[1]), to_extend=ext, extended=bool(ext.any()), moved=moved)
+
+    # ---- one full step (same operator order as DeviceEngine.step) ------------------------------------------------------
+    def step(self, dt, q, m, reverse_x, write_part=False, event_slot=None, marks=None):
+        eng = self.eng
+        mark = marks if marks is not None else (lambda name: None)
+        eng.update_efield(0.5 * dt); mark("update E")
+        self.sync_guard_fields(E_MASK); mark("sync E (local + NCCL)")
+        eng.update_bfield(0.5 * dt); mark("update B")
+        self.sync_guard_fields(B_MASK); mark("sync B (local + NCCL)")
+        nbuf = [eng.sort(s, reverse_x[s]) for s in range(eng.nspec)]; mark("sort")
+        eng.reset_currents()
+        for s in range(eng.nspec):
+            if event_slot is not None:
+                eng.record_event(event_slot + 2 * s)
+            eng.push_deposit(s, dt, q[s], m[s], write_part)
+            if event_slot is not None:
+                eng.record_event(event_slot + 2 * s + 1)
+        mark("push + deposit")
+        self.halo_start(J_MASK, 1)
+        eng.sync_currents(); mark("current reduce (local, NCCL in flight)")
+        mig = [self.sync_particles(s) for s in range(eng.nspec)]; mark("migration (local + NCCL)")
+        self.halo_wait(); mark("current reduce (remote part)")
+        eng.update_bfield(0.5 * dt); mark("update B")
+        self.sync_guard_fields(B_MASK); mark("sync B (local + NCCL)")
+        eng.update_efield(0.5 * dt); mark("update E")
+        self.sync_guard_fields(E_MASK); mark("sync E (local + NCCL)")
+        return nbuf, mig
+
+
 class RankProgram:
     """The inter-rank part of one rank's PIC step.  `alloc(nwords)` returns a device fp64 buffer object exposing
     `.data_ptr()` (a torch CUDA tensor)."""
@@ -58,17 +163,8 @@ class RankProgram:
     def __init__(self, eng, grid, alloc):
         self.eng, self.grid, self.alloc = eng, grid, alloc
         self.L = eng.L
-        self.peers, send, recv = build_plan(grid)
+        self.peers, send, recv, nsend, nrecv = register_plan(eng, grid)
         self.send_entries, self.recv_entries = send, recv
-        i64 = lambda a: np.ascontiguousarray(a, dtype=np.int64)  # noqa: E731
-        nsend = i64([len(send[r]) for r in self.peers])
-        nrecv = i64([len(recv[r]) for r in self.peers])
-        sp = i64([e[0] for r in self.peers for e in send[r]])
-        sb = i64([e[1] for r in self.peers for e in send[r]])
-        rp = i64([e[0] for r in self.peers for e in recv[r]])
-        rb = i64([e[1] for r in self.peers for e in recv[r]])
-        P = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
-        check(self.L.lpic_halo_plan(eng.ctx, len(self.peers), P(nsend), P(sp), P(sb), P(nrecv), P(rp), P(rb)))
         self.nsend, self.nrecv = nsend, nrecv
         self.send_words = [int(self.L.lpic_halo_words(eng.ctx, i, 0)) for i in range(len(self.peers))]
         self.recv_words = [int(self.L.lpic_halo_words(eng.ctx, i, 1)) for i in range(len(self.peers))]
@@ -264,68 +360,89 @@ def drive_in_process(gens):
     return results
 
 
+def _torch_bcast(obj, root):
+    import torch.distributed as dist
+    box = [obj]
+    dist.broadcast_object_list(box, src=root)
+    return box[0]
+
+
 class HaloExchanger:
-    """bench.py / Simulation glue for the NCCL case: owns the RankProgram of this process."""
+    """bench.py glue: owns this process's exchange object.  Default: the library's NCCL transport (:class:`NcclExchange`);
+    ``LPIC_HOST_EXCHANGE=1``: the host-driven torch.distributed path (:class:`RankProgram` + :func:`drive_nccl`)."""
 
     def __init__(self, eng, grid):
+        import os
         import torch
         self.rank = grid.rank
-        self.prog = RankProgram(eng, grid, torch_alloc(torch.device("cuda", torch.cuda.current_device())))
+        self.host_driven = bool(os.environ.get("LPIC_HOST_EXCHANGE"))
+        if self.host_driven:
+            self.prog = RankProgram(eng, grid, torch_alloc(torch.device("cuda", torch.cuda.current_device())))
+        else:
+            self.prog = NcclExchange(eng, grid, _torch_bcast)
 
-    def step(self, dt, q, m, reverse_x, event_slot=None):
-        return drive_nccl(self.prog.step(dt, q, m, reverse_x, event_slot=event_slot), self.rank)
+    def step(self, dt, q, m, reverse_x, event_slot=None, marks=None):
+        if self.host_driven:
+            return drive_nccl(self.prog.step(dt, q, m, reverse_x, event_slot=event_slot), self.rank)
+        return self.prog.step(dt, q, m, reverse_x, event_slot=event_slot, marks=marks)
 
 
 class MultiRankMPI:
-    """``sim.mpi`` for several ranks (core/mpi/mpi_manager.py:9-298): same method names; each ``*_start`` performs the
-    packed exchange and returns a completed handle, ``*_wait`` is then a no-op."""
+    """``sim.mpi`` for several ranks (core/mpi/mpi_manager.py:9-298): same method names.  Field exchanges are truly
+    asynchronous: ``*_start`` packs and posts the NCCL sends / receives on the library's comm stream and returns, the caller
+    runs the intra-rank copy / reduce, ``*_wait`` makes the compute stream wait and unpacks.  ``sync_particles_start``
+    performs the species' whole migration (other ranks AND intra-rank: the two share one classification pass and one list
+    of dead slots), so the ``Patches.sync_particles`` that follows finds that species already done."""
 
     def __init__(self, sim, comm):
-        import torch
         self.sim, self.comm = sim, comm
         self.rank, self.size = comm.Get_rank(), comm.Get_size()
-        self._alloc = torch_alloc(torch.device("cuda", sim.device))
-        self._prog = None
+        self._xch = None
 
     @property
-    def prog(self):
+    def xch(self):
         eng = self.sim.bridge.engine
-        if self._prog is None or self._prog.eng is not eng:
-            self._prog = RankProgram(eng, self.sim.grid, self._alloc)
-        return self._prog
+        if self._xch is None or self._xch.eng is not eng:
+            self._xch = NcclExchange(eng, self.sim.grid, lambda obj, root: self.comm.bcast(obj, root=root))
+            eng.comm_exchange = self._xch
+        return self._xch
 
-    def _run(self, gen):
-        return drive_nccl(gen, self.rank)
-
-    def sync_guard_fields_start(self, attrs):
+    @staticmethod
+    def _mask(attrs):
         from ._lib import FIELD_ATTRS
         mask = 0
         for a in attrs:
             mask |= 1 << FIELD_ATTRS.index(a)
+        return mask
+
+    def sync_guard_fields_start(self, attrs):
         with self.sim.bridge.coherent():
-            self._run(self.prog.exchange_fields(mask, 0))
-        return "done"
+            self.xch.halo_start(self._mask(attrs), 0)
+        return "guards"
 
     def sync_guard_fields_wait(self, handle):
-        pass
+        with self.sim.bridge.coherent():
+            self.xch.halo_wait()
 
     def sync_guard_fields(self, attrs):
-        self.sync_guard_fields_start(attrs)
+        self.sync_guard_fields_wait(self.sync_guard_fields_start(attrs))
 
     def sync_currents_start(self):
         with self.sim.bridge.coherent():
-            self._run(self.prog.exchange_fields(J_MASK, 1))
-        return "done"
+            self.xch.halo_start(J_MASK, 1)
+        return "currents"
 
     def sync_currents_wait(self, handle):
-        pass
+        with self.sim.bridge.coherent():
+            self.xch.halo_wait()
 
     def sync_currents(self):
-        self.sync_currents_start()
+        self.sync_currents_wait(self.sync_currents_start())
 
     def sync_particles_start(self, ispec):
         with self.sim.bridge.coherent():
-            self._run(self.prog.migrate_remote(ispec))
+            rec = self.xch.sync_particles(ispec)
+            self.xch.migrated[ispec] = rec["to_extend"]
         return "done"
 
     def sync_particles_wait(self, handle):

@@ -25,20 +25,31 @@ def main():
         k["device"] = local
         _orig(self, *a, **k)
     E.DeviceEngine.__init__ = _init
-    engines, grids, meta = h.split_engines_from_golden(g, "t0", world)
-    # keep only this rank's engine (the helper builds all of them; the others are closed at once)
-    for r, e in enumerate(engines):
-        if r != rank:
-            e.close()
-    eng, pg = engines[rank], grids[rank]
-    prog = RankProgram(eng, pg, torch_alloc(torch.device("cuda", local)))
-    rev = [bool(int(g[f"t1/reverse_x/{s}"])) for s in range(eng.nspec)]
-    for k in range(3):
-        drive_nccl(prog.step(meta["dt"], meta["q"], meta["m"], rev), rank)
-        worst = h.compare_split_state_with_golden([eng], [pg], g, f"t{k + 1}", rtol=1e-11)
-    dist.barrier()
-    print(f"nccl-parity ok rank {rank}/{world} worst {worst:.2e} bytes_sent {prog.bytes_sent}", flush=True)
-    eng.close()
+    from lambdapic_b200.multigpu import NcclExchange, _torch_bcast
+    rev = None
+    # both transports: the library's own NCCL path (csrc/comm.cu, asynchronous start/wait) and the host-driven one
+    for mode in ("library", "host"):
+        engines, grids, meta = h.split_engines_from_golden(g, "t0", world)
+        # keep only this rank's engine (the helper builds all of them; the others are closed at once)
+        for r, e in enumerate(engines):
+            if r != rank:
+                e.close()
+        eng, pg = engines[rank], grids[rank]
+        rev = [bool(int(g[f"t1/reverse_x/{s}"])) for s in range(eng.nspec)]
+        if mode == "library":
+            prog = NcclExchange(eng, pg, _torch_bcast)
+        else:
+            prog = RankProgram(eng, pg, torch_alloc(torch.device("cuda", local)))
+        for k in range(3):
+            if mode == "library":
+                prog.step(meta["dt"], meta["q"], meta["m"], rev)
+            else:
+                drive_nccl(prog.step(meta["dt"], meta["q"], meta["m"], rev), rank)
+            worst = h.compare_split_state_with_golden([eng], [pg], g, f"t{k + 1}", rtol=1e-11)
+        dist.barrier()
+        print(f"nccl-parity-{mode} ok rank {rank}/{world} worst {worst:.2e} bytes_sent {prog.bytes_sent}", flush=True)
+        eng.close()
+    print(f"nccl-parity ok rank {rank}/{world}", flush=True)
     dist.destroy_process_group()
 
 
