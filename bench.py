@@ -467,12 +467,10 @@ def e2e_public_api(args, wl, rank=0, world=1):
                           device=int(os.environ.get("LOCAL_RANK", "0")))
     sim.add_species([lp.Electron(density=wl.density, ppc=wl.ppc[0]), lp.Proton(density=wl.density, ppc=wl.ppc[1])])
     sim.initialize()
-    rng = np.random.default_rng(wl.seed + 1)
-    for p in sim.patches:  # thermal momenta on the host mirrors (what SetTemperature does at stage `init`)
-        for isp, part in enumerate(p.particles):
-            for a in ("ux", "uy", "uz"):
-                getattr(part, a)[:] = rng.normal(0.0, wl.uth[isp], part.npart)
-            part.inv_gamma[:] = 1.0 / np.sqrt(1 + part.ux**2 + part.uy**2 + part.uz**2)
+    # thermal momenta on the host mirrors: the reference's own stage-`init` callback (callback/utils.py:922-1049, ported in
+    # lambdapic_b200.utils; same sampler, same draw order), applied here so that its host-side sampling stays outside the timed run()
+    for sp in sim.species:
+        lp.SetTemperature(sp, wl.temperature_eV)(sim)
     t_setup = time.perf_counter() - t_setup
     hist = []
 

@@ -187,6 +187,10 @@ int lpic_remote_migrate_unpack(lpic_ctx *ctx, int ispec, const int64_t *recv_cou
 int lpic_event_record(lpic_ctx *ctx, int slot);                              /* slot in [0, 4096) */
 int lpic_event_elapsed_ms(lpic_ctx *ctx, int slot_a, int slot_b, double *ms); /* synchronises on slot_b */
 int64_t lpic_launch_count(void);
+/* One interior z-plane per patch of the attributes in attr_mask (3D): kz[p] = plane index inside patch p (0 <= kz < nz) or -1
+ * if the patch does not contain the plane.  host = [nattr][npatch][nx][ny] fp64.  Replaces the whole-patch copies behind
+ * callback/utils.py:125-230 (get_fields_3d) and callback/hdf5.py:451-481 (SaveFieldsToHDF5(slice=...)). */
+int lpic_download_field_slice(lpic_ctx *ctx, uint32_t attr_mask, const int64_t *kz, double *host);
 /* ---- inter-rank transport inside the library (comm.cu): NCCL point-to-point on its own stream, ordered against the compute
  * stream with events.  Replaces core/mpi/mpi_manager.py:9-298 and the start/wait pairs of core/mpi/sync_fields{2,3}d.c
  * (:713-866 currents, :883-996 guards) and core/mpi/sync_particles_{2,3}d.c:413-745.  Call order: lpic_halo_plan ->
@@ -206,6 +210,8 @@ int lpic_halo_wait(lpic_ctx *ctx);
  * The call pair performs the WHOLE migration of the species (other ranks and intra-rank). */
 int lpic_migrate_remote_start(lpic_ctx *ctx, int ispec, int resume, int64_t *to_extend, int64_t *info);
 int lpic_migrate_remote_wait(lpic_ctx *ctx, int ispec);
+/* PCI bus id of the context's device, e.g. "0000:1b:00.0" (NUMA placement of the pinned host mirrors) */
+int lpic_device_pci_bus_id(lpic_ctx *ctx, char *out, int len);
 /* measured fp64 FMA throughput of the context's device in TFLOP/s (bench.py's roofline.fp64 co-bound; no reference counterpart) */
 int lpic_fp64_peak(lpic_ctx *ctx, double *tflops);
 

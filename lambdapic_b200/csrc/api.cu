@@ -15,6 +15,10 @@ void lpic_set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+struct AttrIds {
+    int a[LPIC_NFIELD];
+};
+
 extern "C" const char *lpic_last_error(void) { return g_err; }
 extern "C" const char *lpic_version(void) { return "lpic_b200 0.1 sm_100a"; }
 
@@ -126,7 +130,7 @@ extern "C" void lpic_destroy(lpic_ctx *c) {
     lpic_free_peers(c);
     lpic_free_pml(c);
     cudaFree(c->fields); cudaFree(c->d_x0); cudaFree(c->d_y0); cudaFree(c->d_z0); cudaFree(c->d_nbr); cudaFree(c->d_box);
-    cudaFree(c->scr_a); cudaFree(c->scr_b); cudaFree(c->scr_buf); cudaFree(c->d_sort_org); cudaFree(c->d_tmp64); cudaFree(c->d_tmpf); cudaFree(c->d_tile_start);
+    cudaFree(c->scr_a); cudaFree(c->scr_b); cudaFree(c->scr_buf); cudaFree(c->d_sort_org); cudaFree(c->d_tmp64); cudaFree(c->d_tmpf); cudaFree(c->d_tile_start); cudaFree(c->d_slice); cudaFree(c->d_slice_k);
     delete[] c->h_x0; delete[] c->h_y0; delete[] c->h_z0; delete[] c->h_nbr; delete[] c->h_patch_index;
     if (c->events) {
         for (int i = 0; i < 4096; i++)
@@ -205,6 +209,52 @@ extern "C" int lpic_download_field_ptrs(lpic_ctx *c, int attr, double *const *pt
     for (int p = 0; p < c->g.npatch; p++)
         CUDA_TRY(cudaMemcpyAsync(ptrs[p], field_ptr(c, attr) + (size_t)p * c->g.ncell, sizeof(double) * c->g.ncell,
                                  cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- sliced download: one z-plane of the interior per patch (callback/utils.py:125-230 get_fields_3d slices on the host
+// after every rank has copied whole patches; here only the plane crosses PCIe) -------------------------------------------
+__global__ void __launch_bounds__(256) k_gather_zplane(Geom g, const double *__restrict__ F, const int *__restrict__ kz, int nattr,
+                                                       AttrIds attrs, double *__restrict__ out) {
+    const int plane = g.nx * g.ny;
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (i64)g.npatch * plane) return;
+    const int p = (int)(t / plane), r = (int)(t - (i64)p * plane);
+    const int i = r / g.ny, j = r - i * g.ny, k = kz[p];
+    if (k < 0) return;  // this patch does not contain the plane
+    const size_t cell = (size_t)p * g.ncell + (size_t)(i * g.NY + j) * g.NZ + k;
+    for (int a = 0; a < nattr; a++)
+        out[((size_t)a * g.npatch + p) * plane + r] = F[(size_t)attrs.a[a] * g.npatch * g.ncell + cell];
+}
+extern "C" int lpic_download_field_slice(lpic_ctx *c, uint32_t mask, const int64_t *kz, double *host) {
+    DeviceGuard dg(c);
+    const Geom &g = c->g;
+    REQUIRE(g.dim == 3, "lpic_download_field_slice is for 3D grids (2D fields are their own slice)");
+    AttrIds attrs;
+    int na = 0;
+    for (int a = 0; a < LPIC_NFIELD; a++)
+        if (mask & (1u << a)) attrs.a[na++] = a;
+    if (!na) return 0;
+    const size_t plane = (size_t)g.nx * g.ny, words = (size_t)na * g.npatch * plane;
+    if (words > c->slice_cap) {
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_slice); cudaFree(c->d_slice_k);
+        c->d_slice = nullptr; c->d_slice_k = nullptr; c->slice_cap = 0;
+        CUDA_TRY(cudaMalloc(&c->d_slice, sizeof(double) * (size_t)LPIC_NFIELD * g.npatch * plane));
+        CUDA_TRY(cudaMalloc(&c->d_slice_k, sizeof(int) * g.npatch));
+        c->slice_cap = (size_t)LPIC_NFIELD * g.npatch * plane;
+    }
+    std::vector<int> hk(g.npatch);
+    for (int p = 0; p < g.npatch; p++) {
+        REQUIRE(kz[p] < g.nz, "slice index %lld outside patch %d", (long long)kz[p], p);
+        hk[p] = kz[p] < 0 ? -1 : (int)kz[p];
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->d_slice_k, hk.data(), sizeof(int) * g.npatch, cudaMemcpyHostToDevice, c->stream));
+    k_gather_zplane<<<div_up((i64)g.npatch * plane, 256), 256, 0, c->stream>>>(g, c->fields, c->d_slice_k, na, attrs, c->d_slice);
+    LAUNCHED(1);
+    KERNEL_CHECK();
+    CUDA_TRY(cudaMemcpyAsync(host, c->d_slice, sizeof(double) * words, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -541,6 +591,12 @@ extern "C" int lpic_fp64_peak(lpic_ctx *c, double *tflops) {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     *tflops = best;
+    return 0;
+}
+
+// PCI bus id of the context's device ("0000:1b:00.0"): lets the host side place its pinned mirrors on the GPU's NUMA node
+extern "C" int lpic_device_pci_bus_id(lpic_ctx *c, char *out, int len) {
+    CUDA_TRY(cudaDeviceGetPCIBusId(out, len, c->device));
     return 0;
 }
 

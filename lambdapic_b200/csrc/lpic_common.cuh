@@ -109,6 +109,9 @@ struct lpic_ctx {
     bool tile_attr_set = false;              // same for the tile kernels (push_tile.cu)
     int *d_tile_start = nullptr;             // (npatch, ntile + 1) first position of every tile in the cell-ordered permutation
     size_t tile_start_cap = 0;
+    double *d_slice = nullptr;               // staging of lpic_download_field_slice
+    int *d_slice_k = nullptr;
+    size_t slice_cap = 0;
     unsigned long long scratch_epoch = 0;    // bumped by every user of the scratch lists (lpic_ensure_scratch)
     double *d_sort_org = nullptr;            // (3, npatch) bucket origins
     i64 *d_tmp64 = nullptr;                  // small reductions (>= 8 + npatch words)

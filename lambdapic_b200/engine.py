@@ -8,6 +8,7 @@ of every patch is a single copy.  The numpy arrays handed to user code (``p.fiel
 from __future__ import annotations
 
 import ctypes as C
+from contextlib import contextmanager
 
 import numpy as np
 
@@ -22,6 +23,45 @@ PART_FIELD_ATTRS = PART_ATTRS[8:14]
 
 def _ptr(a):
     return C.c_void_p(a.ctypes.data) if a is not None else None
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+@contextmanager
+def numa_local(L, ctx):
+    """Run the body on the CPUs of the GPU's NUMA node, so that pinned host memory allocated (= first touched) inside lands
+    next to the GPU's PCIe root.  Best effort: any missing piece (sysfs, cpuset restrictions) leaves the affinity alone."""
+    import os
+    old = None
+    try:
+        buf = C.create_string_buffer(32)
+        if L.lpic_device_pci_bus_id(ctx, buf, 32) == 0:
+            bus = buf.value.decode().lower()
+            node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+            if node >= 0:
+                cpus = _parse_cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read())
+                mine = os.sched_getaffinity(0)
+                if cpus & mine and (cpus & mine) != mine:
+                    old = mine
+                    os.sched_setaffinity(0, cpus & mine)
+    except (OSError, ValueError, AttributeError):
+        old = None
+    try:
+        yield
+    finally:
+        if old is not None:
+            try:
+                os.sched_setaffinity(0, old)
+            except OSError:
+                pass
 
 
 class HostBuffer:
@@ -60,12 +100,13 @@ class SpeciesMirror:
     def host(self):
         if self._host is None:
             self._host = {}
-            for a in self.attrs + ["is_dead"]:
-                buf = HostBuffer(self.total * (1 if a == "is_dead" else 8))
-                arr = buf.array(np.uint8 if a == "is_dead" else np.float64, self.total)
-                if a == "is_dead":
-                    arr[:] = 1
-                self._host[a], self.buffers[a] = arr, buf
+            with numa_local(self.eng.L, self.eng.ctx):
+                for a in self.attrs + ["is_dead"]:
+                    buf = HostBuffer(self.total * (1 if a == "is_dead" else 8))
+                    arr = buf.array(np.uint8 if a == "is_dead" else np.float64, self.total)
+                    if a == "is_dead":
+                        arr[:] = 1
+                    self._host[a], self.buffers[a] = arr, buf
         return self._host
 
     def refresh_layout(self):
@@ -102,7 +143,8 @@ class DeviceEngine:
         self.shape = (nx + 2 * n_guard, ny + 2 * n_guard) + ((self.nz + 2 * n_guard,) if dim == 3 else ())
         self.ncell = int(self.L.lpic_field_cells(self.ctx))
         assert self.ncell == int(np.prod(self.shape))
-        self._fbuf = HostBuffer(8 * len(FIELD_ATTRS) * npatch * self.ncell)
+        with numa_local(self.L, self.ctx):
+            self._fbuf = HostBuffer(8 * len(FIELD_ATTRS) * npatch * self.ncell)
         self.fields_host = self._fbuf.array(np.float64, len(FIELD_ATTRS) * npatch * self.ncell).reshape(
             (len(FIELD_ATTRS), npatch) + self.shape)
         self.fields_host[...] = 0.0

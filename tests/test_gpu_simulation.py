@@ -397,3 +397,32 @@ def test_extract_species_density_conserves_the_species_charge(dim):
     # steps 0 and 2 trigger; per trigger rho is fetched after species 0 (density of e-, previous rho of p+) and after species 1
     assert st["d2h_bytes"] - before["d2h_bytes"] == sim.bridge.state_bytes() + 2 * 3 * rho_bytes
     sim.bridge.close()
+
+
+@pytest.mark.gpu
+def test_get_fields_inside_run_moves_only_the_slice():
+    """lambdapic_b200.get_fields (callback/utils.py:26-230) called from a device-side callback: in 3D one interior z-plane
+    per patch crosses PCIe (lpic_download_field_slice), and it equals the slice of the full mirror downloaded at run() exit."""
+    import lambdapic_b200 as lp
+    d = 0.8e-6 / 20
+    sim = lp.Simulation3D(nx=32, ny=16, nz=32, dx=d, dy=d, dz=d, npatch_x=2, npatch_y=1, npatch_z=2, dt_cfl=0.95,
+                          boundary_conditions={k: "periodic" for k in ("xmin", "xmax", "ymin", "ymax", "zmin", "zmax")}, random_seed=5)
+    species = [lp.Electron(density=lambda x, y, z: 1.7e27, ppc=4), lp.Proton(density=lambda x, y, z: 1.7e27, ppc=2)]
+    sim.add_species(species)
+    sim.initialize()
+    z_at = sim.Lz * 0.6
+    seen = {}
+
+    @lp.callback("end", needs_host=False)
+    def grab(sim):
+        before = sim.bridge.stats["d2h_bytes"]
+        seen["fields"] = lp.get_fields(sim, ["ex", "jz", "rho"], z_at)
+        seen["bytes"] = sim.bridge.stats["d2h_bytes"] - before
+    sim.run(nsteps=3, callbacks=[lp.SetTemperature(species[0], 2.0e4), lp.SetTemperature(species[1], 2.0e4), grab])
+    plane_bytes = 3 * sim.nx * sim.ny * 8
+    assert 0 < seen["bytes"] <= plane_bytes, (seen["bytes"], plane_bytes)
+    after = lp.get_fields(sim, ["ex", "jz", "rho"], z_at)   # host mirrors are current again after run()
+    for a, b in zip(seen["fields"], after):
+        assert a.shape == (sim.nx, sim.ny) and np.array_equal(a, b)
+    assert np.abs(after[1]).max() > 0 and np.abs(after[2]).max() > 0
+    sim.bridge.close()
