@@ -1,12 +1,14 @@
 // Context, device arenas and host<->device mirrors of the C-ABI (include/lpic_b200.h).
 #include <stdarg.h>
+#include <atomic>
+#include <mutex>
 #include <stdlib.h>
 #include <algorithm>
 #include <vector>
 #include "lpic_common.cuh"
 
 static thread_local char g_err[1024] = "";
-long long g_lpic_launches = 0;
+std::atomic<long long> g_lpic_launches{0};
 
 void lpic_set_error(const char *fmt, ...) {
     va_list ap;
@@ -33,11 +35,13 @@ extern "C" int lpic_device_count(void) {
 
 // pinned allocations are remembered so lpic_host_free knows how to release them
 static std::vector<void *> g_pinned;
+static std::mutex g_pinned_mutex;  // contexts may be driven from several threads
 
 extern "C" void *lpic_host_alloc(int64_t bytes) {
     if (bytes <= 0) bytes = 8;
     void *p = nullptr;
     if (lpic_device_count() > 0 && cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) == cudaSuccess) {
+        std::lock_guard<std::mutex> lock(g_pinned_mutex);
         g_pinned.push_back(p);
         return p;
     }
@@ -47,6 +51,7 @@ extern "C" void *lpic_host_alloc(int64_t bytes) {
 
 extern "C" void lpic_host_free(void *p) {
     if (!p) return;
+    std::unique_lock<std::mutex> lock(g_pinned_mutex);
     auto it = std::find(g_pinned.begin(), g_pinned.end(), p);
     if (it != g_pinned.end()) {
         g_pinned.erase(it);
@@ -130,7 +135,7 @@ extern "C" void lpic_destroy(lpic_ctx *c) {
     lpic_free_peers(c);
     lpic_free_pml(c);
     cudaFree(c->fields); cudaFree(c->d_x0); cudaFree(c->d_y0); cudaFree(c->d_z0); cudaFree(c->d_nbr); cudaFree(c->d_box);
-    cudaFree(c->scr_a); cudaFree(c->scr_b); cudaFree(c->scr_buf); cudaFree(c->d_sort_org); cudaFree(c->d_tmp64); cudaFree(c->d_tmpf); cudaFree(c->d_tile_start); cudaFree(c->d_slice); cudaFree(c->d_slice_k);
+    cudaFree(c->scr_a); cudaFree(c->scr_b); cudaFree(c->scr_buf); cudaFree(c->d_sort_org); cudaFree(c->d_tmp64); cudaFree(c->d_tmpf); cudaFree(c->d_tile_start); cudaFree(c->d_slice); cudaFree(c->d_slice_k); cudaFree(c->d_laser_i); cudaFree(c->d_laser_s); cudaFree(c->d_sort_hist);
     delete[] c->h_x0; delete[] c->h_y0; delete[] c->h_z0; delete[] c->h_nbr; delete[] c->h_patch_index;
     if (c->events) {
         for (int i = 0; i < 4096; i++)
@@ -239,7 +244,7 @@ extern "C" int lpic_download_field_slice(lpic_ctx *c, uint32_t mask, const int64
     const size_t plane = (size_t)g.nx * g.ny, words = (size_t)na * g.npatch * plane;
     if (words > c->slice_cap) {
         CUDA_TRY(cudaStreamSynchronize(c->stream));
-        cudaFree(c->d_slice); cudaFree(c->d_slice_k);
+        cudaFree(c->d_slice); cudaFree(c->d_slice_k); cudaFree(c->d_laser_i); cudaFree(c->d_laser_s); cudaFree(c->d_sort_hist);
         c->d_slice = nullptr; c->d_slice_k = nullptr; c->slice_cap = 0;
         CUDA_TRY(cudaMalloc(&c->d_slice, sizeof(double) * (size_t)LPIC_NFIELD * g.npatch * plane));
         CUDA_TRY(cudaMalloc(&c->d_slice_k, sizeof(int) * g.npatch));
@@ -300,7 +305,10 @@ extern "C" int lpic_species_alloc(lpic_ctx *c, int ispec, const int64_t *npart, 
     sp.total = total;
     const size_t slots = (size_t)std::max<i64>(total, 1);
     for (int a = 0; a < LPIC_NPATTR; a++)
-        if (attr_resident(sp, a)) CUDA_TRY(cudaMalloc(&sp.attr[a], sizeof(double) * slots));
+        if (attr_resident(sp, a)) {
+            CUDA_TRY(cudaMalloc(&sp.attr[a], sizeof(double) * slots));
+            CUDA_TRY(cudaMemsetAsync(sp.attr[a], 0, sizeof(double) * slots, c->stream));  // no stale bit patterns in unused slots
+        }
     CUDA_TRY(cudaMalloc(&sp.dead, slots));
     CUDA_TRY(cudaMemsetAsync(sp.dead, 1, slots, c->stream));
     CUDA_TRY(cudaMalloc(&sp.sort.pidx, sizeof(int) * slots));  // particle_index starts at -1 (particle_sort.py:120-131)
@@ -456,6 +464,7 @@ extern "C" int lpic_species_extend(lpic_ctx *c, int ispec, const int64_t *ext, c
             if (!attr_resident(sp, a)) continue;
             double *fresh = nullptr;
             CUDA_TRY(cudaMalloc(&fresh, sizeof(double) * total));
+            CUDA_TRY(cudaMemsetAsync(fresh, 0, sizeof(double) * total, c->stream));
             k_relayout<double><<<(unsigned)((i64)bpp * n), 256, 0, c->stream>>>(sp.attr[a], fresh, sp.d_off, d_newoff, sp.d_npart, bpp);
             LAUNCHED(1);
             KERNEL_CHECK();

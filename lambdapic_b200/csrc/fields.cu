@@ -595,10 +595,18 @@ extern "C" int lpic_laser_bfields(lpic_ctx *c, int64_t laserpos, int64_t n, cons
         hp[e] = (int)patches[e];
         for (int r = 0; r < 4; r++) hr[4 * e + r] = (int)ranges[4 * e + r];
     }
-    int *d_i = nullptr;
-    double *d_s = nullptr;
-    CUDA_TRY(cudaMalloc(&d_i, sizeof(int) * 5 * n));
-    CUDA_TRY(cudaMalloc(&d_s, sizeof(double) * 2 * n * plane));
+    // persistent staging, grown on demand; the source planes come from pageable host memory, so the copies below are
+    // synchronous with respect to the host and the buffers may be reused by the next call without a stream synchronisation
+    if ((size_t)n > c->laser_cap_n || 2 * (size_t)n * plane > c->laser_cap_words) {
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_laser_i); cudaFree(c->d_laser_s);
+        c->d_laser_i = nullptr; c->d_laser_s = nullptr; c->laser_cap_n = 0; c->laser_cap_words = 0;
+        CUDA_TRY(cudaMalloc(&c->d_laser_i, sizeof(int) * 5 * n));
+        CUDA_TRY(cudaMalloc(&c->d_laser_s, sizeof(double) * 2 * n * plane));
+        c->laser_cap_n = (size_t)n; c->laser_cap_words = 2 * (size_t)n * plane;
+    }
+    int *d_i = c->d_laser_i;
+    double *d_s = c->d_laser_s;
     CUDA_TRY(cudaMemcpyAsync(d_i, hp.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemcpyAsync(d_i + n, hr.data(), sizeof(int) * 4 * n, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemcpyAsync(d_s, ey_src, sizeof(double) * n * plane, cudaMemcpyHostToDevice, c->stream));
@@ -607,8 +615,5 @@ extern "C" int lpic_laser_bfields(lpic_ctx *c, int64_t laserpos, int64_t n, cons
     k_laser<<<grid, 128, 0, c->stream>>>(g, c->fields, d_i, d_i + n, d_s, d_s + n * plane, (int)laserpos, dt);
     LAUNCHED(1);
     KERNEL_CHECK();
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    cudaFree(d_i);
-    cudaFree(d_s);
     return 0;
 }

@@ -112,6 +112,11 @@ struct lpic_ctx {
     double *d_slice = nullptr;               // staging of lpic_download_field_slice
     int *d_slice_k = nullptr;
     size_t slice_cap = 0;
+    int *d_sort_hist = nullptr;              // global histogram of lpic_sort when a patch has more bins than fit shared memory
+    size_t sort_hist_cap = 0;
+    int *d_laser_i = nullptr;                // staging of lpic_laser_bfields (patch list, ranges, source planes)
+    double *d_laser_s = nullptr;
+    size_t laser_cap_n = 0, laser_cap_words = 0;
     unsigned long long scratch_epoch = 0;    // bumped by every user of the scratch lists (lpic_ensure_scratch)
     double *d_sort_org = nullptr;            // (3, npatch) bucket origins
     i64 *d_tmp64 = nullptr;                  // small reductions (>= 8 + npatch words)
@@ -205,7 +210,8 @@ __host__ __device__ inline int wrapneg(int i, int N) { return i < 0 ? i + N : i;
 // kernels' launch helpers
 static inline unsigned div_up(i64 a, i64 b) { return (unsigned)((a + b - 1) / b); }
 
-extern long long g_lpic_launches;  // kernels launched by this library (bench.py's gpu_launches)
+#include <atomic>
+extern std::atomic<long long> g_lpic_launches;  // kernels launched by this library (bench.py's gpu_launches)
 #define LAUNCHED(n) (g_lpic_launches += (n))
 
 // entry points implemented per file

@@ -246,7 +246,7 @@ int make_args(lpic_ctx *c, int ispec, MigArgs &a) {
     a.out = sp.d_out; a.ndead = sp.d_ndead; a.incoming = sp.d_incoming; a.extend = sp.d_extend; a.alive = sp.d_alive;
     a.la = c->scr_a; a.lb = c->scr_b;
     a.remote_in = nullptr;
-    a.dirstart = (int *)(c->d_tmp64 + 64);  // npatch*nb ints <= 4*npatch i64 words (26 ints = 13 words): checked below
+    a.dirstart = (int *)(c->d_tmp64 + 64);  // npatch*nb ints = 13 npatch i64 words at most; d_tmp64 holds 64 + 16 npatch (lpic_create)
     a.nattr = 0; a.ia_x = a.ia_y = a.ia_z = -1;
     for (int t = 0; t < LPIC_NPATTR; t++) {
         if (!sp.attr[t]) continue;

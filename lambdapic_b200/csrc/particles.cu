@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) k_init_uniform(Geom g, const double *px0,
     id[ip] = __longlong_as_double((long long)bits);
     if (local >= ncell * ppc) {  // spare capacity: dead slot as ParticlesBase.extend leaves it
         const double nan = __longlong_as_double(0x7ff8000000000000ll);
-        s.x[ip] = nan; s.y[ip] = nan; if (g.dim == 3) s.z[ip] = nan;
+        s.x[ip] = nan; s.y[ip] = nan; s.z[ip] = g.dim == 3 ? nan : 0.0;
         s.ux[ip] = nan; s.uy[ip] = nan; s.uz[ip] = nan; s.ig[ip] = nan; s.w[ip] = 0.0;
         dead[ip] = 1;
         return;
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) k_init_uniform(Geom g, const double *px0,
     const double r2 = u01(h); h = mix64(h);
     s.x[ip] = px0[p] + (i + r0 - 0.5) * g.dx;
     s.y[ip] = py0[p] + (j + r1 - 0.5) * g.dy;
-    if (g.dim == 3) s.z[ip] = pz0[p] + (k + r2 - 0.5) * g.dz;
+    s.z[ip] = g.dim == 3 ? pz0[p] + (k + r2 - 0.5) * g.dz : 0.0;
     const double a0 = u01(h); h = mix64(h);
     const double a1 = u01(h); h = mix64(h);
     const double a2 = u01(h); h = mix64(h);

@@ -365,8 +365,16 @@ extern "C" int lpic_sort(lpic_ctx *c, int ispec, int reverse_x, int64_t nxb, int
     for (i64 p = 0; p < n; p++) { org[p] = x0s[p]; org[n + p] = y0s[p]; org[2 * n + p] = (g.dim == 3 && z0s) ? z0s[p] : 0.0; }
     CUDA_TRY(cudaMemcpyAsync(c->d_sort_org, org.data(), sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
     int *g_hist = nullptr, *g_cur = nullptr;
-    if (nbin > SMEM_BINS) {
-        CUDA_TRY(cudaMalloc(&g_hist, sizeof(int) * n * nbin * 2));
+    if (nbin > SMEM_BINS) {  // persistent, grown on demand
+        const size_t need = (size_t)n * nbin * 2;
+        if (need > c->sort_hist_cap) {
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            cudaFree(c->d_sort_hist);
+            c->d_sort_hist = nullptr; c->sort_hist_cap = 0;
+            CUDA_TRY(cudaMalloc(&c->d_sort_hist, sizeof(int) * need));
+            c->sort_hist_cap = need;
+        }
+        g_hist = c->d_sort_hist;
         g_cur = g_hist + n * nbin;
         CUDA_TRY(cudaMemsetAsync(g_hist, 0, sizeof(int) * n * nbin * 2, c->stream));
     }
@@ -384,7 +392,6 @@ extern "C" int lpic_sort(lpic_ctx *c, int ispec, int reverse_x, int64_t nxb, int
     std::vector<i64> h_nbuf(n);
     CUDA_TRY(cudaMemcpyAsync(h_nbuf.data(), d_nbuf, sizeof(i64) * n, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    if (g_hist) cudaFree(g_hist);
     i64 total = 0;
     for (i64 p = 0; p < n; p++) total += h_nbuf[p];
     if (nbuf_total) *nbuf_total = total;
@@ -427,13 +434,12 @@ extern "C" int lpic_sort_download(lpic_ctx *c, int ispec, int which, int64_t *ou
     SortState &st = sp.sort;
     const i64 n = c->g.npatch;
     if (which == LPIC_SORT_PARTICLE_INDEX) {
-        i64 *tmp = nullptr;
-        CUDA_TRY(cudaMalloc(&tmp, sizeof(i64) * std::max<i64>(sp.total, 1)));
+        if (int r = lpic_ensure_scratch(c, sp.total)) return r;
+        i64 *tmp = (i64 *)c->scr_buf;  // the sort's fp64 staging buffer: one 8-byte word per slot, idle outside lpic_sort
         k_widen<<<div_up(std::max<i64>(sp.total, 1), 256), 256, 0, c->stream>>>(st.pidx, tmp, sp.total);
         LAUNCHED(1);
         CUDA_TRY(cudaMemcpyAsync(out, tmp, sizeof(i64) * sp.total, cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
-        cudaFree(tmp);
         return 0;
     }
     REQUIRE(st.nbin > 0, "sorter of species %d has not run yet", ispec);

@@ -2,8 +2,9 @@
 on the GPU engine.  Constructor arguments, public attributes, the 14 callback stages, the order of operators inside
 one step and the timer names are the reference's; every operator is a facade over the C-ABI (operators.py).
 
-Out of scope this round (raised explicitly instead of silently differing): CPML boundaries, QED,
-collisions, load balancing.  Multi-rank runs use lambdapic_b200.multigpu (static block partition, NCCL halos).
+Built on the device: periodic and CPML boundaries, the laser antenna, the moving window.  Outside the accelerated path
+(raised explicitly instead of silently differing): QED, collisions, load balancing.  Multi-rank runs use
+lambdapic_b200.multigpu (static block partition, NCCL halos inside the library).
 """
 from __future__ import annotations
 
@@ -53,9 +54,16 @@ class SimulationCallbacks:
 
 
 class Timer:
-    """Accumulates wall time per operator name (the reference's names)."""
+    """Wall time per operator name (the reference's names; core/utils/timer.py:29-96).  With
+    ``enable_timer`` every interval above 0.1 ms is also appended to ``<log_file stem>.timer.txt`` in the reference's record
+    format (``... | TIMER | Rank r <name> took <ms>ms``), which is what ``lambdapic timer-stat`` aggregates
+    (cli/stat.py:12).  Device work is asynchronous, so in timer mode the stream is synchronised when an interval closes:
+    the numbers are per-operator device times, and the step is serialised while the timer is on."""
     totals: dict = {}
     enabled = False
+    sink = None     # open text file of the TIMER records, or None
+    rank = 0
+    sync = None     # callable that waits for the device, set by Simulation.initialize
 
     def __init__(self, name):
         self.name = name
@@ -67,8 +75,28 @@ class Timer:
 
     def __exit__(self, *exc):
         if Timer.enabled:
-            Timer.totals[self.name] = Timer.totals.get(self.name, 0.0) + _time.perf_counter() - self.t0
+            if Timer.sync is not None:
+                Timer.sync()
+            dt = _time.perf_counter() - self.t0
+            Timer.totals[self.name] = Timer.totals.get(self.name, 0.0) + dt
+            if Timer.sink is not None and dt > 1e-4:
+                stamp = _time.strftime("%Y-%m-%d %H:%M:%S") + f".{int((_time.time() % 1) * 1000):03d}"
+                Timer.sink.write(f"{stamp} | TIMER    | Rank {Timer.rank} {self.name} took {1e3 * dt:.1f}ms\n")
         return False
+
+    @staticmethod
+    def open_sink(log_file, truncate=True):
+        """log.txt -> log.timer.txt (core/utils/logger.py:14-25)."""
+        import os
+        if Timer.sink is not None:
+            Timer.sink.close()
+            Timer.sink = None
+        if not log_file:
+            return None
+        stem, ext = os.path.splitext(str(log_file))
+        path = f"{stem}.timer{ext or '.txt'}"
+        Timer.sink = open(path, "w" if truncate else "a", buffering=1)
+        return path
 
 
 @dataclass
@@ -157,6 +185,8 @@ class Simulation:
         self.ispec = None
         self.istep = 0
         Timer.enabled = bool(self.enable_timer)
+        if Timer.enabled:
+            Timer.open_sink(self.log_file, self.truncate_log)
 
     # ---- species -----------------------------------------------------------------------------------------------
     def add_species(self, species: Sequence[Species]):
@@ -224,6 +254,8 @@ class Simulation:
         self._set_global_domain_bounds()
         self.bridge = DeviceBridge(self.patches, self.n_guard, device=self.device, with_part=self.store_part_fields,
                                    nspec=len(self.species))
+        Timer.rank = rank
+        Timer.sync = self.bridge.engine.sync if self.enable_timer else None
         if size > 1:
             from .multigpu import MultiRankMPI
             self.mpi = MultiRankMPI(self, comm)
@@ -467,7 +499,7 @@ class Simulation:
                     self.maxwell.update_efield(0.5 * self.dt)
                 self._sync_guards(E, "E")
                 self._stage(cbs, "maxwell_2", "Callbacks: maxwell_2 stage")
-                self._stage(cbs, "end", "Callbacks: maxwell_2 stage")
+                self._stage(cbs, "end", "Callbacks: end stage")
 
                 self.time += self.dt
                 self.itime += 1

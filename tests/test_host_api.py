@@ -240,3 +240,24 @@ def test_stage_mirror_traffic_follows_the_callback_hints():
     assert log == [("down", frozenset({"rho", "ex"})), ("up", frozenset())] and after
     log, seen, after = run([hinted, plain])
     assert log == [("down", None), ("up", None)] and seen == [False, False] and after
+
+
+def test_timer_records_have_the_format_timer_stat_parses(tmp_path):
+    """enable_timer writes `<log>.timer.txt` with the reference's TIMER records (core/utils/timer.py:84-96); the pattern is
+    the one `lambdapic timer-stat` uses (cli/stat.py:12)."""
+    import re
+    import time
+    from lambdapic_b200.simulation import Timer
+    Timer.enabled, Timer.sync = True, None
+    path = Timer.open_sink(str(tmp_path / "log.txt"))
+    assert path.endswith("log.timer.txt")
+    with Timer("unified pusher for electron"):
+        time.sleep(0.002)
+    with Timer("too short to log"):
+        pass
+    Timer.sink.close()
+    Timer.sink, Timer.enabled = None, False
+    lines = [ln for ln in open(path) if "TIMER" in ln]
+    assert len(lines) == 1
+    m = re.search(r"Rank \d+ (.*?) took ([\d.]+)ms", lines[0].split("|")[-1].strip())
+    assert m and m.group(1) == "unified pusher for electron" and float(m.group(2)) >= 2.0
