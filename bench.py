@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-cells", type=int, default=64, help="edge of the CPU sample box (cells)")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the multi-rank parity self-check (N > 1)")
+    ap.add_argument("--cell-sort", action="store_true", help="experiment: the reference's FULL-bucket sorter configuration (one bucket per "
+                    "cell, what ParticleSort3D uses for species with collisions, simulation.py:1373) instead of the default x-column "
+                    "buckets; the slot order then stays cell order, but it is not the order of the reference's default path")
     args = ap.parse_args()
     if args.ppc is None:
         args.ppc = [32, 32] if args.scaling == "weak" else [4, 4]
@@ -200,7 +203,7 @@ def config_dict(args, wl, nranks):
                         f"({wl.cells[0]}x{wl.cells[1]}x{wl.cells[2]} cells on {nranks} GPU(s), "
                         f"{args.ppc[0]}+{args.ppc[1]} ppc, {args.patch}^3-cell patches, 1 keV, fp64)",
             "cells_global": list(wl.cells), "particles_global": wl.n_particles(), "patch_cells": args.patch,
-            "ppc": list(args.ppc), "n_guard": 3, "parallelism": f"patch blocks over {nranks} GPU(s)",
+            "ppc": list(args.ppc), "n_guard": 3, "sorter": "one bucket per cell (--cell-sort experiment)" if args.cell_sort else "x-column buckets (reference default)", "parallelism": f"patch blocks over {nranks} GPU(s)",
             "l2_policy": "inputs larger than L2 (particle arenas are tens of GB; no flush needed)"}
 
 
@@ -300,6 +303,10 @@ def main():
         parity = multirank_parity_check(args, rank, world, local)
     eng = build_engine(wl, device=local, rank=rank, nranks=world, slack=1.4 if args.scaling == "weak" else 1.3)
     eng.slot_order = args.slot_order
+    if args.cell_sort:
+        pg0 = eng.grid
+        for sidx in range(eng.nspec):
+            eng.configure_sort(sidx, pg0.nx, pg0.ny, pg0.nz, pg0.dx, pg0.dy, pg0.dz, pg0.x0 - pg0.dx / 2, pg0.y0 - pg0.dy / 2, pg0.z0 - pg0.dz / 2)
     if world > 1:
         from lambdapic_b200.multigpu import HaloExchanger
         eng.halo = HaloExchanger(eng, eng.grid)
