@@ -187,6 +187,11 @@ int lpic_remote_migrate_unpack(lpic_ctx *ctx, int ispec, const int64_t *recv_cou
 int lpic_event_record(lpic_ctx *ctx, int slot);                              /* slot in [0, 4096) */
 int lpic_event_elapsed_ms(lpic_ctx *ctx, int slot_a, int slot_b, double *ms); /* synchronises on slot_b */
 int64_t lpic_launch_count(void);
+/* MovingWindow recycle without a round trip of the whole state (callback/utils.py:591-840): the recycled patches' fields and psi
+ * arrays are cleared on the device, and only their freshly loaded particles are uploaded (slots [off[p], off[p] + npart[p]) of
+ * an arena with the device's layout, after lpic_species_set_npart). */
+int lpic_zero_patches(lpic_ctx *ctx, int64_t n, const int64_t *patches);
+int lpic_upload_particles_patch(lpic_ctx *ctx, int ispec, int attr, int64_t patch, const void *host_arena);
 /* One interior z-plane per patch of the attributes in attr_mask (3D): kz[p] = plane index inside patch p (0 <= kz < nz) or -1
  * if the patch does not contain the plane.  host = [nattr][npatch][nx][ny] fp64.  Replaces the whole-patch copies behind
  * callback/utils.py:125-230 (get_fields_3d) and callback/hdf5.py:451-481 (SaveFieldsToHDF5(slice=...)). */

@@ -84,6 +84,8 @@ SIGNATURES = {
     "lpic_event_elapsed_ms": (_int, [_vp, _int, _int, _vp]),
     "lpic_launch_count": (_i64, []),
     "lpic_fp64_peak": (_int, [_vp, _vp]),
+    "lpic_zero_patches": (_int, [_vp, _i64, _vp]),
+    "lpic_upload_particles_patch": (_int, [_vp, _int, _int, _i64, _vp]),
     "lpic_device_pci_bus_id": (_int, [_vp, _vp, _int]),
     "lpic_download_field_slice": (_int, [_vp, _u32, _vp, _vp]),
     "lpic_comm_unique_id": (_int, [_vp]),

@@ -125,6 +125,7 @@ static void free_species(Species &sp) {
 
 void lpic_free_peers(lpic_ctx *c);
 void lpic_free_pml(lpic_ctx *c);
+int lpic_pml_zero_psi_of(lpic_ctx *c, i64 n, const int64_t *patches);  // fields.cu
 
 extern "C" void lpic_destroy(lpic_ctx *c) {
     if (!c) return;
@@ -355,6 +356,31 @@ extern "C" int lpic_upload_particles(lpic_ctx *c, int ispec, int attr, const voi
     c->spec[ispec].sort.valid = false;
     c->spec[ispec].lists_valid = false;
     return 0;
+}
+// One patch's slots [off[p], off[p] + npart[p]) of one attribute, from an arena with the device's layout (MovingWindow:
+// only the recycled patches' particles cross PCIe)
+extern "C" int lpic_upload_particles_patch(lpic_ctx *c, int ispec, int attr, int64_t patch, const void *host_arena) {
+    DeviceGuard dg(c);
+    void *dev; size_t esz;
+    if (int r = particle_array(c, ispec, attr, &dev, &esz)) return r;
+    Species &sp = c->spec[ispec];
+    REQUIRE(patch >= 0 && patch < c->g.npatch, "bad patch %lld", (long long)patch);
+    const size_t first = (size_t)sp.h_off[patch] * esz, bytes = (size_t)sp.h_npart[patch] * esz;
+    if (bytes) CUDA_TRY(cudaMemcpyAsync((char *)dev + first, (const char *)host_arena + first, bytes, cudaMemcpyHostToDevice, c->stream));
+    sp.sort.valid = false;
+    sp.lists_valid = false;
+    return 0;
+}
+// Vacuum fields (all ten attributes) and psi arrays of the listed patches, on the device (callback/utils.py:790-800)
+extern "C" int lpic_zero_patches(lpic_ctx *c, int64_t n, const int64_t *patches) {
+    DeviceGuard dg(c);
+    const Geom &g = c->g;
+    for (i64 i = 0; i < n; i++) {
+        REQUIRE(patches[i] >= 0 && patches[i] < g.npatch, "bad patch in the list");
+        for (int a = 0; a < LPIC_NFIELD; a++)
+            CUDA_TRY(cudaMemsetAsync(field_ptr(c, a) + (size_t)patches[i] * g.ncell, 0, sizeof(double) * g.ncell, c->stream));
+    }
+    return lpic_pml_zero_psi_of(c, n, patches);
 }
 extern "C" int lpic_download_particles(lpic_ctx *c, int ispec, int attr, void *host) {
     DeviceGuard dg(c);

@@ -566,6 +566,20 @@ extern "C" int lpic_pml_configure(lpic_ctx *c, int64_t ninst, const int64_t *ins
     return 0;
 }
 
+// psi arrays of every CPML face that belongs to one of the listed patches -> 0 (the patch was recycled by the moving window)
+int lpic_pml_zero_psi_of(lpic_ctx *c, i64 n, const int64_t *patches) {
+    PmlState *pm = c->pml;
+    if (!pm || pm->ninst == 0) return 0;
+    std::vector<int> inst((size_t)pm->ninst * 8);
+    CUDA_TRY(cudaMemcpyAsync(inst.data(), pm->d_inst, sizeof(int) * inst.size(), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (i64 s = 0; s < pm->ninst; s++)
+        for (i64 i = 0; i < n; i++)
+            if (inst[s * 8] == (int)patches[i])  // slot-grouped position s holds the caller's instance h_order[s]
+                CUDA_TRY(cudaMemsetAsync(pm->d_psi + (size_t)pm->h_order[s] * 4 * pm->ncint, 0, sizeof(double) * 4 * pm->ncint, c->stream));
+    return 0;
+}
+
 extern "C" int64_t lpic_pml_psi_words(const lpic_ctx *c) {
     DeviceGuard dg(c); return c->pml ? c->pml->ninst * 4 * c->pml->ncint : 0; }
 extern "C" int lpic_pml_upload_psi(lpic_ctx *c, const double *host) {

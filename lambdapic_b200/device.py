@@ -13,7 +13,8 @@ from contextlib import contextmanager
 
 import numpy as np
 
-from ._lib import FIELD_ATTRS, PART_ATTRS
+from . import _lib
+from ._lib import FIELD_ATTRS, P_IS_DEAD, PART_ATTRS
 from .engine import ALL_FIELDS, DeviceEngine
 from .fields import Fields2D, Fields3D
 
@@ -157,6 +158,56 @@ class DeviceBridge:
                 self._host_only_part_fields(pt)
             eng.npart_created[s][ip] = pt._npart_created
         return True
+
+    def recycle(self, recycled):
+        """MovingWindow fast path (device authoritative): the listed patches were recycled on the host -- fresh particle
+        arrays from the loader, vacuum fields.  Their fields and psi arrays are cleared ON the device and only their new
+        particles are uploaded; every other patch keeps its device state and no mirror is refreshed.  Geometry (origins,
+        neighbour tables, particle boxes) is re-registered.  Returns the bytes sent."""
+        import ctypes as C
+        eng, ps = self.engine, self.patches
+        assert self.resident, "recycle() is the device-resident path"
+        recycled = [int(ip) for ip in recycled]
+        nbytes = 0
+        for s in range(eng.nspec):
+            m = eng.species[s]
+            parts = [ps[ip].particles[s] for ip in recycled]
+            if not any(pt._detached for pt in parts):
+                continue  # species without a density profile: the loader left it alone
+            npart = m.npart.copy()
+            ext = np.zeros(eng.npatch, dtype=np.int64)
+            for ip, pt in zip(recycled, parts):
+                if pt.npart > m.pcap[ip]:
+                    ext[ip] = pt.npart - m.npart[ip]
+            if ext.any():  # a recycled patch holds more particles than its segment: grow it on the device first
+                eng.extend(s, ext)
+                m = eng.species[s]
+                npart = m.npart.copy()
+            for ip, pt in zip(recycled, parts):
+                npart[ip] = pt.npart
+            eng.set_npart(s, npart)
+            m = eng.species[s]
+            m.host  # the pinned arenas exist from here on
+            for ip, pt in zip(recycled, parts):
+                vals, dead = {a: getattr(pt, a) for a in m.attrs}, pt.is_dead
+                self._seat(pt, m, ip)
+                for a in m.attrs:
+                    getattr(pt, a)[...] = vals[a]
+                pt.is_dead[...] = dead
+                if not self.with_part:
+                    self._host_only_part_fields(pt)
+                eng.npart_created[s][ip] = pt._npart_created
+                for a in m.attrs + ["is_dead"]:
+                    aid = P_IS_DEAD if a == "is_dead" else PART_ATTRS.index(a)
+                    _lib.check(eng.L.lpic_upload_particles_patch(eng.ctx, s, aid, ip, C.c_void_p(m.host[a].ctypes.data)))
+                nbytes += pt.npart * (8 * len(m.attrs) + 1)
+        arr = np.ascontiguousarray(recycled, dtype=np.int64)
+        _lib.check(eng.L.lpic_zero_patches(eng.ctx, len(recycled), C.c_void_p(arr.ctypes.data)))
+        self._set_geometry()
+        eng.sync()  # the pinned slices may be rewritten by the next shift
+        self.stats["h2d_bytes"] += int(nbytes)
+        self.stats["recycles"] = self.stats.get("recycles", 0) + 1
+        return nbytes
 
     @staticmethod
     def _host_only_part_fields(pt):

@@ -3,13 +3,15 @@ patches at a time.  Same constructor, stage (`start`) and bookkeeping (total_shi
 reference; the shift itself works on the host mirrors of the DeviceBridge:
 
   non-shift steps  nothing crosses PCIe (`needs_host = False`: the bridge does not refresh the mirrors for this callback);
-  shift steps      download -> rotate ipatch_x / x0 / axes of the recycled column, rebuild the neighbour tables, drop the
-                   PMLX faces (first activation), re-load the recycled patches' particles from the density profile with the
-                   reference's generator stream, zero their fields and psi, recompute the sort origins -> re-register the
-                   geometry with the device and upload.  One column is recycled every nx_per_patch*dx/(v dt) steps, so the
-                   round trip is amortised over ~10-70 steps; a device-side recycle is the next step.
+  shift steps      rotate ipatch_x / x0 / axes of the recycled column on the host objects, rebuild the neighbour tables,
+                   re-load the recycled patches' particles from the density profile with the reference's generator
+                   stream, recompute the sort origins.  Then, device-resident (DeviceBridge.recycle): the recycled
+                   patches' fields and psi arrays are cleared ON the device, only their new particles are uploaded
+                   (lpic_species_set_npart + lpic_upload_particles_patch) and the geometry is re-registered -- no mirror
+                   is downloaded, no other patch is touched.  The first activation also drops the PMLX faces, which changes
+                   the set of CPML instances: that one step takes the download -> re-register -> upload route.
 
-Single rank only in this round: with more than one rank the exchange plan would have to be rebuilt after every shift.
+Single rank only: with more than one rank the exchange plan would have to be rebuilt after every shift.
 """
 from __future__ import annotations
 
@@ -65,16 +67,23 @@ class MovingWindow:
 
         br = sim.bridge
         was_resident = br.resident
-        if was_resident:
+        fast = was_resident and direction and not drop_pmlx  # device-side recycle: nothing but the new particles moves
+        if was_resident and not fast:
             br.download()
             br.resident = False
         if drop_pmlx:  # the x faces stop absorbing once the window moves (callback/utils.py:545-552)
             for p in sim.patches:
                 p.pml_boundary = [m for m in p.pml_boundary if m.axis != 0]
+        new_patches = []
         if direction:
             new_patches = self._shift(sim, direction)
             sim.patches.geometry_version = getattr(sim.patches, "geometry_version", 0) + 1
             self._update_patch_info(sim)
+            if fast:  # the host objects are stale while the device is authoritative: the id counters live in the engine
+                where = {id(p): ip for ip, p in enumerate(sim.patches)}
+                for p in new_patches:
+                    for ispec, pt in enumerate(p.particles):
+                        pt._npart_created = int(br.engine.npart_created[ispec][where[id(p)]])
             self._fill_particles(sim, new_patches)
             for p in new_patches:  # recycled patches start from vacuum fields
                 for attr in p.fields.attrs:
@@ -86,6 +95,10 @@ class MovingWindow:
             for sorter in sim.sorter:
                 sorter.generate_field_lists()
                 sorter.generate_particle_lists()
+        if fast:
+            where = {id(p): ip for ip, p in enumerate(sim.patches)}
+            self.last_shift_bytes = br.recycle([where[id(p)] for p in new_patches])
+            return
         br.refresh_geometry(pml_changed=drop_pmlx)
         if was_resident:
             br.upload()
