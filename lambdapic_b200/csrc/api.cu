@@ -136,7 +136,7 @@ extern "C" void lpic_destroy(lpic_ctx *c) {
     lpic_free_peers(c);
     lpic_free_pml(c);
     cudaFree(c->fields); cudaFree(c->d_x0); cudaFree(c->d_y0); cudaFree(c->d_z0); cudaFree(c->d_nbr); cudaFree(c->d_box);
-    cudaFree(c->scr_a); cudaFree(c->scr_b); cudaFree(c->scr_buf); cudaFree(c->d_sort_org); cudaFree(c->d_tmp64); cudaFree(c->d_tmpf); cudaFree(c->d_tile_start); cudaFree(c->d_slice); cudaFree(c->d_slice_k); cudaFree(c->d_laser_i); cudaFree(c->d_laser_s); cudaFree(c->d_sort_hist);
+    cudaFree(c->scr_a); cudaFree(c->scr_b); cudaFree(c->scr_buf); cudaFree(c->d_sort_org); cudaFree(c->d_tmp64); cudaFree(c->d_tmpf); cudaFree(c->d_tile_start); cudaFree(c->d_slice); cudaFree(c->d_slice_k); cudaFree(c->d_laser_i); cudaFree(c->d_laser_s); cudaFree(c->d_sort_hist); cudaFree(c->d_ext_tab); cudaFree(c->d_ext_attrs);
     delete[] c->h_x0; delete[] c->h_y0; delete[] c->h_z0; delete[] c->h_nbr; delete[] c->h_patch_index;
     if (c->events) {
         for (int i = 0; i < 4096; i++)
@@ -245,7 +245,7 @@ extern "C" int lpic_download_field_slice(lpic_ctx *c, uint32_t mask, const int64
     const size_t plane = (size_t)g.nx * g.ny, words = (size_t)na * g.npatch * plane;
     if (words > c->slice_cap) {
         CUDA_TRY(cudaStreamSynchronize(c->stream));
-        cudaFree(c->d_slice); cudaFree(c->d_slice_k); cudaFree(c->d_laser_i); cudaFree(c->d_laser_s); cudaFree(c->d_sort_hist);
+        cudaFree(c->d_slice); cudaFree(c->d_slice_k); cudaFree(c->d_laser_i); cudaFree(c->d_laser_s); cudaFree(c->d_sort_hist); cudaFree(c->d_ext_tab); cudaFree(c->d_ext_attrs);
         c->d_slice = nullptr; c->d_slice_k = nullptr; c->slice_cap = 0;
         CUDA_TRY(cudaMalloc(&c->d_slice, sizeof(double) * (size_t)LPIC_NFIELD * g.npatch * plane));
         CUDA_TRY(cudaMalloc(&c->d_slice_k, sizeof(int) * g.npatch));
@@ -467,10 +467,14 @@ extern "C" int lpic_species_extend(lpic_ctx *c, int ispec, const int64_t *ext, c
     }
     if (max_ext == 0) return 0;
     // small device tables: old npart is still in d_npart; ext / id_first go to scratch
-    i64 *d_ext = nullptr;
-    u64 *d_idf = nullptr;
-    CUDA_TRY(cudaMalloc(&d_ext, sizeof(i64) * n * 3));
-    d_idf = (u64 *)(d_ext + n);
+    // (persistent per context: cudaMalloc / cudaFree in a call that sparse moving-window runs make every step would
+    // synchronise the whole device each time)
+    if (!c->d_ext_tab) {
+        CUDA_TRY(cudaMalloc(&c->d_ext_tab, sizeof(i64) * n * 3));
+        CUDA_TRY(cudaMalloc(&c->d_ext_attrs, sizeof(double *) * LPIC_NPATTR));
+    }
+    i64 *d_ext = c->d_ext_tab;
+    u64 *d_idf = (u64 *)(d_ext + n);
     i64 *d_newoff = d_ext + 2 * n;
     CUDA_TRY(cudaMemcpyAsync(d_ext, ext, sizeof(i64) * n, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemcpyAsync(d_idf, id_first, sizeof(u64) * n, cudaMemcpyHostToDevice, c->stream));
@@ -531,8 +535,7 @@ extern "C" int lpic_species_extend(lpic_ctx *c, int ispec, const int64_t *ext, c
         if (a == LPIC_P_ID) ia_id = na;
         h_attrs[na++] = sp.attr[a];
     }
-    double **d_attrs = nullptr;
-    CUDA_TRY(cudaMalloc(&d_attrs, sizeof(double *) * na));
+    double **d_attrs = c->d_ext_attrs;
     CUDA_TRY(cudaMemcpyAsync(d_attrs, h_attrs, sizeof(double *) * na, cudaMemcpyHostToDevice, c->stream));
     const int bpp = (int)div_up(max_ext, 256);
     k_extend_init<<<(unsigned)((i64)bpp * n), 256, 0, c->stream>>>((int)n, sp.d_off, sp.d_npart, d_ext, d_idf, d_attrs, na,
@@ -548,9 +551,7 @@ extern "C" int lpic_species_extend(lpic_ctx *c, int ispec, const int64_t *ext, c
         LAUNCHED(1);
         KERNEL_CHECK();
     }
-    int r = upload_layout(c, sp);  // synchronises the stream
-    cudaFree(d_ext);
-    cudaFree(d_attrs);
+    int r = upload_layout(c, sp);  // synchronises the stream: the host tables above may go out of scope
     sp.sort.valid = false;
     sp.lists_valid = false;
     return r;

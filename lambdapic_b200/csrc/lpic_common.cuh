@@ -112,6 +112,8 @@ struct lpic_ctx {
     double *d_slice = nullptr;               // staging of lpic_download_field_slice
     int *d_slice_k = nullptr;
     size_t slice_cap = 0;
+    i64 *d_ext_tab = nullptr;                // lpic_species_extend: ext / first id / new offsets (3 x npatch)
+    double **d_ext_attrs = nullptr;          // ... and its table of attribute pointers
     int *d_sort_hist = nullptr;              // global histogram of lpic_sort when a patch has more bins than fit shared memory
     size_t sort_hist_cap = 0;
     int *d_laser_i = nullptr;                // staging of lpic_laser_bfields (patch list, ranges, source planes)

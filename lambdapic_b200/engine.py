@@ -102,11 +102,17 @@ class SpeciesMirror:
             self._host = {}
             with numa_local(self.eng.L, self.eng.ctx):
                 for a in self.attrs + ["is_dead"]:
-                    buf = HostBuffer(self.total * (1 if a == "is_dead" else 8))
+                    need = self.total * (1 if a == "is_dead" else 8)
+                    buf = self.buffers.get(a)
+                    if buf is None or buf.nbytes < need:  # pinning is slow (~ms per 100 MB): keep buffers, grow with headroom
+                        if buf is not None:
+                            buf.free()
+                        buf = HostBuffer(need + need // 4)
+                        self.buffers[a] = buf
                     arr = buf.array(np.uint8 if a == "is_dead" else np.float64, self.total)
                     if a == "is_dead":
                         arr[:] = 1
-                    self._host[a], self.buffers[a] = arr, buf
+                    self._host[a] = arr
         return self._host
 
     def refresh_layout(self):
@@ -118,7 +124,7 @@ class SpeciesMirror:
         same = self.off is not None and total.value == self.total and np.array_equal(off, self.off)
         self.off, self.pcap, self.npart, self.total = off, pcap, npart, int(total.value)
         if not same:
-            self.free()
+            self._host = None  # the views are rebuilt on next use; the pinned buffers stay while they are large enough
 
     def view(self, attr: str, p: int):
         a = self.host[attr][self.off[p]:self.off[p] + self.npart[p]]
