@@ -205,6 +205,8 @@ int lpic_comm_unique_id(void *id128);
 int lpic_comm_nccl_version(void);
 int lpic_comm_init(lpic_ctx *ctx, const void *id128, int rank, int nranks, const int64_t *peer_rank);
 int64_t lpic_comm_bytes_sent(const lpic_ctx *ctx);
+/* after lpic_halo_plan replaced the plan of a context that has a communicator (MovingWindow shift, callback/utils.py:648-716) */
+int lpic_comm_update(lpic_ctx *ctx, const int64_t *peer_rank);
 /* pack + ncclSend/ncclRecv per peer, asynchronous; run the intra-rank lpic_sync_guard_fields / lpic_sync_currents between
  * start and wait (simulation/simulation.py:948-952); wait = compute stream waits for the receive, then one unpack kernel */
 int lpic_halo_start(lpic_ctx *ctx, uint32_t attr_mask, int reduce);

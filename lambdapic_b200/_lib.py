@@ -92,6 +92,7 @@ SIGNATURES = {
     "lpic_comm_nccl_version": (_int, []),
     "lpic_comm_init": (_int, [_vp, _vp, _int, _int, _vp]),
     "lpic_comm_bytes_sent": (_i64, [_vp]),
+    "lpic_comm_update": (_int, [_vp, _vp]),
     "lpic_halo_start": (_int, [_vp, _u32, _int]),
     "lpic_halo_wait": (_int, [_vp]),
     "lpic_migrate_remote_start": (_int, [_vp, _int, _int, _vp, _vp]),

@@ -91,6 +91,7 @@ struct CommState {
     double *psend[LPIC_MAX_PEERS] = {nullptr}, *precv[LPIC_MAX_PEERS] = {nullptr};
     i64 psend_cap[LPIC_MAX_PEERS] = {0}, precv_cap[LPIC_MAX_PEERS] = {0};
     bool mig_pending = false;
+    bool plan_stale = false;  // lpic_halo_plan replaced the plan: lpic_comm_update has to re-size the staging first
     i64 mig_max_remote = 0;
     long long bytes_sent = 0;
 };
@@ -113,6 +114,40 @@ void lpic_free_comm(lpic_ctx *c) {
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
     c->comm = nullptr;
+}
+
+void lpic_comm_plan_changed(lpic_ctx *c) {
+    if (c->comm) c->comm->plan_stale = true;
+}
+
+static int alloc_plan_buffers(lpic_ctx *c, CommState *m, const int64_t *peer_rank) {
+    HaloPlan *h = c->halo;
+    if (m->stream) CUDA_TRY(cudaStreamSynchronize(m->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (int s = 0; s < LPIC_MAX_PEERS; s++) {
+        cudaFree(m->fsend[s]); cudaFree(m->frecv[s]);
+        m->fsend[s] = m->frecv[s] = nullptr;
+    }
+    cudaFree(m->d_recv_cnt_ent);
+    m->d_recv_cnt_ent = nullptr;
+    for (int s = 0; s < h->npeers; s++) {
+        REQUIRE(peer_rank[s] >= 0 && peer_rank[s] < m->nranks && peer_rank[s] != m->rank, "bad peer rank in slot %d", s);
+        m->peer_rank[s] = (int)peer_rank[s];
+        CUDA_TRY(cudaMalloc(&m->fsend[s], sizeof(double) * 4 * std::max<i64>(h->send_words[s], 1)));
+        CUDA_TRY(cudaMalloc(&m->frecv[s], sizeof(double) * 4 * std::max<i64>(h->recv_words[s], 1)));
+    }
+    CUDA_TRY(cudaMalloc(&m->d_recv_cnt_ent, sizeof(i64) * (h->nrecv_total + 1)));
+    m->plan_stale = false;
+    m->pending = m->mig_pending = false;
+    return 0;
+}
+
+// After lpic_halo_plan replaced the plan of a context that already has a communicator (MovingWindow: the neighbour tables
+// change with every shift): new peer table, staging re-sized; the NCCL communicator, stream and events are kept.
+extern "C" int lpic_comm_update(lpic_ctx *c, const int64_t *peer_rank) {
+    DeviceGuard dg(c);
+    REQUIRE(c->comm && c->halo, "lpic_comm_update: no communicator / plan");
+    return alloc_plan_buffers(c, c->comm, peer_rank);
 }
 
 extern "C" int lpic_comm_unique_id(void *id128) {
@@ -140,10 +175,6 @@ extern "C" int lpic_comm_init(lpic_ctx *c, const void *id128, int rank, int nran
     CommState *m = new CommState();
     c->comm = m;
     m->rank = rank; m->nranks = nranks;
-    for (int s = 0; s < h->npeers; s++) {
-        REQUIRE(peer_rank[s] >= 0 && peer_rank[s] < nranks && peer_rank[s] != rank, "bad peer rank in slot %d", s);
-        m->peer_rank[s] = (int)peer_rank[s];
-    }
     ncclUniqueId id;
     memcpy(&id, id128, sizeof(id));
     NCCL_TRY(g_nccl.CommInitRank(&m->comm, nranks, id, rank));
@@ -154,12 +185,8 @@ extern "C" int lpic_comm_init(lpic_ctx *c, const void *id128, int rank, int nran
     CUDA_TRY(cudaEventCreateWithFlags(&m->ev_ppacked, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&m->ev_precv, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&m->ev_punpacked, cudaEventDisableTiming));
-    for (int s = 0; s < h->npeers; s++) {
-        CUDA_TRY(cudaMalloc(&m->fsend[s], sizeof(double) * 4 * std::max<i64>(h->send_words[s], 1)));
-        CUDA_TRY(cudaMalloc(&m->frecv[s], sizeof(double) * 4 * std::max<i64>(h->recv_words[s], 1)));
-    }
+    if (int r = alloc_plan_buffers(c, m, peer_rank)) return r;
     const i64 n = c->g.npatch;
-    CUDA_TRY(cudaMalloc(&m->d_recv_cnt_ent, sizeof(i64) * (h->nrecv_total + 1)));
     CUDA_TRY(cudaMalloc(&m->d_peer_tot, sizeof(i64) * 3 * LPIC_MAX_PEERS));
     CUDA_TRY(cudaMalloc(&m->d_remote_in, sizeof(i64) * n));
     CUDA_TRY(cudaMemset(m->d_remote_in, 0, sizeof(i64) * n));
@@ -182,6 +209,7 @@ extern "C" int lpic_halo_start(lpic_ctx *c, uint32_t mask, int reduce) {
     CommState *m = c->comm;
     HaloPlan *h = c->halo;
     REQUIRE(m && h, "lpic_halo_start: no communicator (lpic_comm_init)");
+    REQUIRE(!m->plan_stale, "lpic_halo_start: the exchange plan changed, call lpic_comm_update first");
     REQUIRE(!m->pending, "lpic_halo_start: the previous exchange has not been waited for");
     int nattr = 0;
     for (int a = 0; a < LPIC_NFIELD; a++) nattr += (mask >> a) & 1;
@@ -285,6 +313,7 @@ extern "C" int lpic_migrate_remote_start(lpic_ctx *c, int ispec, int resume, int
     CommState *m = c->comm;
     HaloPlan *h = c->halo;
     REQUIRE(m && h, "lpic_migrate_remote_start: no communicator (lpic_comm_init)");
+    REQUIRE(!m->plan_stale, "lpic_migrate_remote_start: the exchange plan changed, call lpic_comm_update first");
     REQUIRE(ispec >= 0 && ispec < c->nspec && c->spec[ispec].allocated, "species %d not allocated", ispec);
     REQUIRE(!m->mig_pending, "lpic_migrate_remote_start: the previous particle exchange has not been waited for");
     Species &sp = c->spec[ispec];

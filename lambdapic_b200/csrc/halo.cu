@@ -146,8 +146,14 @@ AttrList attr_list(uint32_t mask) {
 }  // namespace
 
 void lpic_free_comm(lpic_ctx *c);
+void lpic_comm_plan_changed(lpic_ctx *c);
+// the exchange plan alone (lpic_halo_plan replaces it after a MovingWindow shift; the NCCL communicator survives)
+static void free_plan(lpic_ctx *c);
 void lpic_free_peers(lpic_ctx *c) {
-    lpic_free_comm(c);  // the communicator's staging buffers are sized by the plan
+    lpic_free_comm(c);
+    free_plan(c);
+}
+static void free_plan(lpic_ctx *c) {
     HaloPlan *h = c->halo;
     if (!h) return;
     delete[] h->h_send_patch; delete[] h->h_send_b; delete[] h->h_recv_patch; delete[] h->h_recv_b; delete[] h->h_mig_send_cnt;
@@ -163,7 +169,8 @@ extern "C" int lpic_halo_plan(lpic_ctx *c, int npeers, const int64_t *nsend, con
     DeviceGuard dg(c);
     REQUIRE(npeers >= 0 && npeers <= LPIC_MAX_PEERS, "at most %d peer ranks are supported", LPIC_MAX_PEERS);
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    lpic_free_peers(c);
+    free_plan(c);
+    lpic_comm_plan_changed(c);  // an existing communicator keeps its NCCL state; its staging is re-sized by lpic_comm_update
     const Geom &g = c->g;
     HaloPlan *h = new HaloPlan();
     c->halo = h;

@@ -11,7 +11,9 @@ reference; the shift itself works on the host mirrors of the DeviceBridge:
                    is downloaded, no other patch is touched.  The first activation also drops the PMLX faces, which changes
                    the set of CPML instances: that one step takes the download -> re-register -> upload route.
 
-Single rank only: with more than one rank the exchange plan would have to be rebuilt after every shift.
+Several ranks: patches keep their owner; the rotated column positions are allgathered (callback/utils.py:648-716), the
+neighbour tables rebuilt and the inter-rank exchange plan replaced (`sim.mpi.replan()`: lpic_halo_plan + lpic_comm_update,
+the NCCL communicator survives).
 """
 from __future__ import annotations
 
@@ -46,8 +48,6 @@ class MovingWindow:
             self.patch_this_shift = patch_Lx
         if sim.time < self.start_time:
             return
-        if sim.mpi.size > 1:
-            raise NotImplementedError("MovingWindow: single rank only in this round (the inter-GPU exchange plan is static)")
         drop_pmlx = self.num_shifts == 0 and any(m.axis == 0 for p in sim.patches for m in p.pml_boundary)
 
         current_velocity = self.velocity(sim.time) if callable(self.velocity) else self.velocity
@@ -124,20 +124,28 @@ class MovingWindow:
 
     @staticmethod
     def _update_patch_info(sim):
-        """callback/utils.py:648-716 (single rank: the allgather is the identity)."""
+        """callback/utils.py:648-716: every rank learns where every patch sits now (allgather of (position, index, rank)),
+        then the neighbour index / local position / rank tables are rebuilt."""
         ps = sim.patches
-        if sim.dimension == 3:
-            index_map = {(p.ipatch_x, p.ipatch_y, p.ipatch_z): p.index for p in ps}
+        three = sim.dimension == 3
+        local = [((p.ipatch_x, p.ipatch_y) + ((p.ipatch_z,) if three else ()), p.index, p.rank) for p in ps]
+        index_map, rank_map = {}, {}
+        for info in sim.mpi.comm.allgather(local):
+            for pos, idx, r in info:
+                index_map[pos] = idx
+                rank_map[idx] = r
+        if three:
             ps.init_rect_neighbor_index_3d(sim.npatch_x, sim.npatch_y, sim.npatch_z, boundary_conditions=sim.boundary_conditions,
                                            patch_index_map=index_map)
             ps.init_neighbor_ipatch_3d()
-            ps.init_neighbor_rank_3d({p.index: p.rank for p in ps})
+            ps.init_neighbor_rank_3d(rank_map)
         else:
-            index_map = {(p.ipatch_x, p.ipatch_y): p.index for p in ps}
             ps.init_rect_neighbor_index_2d(sim.npatch_x, sim.npatch_y, boundary_conditions=sim.boundary_conditions,
                                            patch_index_map=index_map)
             ps.init_neighbor_ipatch_2d()
-            ps.init_neighbor_rank_2d({p.index: p.rank for p in ps})
+            ps.init_neighbor_rank_2d(rank_map)
+        if sim.mpi.size > 1:
+            sim.mpi.replan()
 
     def _fill_particles(self, sim, new_patches):
         """callback/utils.py:718-840: every species with a density profile is re-initialised in the recycled patches

@@ -61,6 +61,15 @@ def build_plan(grid):
     return peers, s, v
 
 
+def plan_view(patches, rank, nranks):
+    """What build_plan needs, read from the host patch objects (their neighbour tables are the ones MovingWindow updates)."""
+    import types
+    return types.SimpleNamespace(dim=patches.dimension, npatch=patches.npatches, rank=rank, nranks=nranks,
+                                 index=np.array([p.index for p in patches], dtype=np.int64),
+                                 neighbor_index=np.stack([p.neighbor_index for p in patches]).astype(np.int64),
+                                 neighbor_rank=np.stack([p.neighbor_rank for p in patches]).astype(np.int64))
+
+
 def register_plan(eng, grid):
     """Build the exchange plan and hand it to the library (lpic_halo_plan); returns (peers, send, recv, nsend, nrecv)."""
     peers, send, recv = build_plan(grid)
@@ -95,6 +104,15 @@ class NcclExchange:
     @property
     def bytes_sent(self):
         return int(self.L.lpic_comm_bytes_sent(self.eng.ctx))
+
+    def replan(self, grid):
+        """The neighbour tables changed (MovingWindow shift): new exchange plan, staging re-sized; the NCCL communicator is
+        kept (lpic_halo_plan + lpic_comm_update).  `grid`: anything with dim / npatch / index / neighbor_index /
+        neighbor_rank, e.g. :func:`plan_view` of the patches."""
+        self.grid = grid
+        self.peers, self.send_entries, self.recv_entries, self.nsend, self.nrecv = register_plan(self.eng, grid)
+        peer_rank = np.ascontiguousarray(self.peers if self.peers else [0], dtype=np.int64)
+        check(self.L.lpic_comm_update(self.eng.ctx, C.c_void_p(peer_rank.ctypes.data)))
 
     # ---- fields ------------------------------------------------------------------------------------------------------
     def halo_start(self, mask, reduce):
@@ -450,3 +468,7 @@ class MultiRankMPI:
 
     def sync_particles(self, ispec):
         self.sync_particles_start(ispec)
+
+    def replan(self):
+        """Rebuild the exchange plan from the patches' current neighbour tables (after a MovingWindow shift)."""
+        self.xch.replan(plan_view(self.sim.patches, self.rank, self.size))
