@@ -189,10 +189,15 @@ __device__ __forceinline__ void deposit3(const Geom &g, const PatchView &v, cons
                 jxb[kk][j] -= fx * (ay * S0z[kk] + cy * DSz[kk]);
                 jyb[kk] -= fy * (ax * S0z[kk] + cx * DSz[kk]);
                 jzb -= fdz * DSz[kk] * tz;
-                atomicAdd(v.jx + id, jxb[kk][j]);
-                atomicAdd(v.jy + id, jyb[kk]);
-                atomicAdd(v.jz + id, jzb);
-                atomicAdd(v.rho + id, rxy * S1z[kk]);
+                // The running sums end on sum(DS) = 0: the last jx plane / jy row / jz column of the support hold only the
+                // rounding residue of that cancellation (<= 4 eps of the particle's largest term) and are not deposited, like
+                // exact zeros (rho and J vanish where only S0 or only S1 has support).  This kernel is bound by the L2
+                // atomic unit (ncu: lts__d_atomic_input_cycles_active 47 %), so every RED that is not issued counts.
+                const double rho_v = rxy * S1z[kk];
+                if (i != ie - 1 && jxb[kk][j] != 0.0) atomicAdd(v.jx + id, jxb[kk][j]);
+                if (j != je - 1 && jyb[kk] != 0.0) atomicAdd(v.jy + id, jyb[kk]);
+                if (kk != ke - 1 && jzb != 0.0) atomicAdd(v.jz + id, jzb);
+                if (rho_v != 0.0) atomicAdd(v.rho + id, rho_v);
             }
         }
     }
@@ -233,10 +238,11 @@ __device__ __forceinline__ void deposit2(const Geom &g, const PatchView &v, cons
             const double b = S0y[j] + 0.5 * DSy[j];
             jxb[j] -= fxi * b;
             jyb -= fdy * (DSy[j] * a);
-            atomicAdd(v.jx + id, jxb[j]);
-            atomicAdd(v.jy + id, jyb);
-            atomicAdd(v.jz + id, fvz * (a * b + t12 * DSy[j]));
-            atomicAdd(v.rho + id, cd * S1x[i] * S1y[j]);
+            const double jz_v = fvz * (a * b + t12 * DSy[j]), rho_v = cd * S1x[i] * S1y[j];
+            if (i != ie - 1 && jxb[j] != 0.0) atomicAdd(v.jx + id, jxb[j]);  // (last row / column: see deposit3)
+            if (j != je - 1 && jyb != 0.0) atomicAdd(v.jy + id, jyb);
+            if (jz_v != 0.0) atomicAdd(v.jz + id, jz_v);
+            if (rho_v != 0.0) atomicAdd(v.rho + id, rho_v);
         }
     }
 }
