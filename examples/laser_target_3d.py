@@ -21,6 +21,7 @@ from lambdapic_b200 import Electron, GaussianLaser3D, Proton, Simulation3D, c, c
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--nsteps", type=int, default=1001)
+ap.add_argument("--timer", action="store_true", help="per-operator device times (serialises the step)")
 args = ap.parse_args()
 
 um = 1e-6
@@ -42,7 +43,8 @@ def density(n0):
 
 
 laser = GaussianLaser3D(a0=10, w0=2e-6, l0=0.8e-6, ctau=5e-6, focus_position=Lx / 2, x0=10e-6)
-sim = Simulation3D(nx=nx, ny=ny, nz=nz, dx=dx, dy=dy, dz=dz, nsteps=args.nsteps, random_seed=3, store_part_fields=False)
+sim = Simulation3D(nx=nx, ny=ny, nz=nz, dx=dx, dy=dy, dz=dz, nsteps=args.nsteps, random_seed=3, store_part_fields=False,
+                   enable_timer=args.timer)
 ele = Electron(density=density(1 * nc), ppc=2)
 proton = Proton(density=density(1 * nc), ppc=2)
 sim.add_species([ele, proton])
@@ -71,6 +73,10 @@ if __name__ == "__main__":
     t2 = time.perf_counter()
     n_end = sum(int((~pt.is_dead).sum()) for p in sim.patches for pt in p.particles)
     steps = sim.itime
+    if args.timer:
+        from lambdapic_b200.simulation import Timer
+        for name, sec in sorted(Timer.totals.items(), key=lambda kv: -kv[1])[:14]:
+            print(f"  {name:44s} {1e3 * sec / steps:8.3f} ms/step", flush=True)
     st = sim.bridge.stats
     print(f"laser-target-3d {nx}x{ny}x{nz}, {sim.patches.npatches} patches, {npart} particles ({n_end} at the end): "
           f"{steps} steps in {t2 - t1:.2f} s = {steps / (t2 - t1):.2f} steps/s, {0.5 * (npart + n_end) * steps / (t2 - t1):.3e} particle-updates/s "

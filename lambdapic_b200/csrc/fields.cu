@@ -8,6 +8,7 @@
 // HBM roofline note: all four kernels are pure streaming; one thread owns one (patch, cell).
 // Threads run along z (the contiguous axis) so a warp reads 128-256 B runs; neighbours in y/x come from L1/L2.
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 #include "lpic_common.cuh"
 
@@ -143,6 +144,124 @@ __global__ void __launch_bounds__(256) k_update_bfield(Geom g, double *__restric
         bx[o] = __dsub_rn(bx[o], __dmul_rn(dt, cx));
         by[o] = __dsub_rn(by[o], __dmul_rn(dt, cy));
         bz[o] = __dsub_rn(bz[o], __dmul_rn(dt, cz));
+    }
+}
+
+// ---- shared-memory-tiled variants (3D, the default) -----------------------------------------------------------------------
+// One CTA owns FT_X x FT_Y x FT_Z interior cells of one patch.  The three components the curl differentiates are staged in
+// shared memory with their one-cell halo (low side for E <- curl B, high side for B <- curl E) in LOGICAL order: every value
+// is read from global memory once per tile instead of up to four times through L1, and the wrapped-guard index arithmetic is
+// paid per staged value.  The updated component, J and kappa are touched once per cell and stay in global memory.  The
+// arithmetic is the per-cell kernels' (same intrinsics, same association), so the result is bit-identical.
+constexpr int FT_X = 4, FT_Y = 8, FT_Z = 32, FT_THREADS = 256;
+constexpr int FT_HX = FT_X + 1, FT_HY = FT_Y + 1, FT_HZ = FT_Z + 1;
+
+struct FdtdTile {
+    int p, i0, j0, k0;
+};
+__device__ __forceinline__ FdtdTile fdtd_tile(const Geom &g) {
+    const int tz = (g.nz + FT_Z - 1) / FT_Z, ty = (g.ny + FT_Y - 1) / FT_Y, tx = (g.nx + FT_X - 1) / FT_X;
+    int b = blockIdx.x;
+    FdtdTile t;
+    t.k0 = (b % tz) * FT_Z; b /= tz;
+    t.j0 = (b % ty) * FT_Y; b /= ty;
+    t.i0 = (b % tx) * FT_X;
+    t.p = b / tx;
+    return t;
+}
+static unsigned fdtd_tiles(const Geom &g) {
+    return (unsigned)((i64)g.npatch * ((g.nx + FT_X - 1) / FT_X) * ((g.ny + FT_Y - 1) / FT_Y) * ((g.nz + FT_Z - 1) / FT_Z));
+}
+
+// lo = 1: halo on the low side (staged index 0 is logical origin - 1), lo = 0: halo on the high side
+template <int LO>
+__device__ __forceinline__ void stage3(const Geom &g, const double *__restrict__ src, const FdtdTile &t, double (*dst)[FT_HY][FT_HZ]) {
+    for (int idx = threadIdx.x; idx < FT_HX * FT_HY * FT_HZ; idx += FT_THREADS) {
+        const int lz = idx % FT_HZ, ly = (idx / FT_HZ) % FT_HY, lx = idx / (FT_HZ * FT_HY);
+        const int i = t.i0 + lx - LO, j = t.j0 + ly - LO, k = t.k0 + lz - LO;
+        // (cells past the patch's interior + one halo cell are never read)
+        if (i <= g.nx && j <= g.ny && k <= g.nz) dst[lx][ly][lz] = src[sidx(g, i, j, k)];
+    }
+}
+
+__global__ void __launch_bounds__(FT_THREADS) k_update_efield_tiled(Geom g, double *__restrict__ F, double bfactor, double jfactor,
+                                                                    const u8 *__restrict__ is_pml, const double *__restrict__ kappa, int nmax) {
+    __shared__ double sbx[FT_HX][FT_HY][FT_HZ], sby[FT_HX][FT_HY][FT_HZ], sbz[FT_HX][FT_HY][FT_HZ];
+    const FdtdTile t = fdtd_tile(g);
+    const size_t stride = (size_t)g.npatch * g.ncell;
+    double *base = F + (size_t)t.p * g.ncell;
+    double *ex = base + LPIC_EX * stride, *ey = base + LPIC_EY * stride, *ez = base + LPIC_EZ * stride;
+    const double *jx = base + LPIC_JX * stride, *jy = base + LPIC_JY * stride, *jz = base + LPIC_JZ * stride;
+    stage3<1>(g, base + LPIC_BX * stride, t, sbx);
+    stage3<1>(g, base + LPIC_BY * stride, t, sby);
+    stage3<1>(g, base + LPIC_BZ * stride, t, sbz);
+    __syncthreads();
+    const bool pml = is_pml && is_pml[t.p];
+    const double *kp = kappa + (size_t)t.p * 6 * nmax;  // [e|b][axis][nmax], e first
+    for (int c = threadIdx.x; c < FT_X * FT_Y * FT_Z; c += FT_THREADS) {
+        const int lz = c % FT_Z, ly = (c / FT_Z) % FT_Y, lx = c / (FT_Z * FT_Y);
+        const int i = t.i0 + lx, j = t.j0 + ly, k = t.k0 + lz;
+        if (i >= g.nx || j >= g.ny || k >= g.nz) continue;
+        const int o = sidx(g, i, j, k);
+        const double bxc = sbx[lx + 1][ly + 1][lz + 1], byc = sby[lx + 1][ly + 1][lz + 1], bzc = sbz[lx + 1][ly + 1][lz + 1];
+        const double bz_ym = sbz[lx + 1][ly][lz + 1], by_zm = sby[lx + 1][ly + 1][lz], bx_zm = sbx[lx + 1][ly + 1][lz];
+        const double bz_xm = sbz[lx][ly + 1][lz + 1], by_xm = sby[lx][ly + 1][lz + 1], bx_ym = sbx[lx + 1][ly][lz + 1];
+        if (pml) {  // core/boundary/cpml.py:437-457
+            const double bfx = __ddiv_rn(bfactor, kp[i]), bfy = __ddiv_rn(bfactor, kp[nmax + j]), bfz = __ddiv_rn(bfactor, kp[2 * nmax + k]);
+            const double cx = __dsub_rn(__ddiv_rn(__dmul_rn(bfy, __dsub_rn(bzc, bz_ym)), g.dy), __ddiv_rn(__dmul_rn(bfz, __dsub_rn(byc, by_zm)), g.dz));
+            const double cy = __dsub_rn(__ddiv_rn(__dmul_rn(bfz, __dsub_rn(bxc, bx_zm)), g.dz), __ddiv_rn(__dmul_rn(bfx, __dsub_rn(bzc, bz_xm)), g.dx));
+            const double cz = __dsub_rn(__ddiv_rn(__dmul_rn(bfx, __dsub_rn(byc, by_xm)), g.dx), __ddiv_rn(__dmul_rn(bfy, __dsub_rn(bxc, bx_ym)), g.dy));
+            ex[o] = __dadd_rn(ex[o], __dsub_rn(cx, __dmul_rn(jfactor, jx[o])));
+            ey[o] = __dadd_rn(ey[o], __dsub_rn(cy, __dmul_rn(jfactor, jy[o])));
+            ez[o] = __dadd_rn(ez[o], __dsub_rn(cz, __dmul_rn(jfactor, jz[o])));
+        } else {    // core/maxwell/cpu.py:92-97
+            const double cx = __dsub_rn(__ddiv_rn(__dsub_rn(bzc, bz_ym), g.dy), __ddiv_rn(__dsub_rn(byc, by_zm), g.dz));
+            const double cy = __dsub_rn(__ddiv_rn(__dsub_rn(bxc, bx_zm), g.dz), __ddiv_rn(__dsub_rn(bzc, bz_xm), g.dx));
+            const double cz = __dsub_rn(__ddiv_rn(__dsub_rn(byc, by_xm), g.dx), __ddiv_rn(__dsub_rn(bxc, bx_ym), g.dy));
+            ex[o] = __dadd_rn(ex[o], __dsub_rn(__dmul_rn(bfactor, cx), __dmul_rn(jfactor, jx[o])));
+            ey[o] = __dadd_rn(ey[o], __dsub_rn(__dmul_rn(bfactor, cy), __dmul_rn(jfactor, jy[o])));
+            ez[o] = __dadd_rn(ez[o], __dsub_rn(__dmul_rn(bfactor, cz), __dmul_rn(jfactor, jz[o])));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FT_THREADS) k_update_bfield_tiled(Geom g, double *__restrict__ F, double dt, const u8 *__restrict__ is_pml,
+                                                                    const double *__restrict__ kappa, int nmax) {
+    __shared__ double sex[FT_HX][FT_HY][FT_HZ], sey[FT_HX][FT_HY][FT_HZ], sez[FT_HX][FT_HY][FT_HZ];
+    const FdtdTile t = fdtd_tile(g);
+    const size_t stride = (size_t)g.npatch * g.ncell;
+    double *base = F + (size_t)t.p * g.ncell;
+    double *bx = base + LPIC_BX * stride, *by = base + LPIC_BY * stride, *bz = base + LPIC_BZ * stride;
+    stage3<0>(g, base + LPIC_EX * stride, t, sex);
+    stage3<0>(g, base + LPIC_EY * stride, t, sey);
+    stage3<0>(g, base + LPIC_EZ * stride, t, sez);
+    __syncthreads();
+    const bool pml = is_pml && is_pml[t.p];
+    const double *kp = kappa + ((size_t)t.p * 6 + 3) * nmax;
+    for (int c = threadIdx.x; c < FT_X * FT_Y * FT_Z; c += FT_THREADS) {
+        const int lz = c % FT_Z, ly = (c / FT_Z) % FT_Y, lx = c / (FT_Z * FT_Y);
+        const int i = t.i0 + lx, j = t.j0 + ly, k = t.k0 + lz;
+        if (i >= g.nx || j >= g.ny || k >= g.nz) continue;
+        const int o = sidx(g, i, j, k);
+        const double exc = sex[lx][ly][lz], eyc = sey[lx][ly][lz], ezc = sez[lx][ly][lz];
+        const double ez_yp = sez[lx][ly + 1][lz], ey_zp = sey[lx][ly][lz + 1], ex_zp = sex[lx][ly][lz + 1];
+        const double ez_xp = sez[lx + 1][ly][lz], ey_xp = sey[lx + 1][ly][lz], ex_yp = sex[lx][ly + 1][lz];
+        if (pml) {  // core/boundary/cpml.py:459-477
+            const double efx = __ddiv_rn(dt, kp[i]), efy = __ddiv_rn(dt, kp[nmax + j]), efz = __ddiv_rn(dt, kp[2 * nmax + k]);
+            const double cx = __dsub_rn(__ddiv_rn(__dmul_rn(efy, __dsub_rn(ez_yp, ezc)), g.dy), __ddiv_rn(__dmul_rn(efz, __dsub_rn(ey_zp, eyc)), g.dz));
+            const double cy = __dsub_rn(__ddiv_rn(__dmul_rn(efz, __dsub_rn(ex_zp, exc)), g.dz), __ddiv_rn(__dmul_rn(efx, __dsub_rn(ez_xp, ezc)), g.dx));
+            const double cz = __dsub_rn(__ddiv_rn(__dmul_rn(efx, __dsub_rn(ey_xp, eyc)), g.dx), __ddiv_rn(__dmul_rn(efy, __dsub_rn(ex_yp, exc)), g.dy));
+            bx[o] = __dsub_rn(bx[o], cx);
+            by[o] = __dsub_rn(by[o], cy);
+            bz[o] = __dsub_rn(bz[o], cz);
+        } else {    // core/maxwell/cpu.py:131-136
+            const double cx = __dsub_rn(__ddiv_rn(__dsub_rn(ez_yp, ezc), g.dy), __ddiv_rn(__dsub_rn(ey_zp, eyc), g.dz));
+            const double cy = __dsub_rn(__ddiv_rn(__dsub_rn(ex_zp, exc), g.dz), __ddiv_rn(__dsub_rn(ez_xp, ezc), g.dx));
+            const double cz = __dsub_rn(__ddiv_rn(__dsub_rn(ey_xp, eyc), g.dx), __ddiv_rn(__dsub_rn(ex_yp, exc), g.dy));
+            bx[o] = __dsub_rn(bx[o], __dmul_rn(dt, cx));
+            by[o] = __dsub_rn(by[o], __dmul_rn(dt, cy));
+            bz[o] = __dsub_rn(bz[o], __dmul_rn(dt, cz));
+        }
     }
 }
 
@@ -426,7 +545,10 @@ extern "C" int lpic_update_efield(lpic_ctx *c, double dt) {
     const u8 *isp = pm ? pm->d_is_pml : nullptr;
     const double *kap = pm ? pm->d_kappa : nullptr;
     const int nmax = pm ? (int)pm->nmax : 0;
-    if (g.dim == 3)
+    static const bool per_cell = getenv("LPIC_FDTD_PER_CELL") != nullptr;  // A/B switch: the round-1 one-thread-per-cell kernels
+    if (g.dim == 3 && !per_cell)
+        k_update_efield_tiled<<<fdtd_tiles(g), FT_THREADS, 0, c->stream>>>(g, c->fields, bfactor, jfactor, isp, kap, nmax);
+    else if (g.dim == 3)
         k_update_efield<3><<<div_up(n, 256), 256, 0, c->stream>>>(g, c->fields, bfactor, jfactor, isp, kap, nmax);
     else
         k_update_efield<2><<<div_up(n, 256), 256, 0, c->stream>>>(g, c->fields, bfactor, jfactor, isp, kap, nmax);
@@ -443,7 +565,10 @@ extern "C" int lpic_update_bfield(lpic_ctx *c, double dt) {
     const u8 *isp = pm ? pm->d_is_pml : nullptr;
     const double *kap = pm ? pm->d_kappa : nullptr;
     const int nmax = pm ? (int)pm->nmax : 0;
-    if (g.dim == 3)
+    static const bool per_cell = getenv("LPIC_FDTD_PER_CELL") != nullptr;
+    if (g.dim == 3 && !per_cell)
+        k_update_bfield_tiled<<<fdtd_tiles(g), FT_THREADS, 0, c->stream>>>(g, c->fields, dt, isp, kap, nmax);
+    else if (g.dim == 3)
         k_update_bfield<3><<<div_up(n, 256), 256, 0, c->stream>>>(g, c->fields, dt, isp, kap, nmax);
     else
         k_update_bfield<2><<<div_up(n, 256), 256, 0, c->stream>>>(g, c->fields, dt, isp, kap, nmax);

@@ -42,6 +42,7 @@ struct Species {
     i64 *d_off = nullptr, *d_npart = nullptr;                     // device copies
     i64 max_npart = 0;
     bool lists_valid = false;  // migrate.cu: la / lb / out / ndead of the last k_lists still describe the slots ...
+    unsigned long long remote_epoch = ~0ull;  // host-driven inter-rank path: scratch epoch at which prepare / relist built the lists
     unsigned long long lists_epoch = 0;  // ... and nobody else used the shared scratch lists since (lpic_ctx::scratch_epoch)
     i64 max_incoming = -1;  // largest per-patch newcomer count of the last lpic_migrate_count (-1: unknown)
     double *attr[LPIC_NPATTR] = {nullptr};

@@ -334,6 +334,7 @@ extern "C" int lpic_remote_migrate_prepare(lpic_ctx *c, int ispec, int64_t *send
     k_lists<<<(unsigned)n, T, 0, c->stream>>>(a);  // counts + lists in one classification pass
     LAUNCHED(1);
     KERNEL_CHECK();
+    sp.remote_epoch = c->scratch_epoch;  // pack / unpack insist that nobody else used the shared scratch lists in between
     std::vector<i64> out(n * nb);
     CUDA_TRY(cudaMemcpyAsync(out.data(), sp.d_out, sizeof(i64) * n * nb, cudaMemcpyDeviceToHost, c->stream));
     if (ndead) CUDA_TRY(cudaMemcpyAsync(ndead, sp.d_ndead, sizeof(i64) * n, cudaMemcpyDeviceToHost, c->stream));
@@ -362,6 +363,7 @@ extern "C" int lpic_remote_migrate_relist(lpic_ctx *c, int ispec) {
     k_lists<<<(unsigned)c->g.npatch, T, 0, c->stream>>>(a);
     LAUNCHED(1);
     KERNEL_CHECK();
+    c->spec[ispec].remote_epoch = c->scratch_epoch;
     return 0;
 }
 
@@ -370,7 +372,11 @@ extern "C" int lpic_remote_migrate_pack(lpic_ctx *c, int ispec, int slot, double
     HaloPlan *h = c->halo;
     REQUIRE(h && slot >= 0 && slot < h->npeers, "no exchange plan / bad peer slot");
     MigArgs a;
+    const unsigned long long epoch = c->scratch_epoch;
     if (int r = make_args(c, ispec, a)) return r;
+    REQUIRE(c->spec[ispec].remote_epoch == epoch,
+            "lpic_remote_migrate_pack: the leaver lists of lpic_remote_migrate_prepare are stale (another operator used the scratch lists)");
+    c->spec[ispec].remote_epoch = c->scratch_epoch;
     i64 total = 0, mx = 0;
     for (i64 e = h->send_first[slot]; e < h->send_first[slot + 1]; e++) { total += h->h_mig_send_cnt[e]; mx = std::max(mx, h->h_mig_send_cnt[e]); }
     if (nparticles) *nparticles = total;
@@ -390,7 +396,10 @@ extern "C" int lpic_remote_migrate_unpack(lpic_ctx *c, int ispec, const int64_t 
     HaloPlan *h = c->halo;
     REQUIRE(h, "no exchange plan");
     MigArgs a;
+    const unsigned long long epoch = c->scratch_epoch;
     if (int r = make_args(c, ispec, a)) return r;
+    REQUIRE(c->spec[ispec].remote_epoch == epoch,
+            "lpic_remote_migrate_unpack: the dead-slot lists of lpic_remote_migrate_prepare are stale (another operator used the scratch lists)");
     const i64 n = c->g.npatch;
     const int nb = c->g.nb;
     std::vector<i64> rcnt(n * nb, 0), rpoff(n * nb, 0), incoming(n, 0);
