@@ -147,13 +147,13 @@ __global__ void __launch_bounds__(256) k_update_bfield(Geom g, double *__restric
     }
 }
 
-// ---- shared-memory-tiled variants (3D, the default) -----------------------------------------------------------------------
+// ---- shared-memory-tiled variants (3D; selected with LPIC_FDTD_TILED=1, measured slower than the per-cell kernels) -----------------------------------------------------------------------
 // One CTA owns FT_X x FT_Y x FT_Z interior cells of one patch.  The three components the curl differentiates are staged in
 // shared memory with their one-cell halo (low side for E <- curl B, high side for B <- curl E) in LOGICAL order: every value
 // is read from global memory once per tile instead of up to four times through L1, and the wrapped-guard index arithmetic is
 // paid per staged value.  The updated component, J and kappa are touched once per cell and stay in global memory.  The
 // arithmetic is the per-cell kernels' (same intrinsics, same association), so the result is bit-identical.
-constexpr int FT_X = 4, FT_Y = 8, FT_Z = 32, FT_THREADS = 256;
+constexpr int FT_X = 4, FT_Y = 16, FT_Z = 16, FT_THREADS = 256;  // a 16^3 patch is four such tiles
 constexpr int FT_HX = FT_X + 1, FT_HY = FT_Y + 1, FT_HZ = FT_Z + 1;
 
 struct FdtdTile {
@@ -545,7 +545,10 @@ extern "C" int lpic_update_efield(lpic_ctx *c, double dt) {
     const u8 *isp = pm ? pm->d_is_pml : nullptr;
     const double *kap = pm ? pm->d_kappa : nullptr;
     const int nmax = pm ? (int)pm->nmax : 0;
-    static const bool per_cell = getenv("LPIC_FDTD_PER_CELL") != nullptr;  // A/B switch: the round-1 one-thread-per-cell kernels
+    // A/B (256^3 cells, one B200, profiles/r2_fdtd_tiled_ab.txt): the one-thread-per-cell kernel 0.707 ms, the shared-memory tile
+    // 0.818 ms -- every B value is reused at most four times and L1 already serves those re-reads, so the staging pass and its
+    // barrier cost more than they save.  The per-cell kernel stays the default; LPIC_FDTD_TILED=1 selects the tiled one.
+    static const bool per_cell = getenv("LPIC_FDTD_TILED") == nullptr;
     if (g.dim == 3 && !per_cell)
         k_update_efield_tiled<<<fdtd_tiles(g), FT_THREADS, 0, c->stream>>>(g, c->fields, bfactor, jfactor, isp, kap, nmax);
     else if (g.dim == 3)
@@ -565,7 +568,7 @@ extern "C" int lpic_update_bfield(lpic_ctx *c, double dt) {
     const u8 *isp = pm ? pm->d_is_pml : nullptr;
     const double *kap = pm ? pm->d_kappa : nullptr;
     const int nmax = pm ? (int)pm->nmax : 0;
-    static const bool per_cell = getenv("LPIC_FDTD_PER_CELL") != nullptr;
+    static const bool per_cell = getenv("LPIC_FDTD_TILED") == nullptr;  // see lpic_update_efield: 0.526 ms per-cell, 0.602 ms tiled
     if (g.dim == 3 && !per_cell)
         k_update_bfield_tiled<<<fdtd_tiles(g), FT_THREADS, 0, c->stream>>>(g, c->fields, dt, isp, kap, nmax);
     else if (g.dim == 3)

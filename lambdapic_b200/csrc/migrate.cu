@@ -317,9 +317,10 @@ __global__ void __launch_bounds__(T) k_remote_unpack(MigArgs a, const int *__res
 
 extern "C" int lpic_particle_record_words(lpic_ctx *c, int ispec) {
     DeviceGuard dg(c);
-    MigArgs a;
-    if (make_args(c, ispec, a)) return -1;
-    return a.nattr;
+    if (ispec < 0 || ispec >= c->nspec || !c->spec[ispec].allocated) return -1;
+    int n = 0;  // resident attributes (a pure query: it must not touch the scratch epoch between prepare and pack)
+    for (int t = 0; t < LPIC_NPATTR; t++) n += c->spec[ispec].attr[t] != nullptr;
+    return n;
 }
 
 extern "C" int lpic_remote_migrate_prepare(lpic_ctx *c, int ispec, int64_t *send_counts, int64_t *ndead) {

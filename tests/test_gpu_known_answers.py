@@ -219,3 +219,35 @@ def test_shift_by_one_cell_migration_counts(dim):
         lo, hi = pg.x0[ip] - pg.dx / 2, pg.x0[ip] + (pg.nx - 1) * pg.dx + pg.dx / 2
         assert np.all((x[~dead] >= lo) & (x[~dead] <= hi))
     eng.close()
+
+
+@pytest.mark.gpu
+def test_tiled_fdtd_kernels_are_bit_identical_to_the_per_cell_kernels(golden3d):
+    """LPIC_FDTD_TILED=1 (shared-memory-tiled Yee update, csrc/fields.cu) in a subprocess, since the switch is read once per
+    process: E and B after two half steps equal the default per-cell kernels' bit for bit."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from tests import gpu_harness as h\n"
+        "g = np.load(%r)\n"
+        "eng, meta = h.engine_from_golden(g, 't1')\n"
+        "for _ in range(2):\n"
+        "    eng.update_efield(0.5 * meta['dt']); eng.update_bfield(0.5 * meta['dt'])\n"
+        "eng.download_fields()\n"
+        "np.save(sys.argv[1], eng.fields_host[:6].copy())\n"
+        "eng.close()\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                            os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_step_3d.npz"))
+    outs = []
+    for tiled in (False, True):
+        env = dict(os.environ)
+        env.pop("LPIC_FDTD_TILED", None)
+        if tiled:
+            env["LPIC_FDTD_TILED"] = "1"
+        path = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"lpic_fdtd_{int(tiled)}.npy")
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=300)
+        outs.append(np.load(path))
+    assert np.array_equal(outs[0], outs[1])
+    assert np.abs(outs[0]).max() > 0
