@@ -528,6 +528,8 @@ def e2e_public_api(args, wl, rank=0, world=1):
            "h2d_bytes_per_step": int(h2d / steps),
            "d2h_bytes_per_step": int(d2h / steps + 8 * len(hist[0]) * world),
            "steps": steps, "ms_per_step": 1e3 * dt / steps, "setup_s": t_setup,
+           "h2d_seconds": st.get("h2d_seconds", 0.0) - before.get("h2d_seconds", 0.0),
+           "d2h_seconds": st.get("d2h_seconds", 0.0) - before.get("d2h_seconds", 0.0),
            "energy_drift_rel": abs(tot[-1] - tot[0]) / tot[0],
            "workload": f"{wl.cells[0]}x{wl.cells[1]}x{wl.cells[2]} cells, {wl.ppc[0]}+{wl.ppc[1]} ppc ({wl.n_particles()} particles)",
            "mode": "Simulation3D.run(nsteps=K): H2D of all state from pinned host mirrors at entry, K steps with a per-step "

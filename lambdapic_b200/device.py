@@ -254,6 +254,14 @@ class DeviceBridge:
         return mask, psi, particles
 
     def upload(self, names=None):
+        import time
+        t0 = time.perf_counter()
+        try:
+            return self._upload(names)
+        finally:
+            self.stats["h2d_seconds"] = self.stats.get("h2d_seconds", 0.0) + time.perf_counter() - t0
+
+    def _upload(self, names=None):
         ps, eng = self.patches, self.engine
         mask, psi, particles = self._selection(names)
         if not (mask or psi or particles):
@@ -290,6 +298,14 @@ class DeviceBridge:
         self.stats["h2d_bytes"] += int(nbytes)
 
     def download(self, names=None):
+        import time
+        t0 = time.perf_counter()
+        try:
+            return self._download(names)
+        finally:
+            self.stats["d2h_seconds"] = self.stats.get("d2h_seconds", 0.0) + time.perf_counter() - t0
+
+    def _download(self, names=None):
         eng = self.engine
         mask, psi, particles = self._selection(names)
         if not (mask or psi or particles):
