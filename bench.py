@@ -413,6 +413,11 @@ def main():
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6.65 TB/s",
                 "avg_launch_ms": avg_push_ms, "algorithmic_bytes_per_launch": bytes_launch,
                 "share_of_step": eng.nspec * avg_push_ms / (ms.value / args.steps),
+                "per_species": [{"species": ["electron", "proton"][sidx] if eng.nspec == 2 else str(sidx),
+                                 "avg_launch_ms": float(np.mean(push_ms[sidx::eng.nspec])),
+                                 "frac": bytes_launch / (float(np.mean(push_ms[sidx::eng.nspec])) * 1e-3) / 1e9 / peak,
+                                 "first_launch_ms": float(push_ms[sidx]), "last_launch_ms": float(push_ms[-eng.nspec + sidx])}
+                                for sidx in range(eng.nspec)],
                 "fp64": {"achieved_tflops": fp64_achieved, "peak_tflops": fp64_peak.value, "frac": fp64_achieved / max(fp64_peak.value, 1e-9),
                          "flop_per_update": FLOP_PER_UPDATE, "peak_source": "measured by lpic_fp64_peak (DFMA chains, this device, this run)"}}
     try:
