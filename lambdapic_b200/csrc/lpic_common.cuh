@@ -107,6 +107,7 @@ struct lpic_ctx {
     double *scr_buf = nullptr;               // staging for the sort's value move
     i64 scr_cap = 0;
     bool perm_attr_set = false;              // k_cell_perm's dynamic shared-memory limit raised on this context's device
+    bool tile2d_attr_set = false;
     bool tile_attr_set = false;              // same for the tile kernels (push_tile.cu)
     int *d_tile_start = nullptr;             // (npatch, ntile + 1) first position of every tile in the cell-ordered permutation
     size_t tile_start_cap = 0;

@@ -71,7 +71,7 @@ struct TilePermArgs {
     int *nlist;       // per patch
 };
 
-template <int TX, int TY, int TZ>
+template <int TX, int TY, int TZ, int DIM>
 __global__ void __launch_bounds__(PT) k_tile_perm(TilePermArgs a) {
     extern __shared__ int hist[];
     __shared__ int sw[PT / 32];
@@ -85,12 +85,12 @@ __global__ void __launch_bounds__(PT) k_tile_perm(TilePermArgs a) {
     const double x0 = a.x0[p], y0 = a.y0[p], z0 = a.z0[p];
     auto key_of = [&](int ip) -> int {
         if (a.dead[off + ip]) return -1;
-        const double x = a.x[off + ip], y = a.y[off + ip], z = a.z[off + ip];
+        const double x = a.x[off + ip], y = a.y[off + ip], z = DIM == 3 ? a.z[off + ip] : 0.0;
         if (isnan(x) || isnan(y) || isnan(z)) return -1;
         const double ig = a.ig[off + ip];
         const int ix = (int)nearest(grid_coord(half_push(x, a.cdt, ig, a.ux[off + ip]), x0, a.inv_dx));
         const int iy = (int)nearest(grid_coord(half_push(y, a.cdt, ig, a.uy[off + ip]), y0, a.inv_dy));
-        const int iz = (int)nearest(grid_coord(half_push(z, a.cdt, ig, a.uz[off + ip]), z0, a.inv_dz));
+        const int iz = DIM == 3 ? (int)nearest(grid_coord(half_push(z, a.cdt, ig, a.uz[off + ip]), z0, a.inv_dz)) : 0;
         if ((unsigned)ix >= (unsigned)a.nx || (unsigned)iy >= (unsigned)a.ny || (unsigned)iz >= (unsigned)a.nz) return -2;
         const int tx = ix / TX, ty = iy / TY, tz = iz / TZ;
         return ((tx * a.nty + ty) * a.ntz + tz) * TC + ((ix - tx * TX) * TY + (iy - ty * TY)) * TZ + (iz - tz * TZ);
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(NW * 32, TILE_MIN_CTAS) k_push_tile(const Tile
 // The listed particles of every patch: entries tagged LIST_WHOLE_STEP get the whole step with gathers from global memory
 // (they sit in the boundary layer outside the tiles), the others were pushed by k_push_tile and only need the general
 // deposit.  Persistent grid: CTAs stride over the patches, threads over each patch's (short) list.
-template <bool WRITE_PART>
+template <bool WRITE_PART, int DIM>
 __global__ void __launch_bounds__(128) k_list_particles(Geom g, double *__restrict__ F, const double *__restrict__ px0,
                                                         const double *__restrict__ py0, const double *__restrict__ pz0, Slots s,
                                                         const int *__restrict__ list, const int *__restrict__ nlist, double dt,
@@ -449,6 +449,8 @@ __global__ void __launch_bounds__(128) k_list_particles(Geom g, double *__restri
     DepositCoef3 k;
     k.q_dV = q / (g.dx * g.dy * g.dz); k.q_dydzdt = q / (g.dy * g.dz * dt);
     k.q_dxdzdt = q / (g.dx * g.dz * dt); k.q_dxdydt = q / (g.dx * g.dy * dt); k.dt = dt;
+    DepositCoef2 k2;
+    k2.q_dxdy = q / (g.dx * g.dy); k2.q_dydt = q / (g.dy * dt); k2.q_dxdt = q / (g.dx * dt); k2.dt = dt;
     const double cdt = LPIC_C_LIGHT * 0.5 * dt, efactor = q * dt / (2 * m * LPIC_C_LIGHT), bfactor = q * dt / (2 * m);
     for (int p = blockIdx.x; p < g.npatch; p += gridDim.x) {
         const int n = nlist[p];
@@ -457,23 +459,240 @@ __global__ void __launch_bounds__(128) k_list_particles(Geom g, double *__restri
         for (int t = threadIdx.x; t < n; t += blockDim.x) {
             const int e = list[s.off[p] + t];
             const i64 ip = s.off[p] + (e & ~LIST_WHOLE_STEP);
-            double x = s.x[ip], y = s.y[ip], z = s.z[ip], ux = s.ux[ip], uy = s.uy[ip], uz = s.uz[ip], ig = s.ig[ip];
+            double x = s.x[ip], y = s.y[ip], z = DIM == 3 ? s.z[ip] : 0.0, ux = s.ux[ip], uy = s.uy[ip], uz = s.uz[ip], ig = s.ig[ip];
             if (e & LIST_WHOLE_STEP) {
-                x = half_push(x, cdt, ig, ux); y = half_push(y, cdt, ig, uy); z = half_push(z, cdt, ig, uz);
+                x = half_push(x, cdt, ig, ux); y = half_push(y, cdt, ig, uy);
+                if (DIM == 3) z = half_push(z, cdt, ig, uz);
                 double eb[6];
-                gather_eb<3>(g, v, x, y, z, eb);
+                gather_eb<DIM>(g, v, x, y, z, eb);
                 if (WRITE_PART) {
 #pragma unroll
                     for (int c = 0; c < 6; c++) s.part[c][ip] = eb[c];
                 }
                 boris_kick(ux, uy, uz, ig, eb, efactor, bfactor);
                 s.ux[ip] = ux; s.uy[ip] = uy; s.uz[ip] = uz; s.ig[ip] = ig;
-                x += cdt * ig * ux; y += cdt * ig * uy; z += cdt * ig * uz;
-                s.x[ip] = x; s.y[ip] = y; s.z[ip] = z;
+                x += cdt * ig * ux; y += cdt * ig * uy;
+                s.x[ip] = x; s.y[ip] = y;
+                if (DIM == 3) { z += cdt * ig * uz; s.z[ip] = z; }
             }
-            deposit3(g, v, k, x, y, z, ux, uy, uz, ig, s.w[ip]);
+            if (DIM == 3) deposit3(g, v, k, x, y, z, ux, uy, uz, ig, s.w[ip]);
+            else deposit2(g, v, k2, x, y, ux, uy, uz, ig, s.w[ip]);
         }
     }
+}
+
+// ---- 2D twin -----------------------------------------------------------------------------------------------------------
+// Same organisation in two dimensions (reference: core/pusher/unified/unified_pusher_2d.c:157-330,
+// core/current/current_deposit.h:150-268): tile = TX x TY cells (y contiguous), 6 x 9 gather points from the staged tile
+// (the three y-neighbours of a stencil row as an aligned LDS.128 + LDS.64), and the whole 3x3 stencil of a particle that
+// stays in its cell is ONE round of the [30][33] reduction tile -- rho 9 rows, jx 6 (the last x row is sum(DSx) = 0 up to
+// rounding), jy 6 (last y column likewise), jz 9 -- with one carried sum per owner lane.
+template <int TX, int TY, int NW, bool WRITE_PART>
+__global__ void __launch_bounds__(NW * 32, 4) k_push_tile2d(const TileArgs a) {
+    constexpr int EX = TX + 3, EY = TY + 4, EN = EX * EY;  // EY: TY + 3 nodes, padded to an even row length
+    constexpr int SX = EY;
+    extern __shared__ __align__(16) double smem[];
+    double *eb = smem;                                            // [6][EX][EY]
+    double *red = smem + 6 * EN + (threadIdx.x >> 5) * (30 * 33);  // this warp's [30][33] reduction tile
+    int *codes = (int *)(smem + 6 * EN + NW * 30 * 33) + (threadIdx.x >> 5) * 32;
+    const Geom &g = a.g;
+    const int p = blockIdx.x / a.ntile, tile = blockIdx.x - p * a.ntile;
+    const int *ts = a.tile_start + (size_t)p * (a.ntile + 1) + tile;
+    const int first = ts[0], last = ts[1];
+    if (first == last) return;
+    const int ty = tile % a.nty, tx = tile / a.nty;
+    const int ox = tx * TX, oy = ty * TY;
+    const size_t stride = (size_t)g.npatch * g.ncell;
+    double *Fp = a.F + (size_t)p * g.ncell;
+    for (int idx = threadIdx.x; idx < EN; idx += NW * 32) {  // stage E/B: nodes [o-2, o+T] per axis, logical order
+        const int ly = idx % EY, lx = idx / EY;
+        const int gx = ox - 2 + lx, gy = oy - 2 + ly;
+        if (gx < g.nx + g.ng && gy < g.ny + g.ng) {
+            const double *src = Fp + wrapneg(gx, g.NX) * g.NY + wrapneg(gy, g.NY);
+#pragma unroll
+            for (int c = 0; c < 6; c++) eb[c * EN + idx] = __ldg(src + c * stride);
+        }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int per = ((last - first + NW * 32 - 1) / (NW * 32)) * 32;
+    const int wfirst = first + warp * per, wlast = min(last, wfirst + per);
+    if (wfirst >= wlast) return;
+    const i64 off = a.s.off[p];
+    const double x0 = a.px0[p], y0 = a.py0[p];
+    // rows: [0,9) rho(i,j)  [9,15) jx(i<2,j)  [15,21) jy(i,j<2)  [21,30) jz(i,j)
+    int comp, si, sj;
+    if (lane < 9) { comp = LPIC_RHO; si = lane / 3; sj = lane - 3 * si; }
+    else if (lane < 15) { comp = LPIC_JX; si = (lane - 9) / 3; sj = (lane - 9) - 3 * si; }
+    else if (lane < 21) { comp = LPIC_JY; si = (lane - 15) >> 1; sj = (lane - 15) & 1; }
+    else { comp = LPIC_JZ; si = (lane - 21) / 3; sj = (lane - 21) - 3 * si; }
+    RowOwner own;
+    own.dst = Fp + comp * stride;
+    own.ax = ox + si - 1; own.ay = oy + sj - 1; own.az = 0;
+    own.NX = g.NX; own.NY = g.NY; own.NZ = 1;
+    const double *row = red + lane * 33;
+    double acc = 0.0;
+    int ccode = -1;
+    for (int t0 = wfirst; t0 < wlast; t0 += 32) {
+        const bool active = t0 + lane < wlast;
+        double x = 0, y = 0, ux = 0, uy = 0, uz = 0, ig = 1, w = 0;
+        int local = 0, cx = 0, cy = 0;
+        if (active) {
+            local = a.perm[off + t0 + lane];
+            const i64 ip = off + local;
+            x = a.s.x[ip]; y = a.s.y[ip];
+            ux = a.s.ux[ip]; uy = a.s.uy[ip]; uz = a.s.uz[ip]; ig = a.s.ig[ip];
+            w = a.s.w[ip];
+            x = half_push(x, a.cdt, ig, ux); y = half_push(y, a.cdt, ig, uy);
+            const double X = grid_coord(x, x0, a.inv_dx), Y = grid_coord(y, y0, a.inv_dy);
+            const double rX = nearest(X), rY = nearest(Y), fX = floor(X), fY = floor(Y);
+            cx = (int)rX; cy = (int)rY;
+            double gx[3], gy0, gy1, gy2, hx[3], hy0, hy1, hy2;
+            spline3(rX - X, gx[0], gx[1], gx[2]); spline3(fX - X + 0.5, hx[0], hx[1], hx[2]);
+            spline3(rY - Y, gy0, gy1, gy2); spline3(fY - Y + 0.5, hy0, hy1, hy2);
+            const int bgx = (cx - ox + 1) * SX, bhx = ((int)fX - ox + 1) * SX;
+            const ZSplit yg = zsplit(cy - oy + 1, gy0, gy1, gy2), yh = zsplit((int)fY - oy + 1, hy0, hy1, hy2);
+            auto gather9 = [&](const double *t, const double *fx, const ZSplit &ys) -> double {
+                double s = 0.0;
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    const double2 v = *reinterpret_cast<const double2 *>(t + i * SX + ys.pair);
+                    s += fx[i] * (ys.wp0 * v.x + ys.wp1 * v.y + ys.ws * t[i * SX + ys.single]);
+                }
+                return s;
+            };
+            // ex(h,g) ey(g,h) ez(g,g) bx(g,h) by(h,g) bz(h,h)  (unified_pusher_2d.c:120-150)
+            double f[6];
+            f[0] = gather9(eb + 0 * EN + bhx, hx, yg);
+            f[1] = gather9(eb + 1 * EN + bgx, gx, yh);
+            f[2] = gather9(eb + 2 * EN + bgx, gx, yg);
+            f[3] = gather9(eb + 3 * EN + bgx, gx, yh);
+            f[4] = gather9(eb + 4 * EN + bhx, hx, yg);
+            f[5] = gather9(eb + 5 * EN + bhx, hx, yh);
+            if (WRITE_PART) {
+#pragma unroll
+                for (int c = 0; c < 6; c++) a.s.part[c][ip] = f[c];
+            }
+            boris_kick(ux, uy, uz, ig, f, a.efactor, a.bfactor);
+            a.s.ux[ip] = ux; a.s.uy[ip] = uy; a.s.uz[ip] = uz; a.s.ig[ip] = ig;
+            x += a.cdt * ig * ux; y += a.cdt * ig * uy;
+            a.s.x[ip] = x; a.s.y[ip] = y;
+        }
+        // ---- deposit set-up (current_deposit.h:196-222) ----------------------------------------------------------------
+        const double vx = ux * LPIC_C_LIGHT * ig, vy = uy * LPIC_C_LIGHT * ig, vz = uz * LPIC_C_LIGHT * ig;
+        const double X0 = div_rn(x - vx * 0.5 * a.dt - x0, g.dx, a.inv_dx), X1 = div_rn(x + vx * 0.5 * a.dt - x0, g.dx, a.inv_dx);
+        const double Y0 = div_rn(y - vy * 0.5 * a.dt - y0, g.dy, a.inv_dy), Y1 = div_rn(y + vy * 0.5 * a.dt - y0, g.dy, a.inv_dy);
+        const double rX0 = floor(X0 + 0.5), rY0 = floor(Y0 + 0.5);
+        const bool fast = active && floor(X1 + 0.5) == rX0 && floor(Y1 + 0.5) == rY0 && (int)rX0 == cx && (int)rY0 == cy;
+        {
+            const unsigned cm = __ballot_sync(0xffffffffu, active && !fast);
+            if (cm) {
+                int basepos = 0;
+                if (lane == __ffs(cm) - 1) basepos = atomicAdd(&a.nlist[p], __popc(cm));
+                basepos = __shfl_sync(0xffffffffu, basepos, __ffs(cm) - 1);
+                if (active && !fast) a.list[off + basepos + __popc(cm & ((1u << lane) - 1u))] = local;
+            }
+        }
+        const int code = fast ? (cx - ox) * TY + (cy - oy) : -1;
+        const unsigned fm = __ballot_sync(0xffffffffu, fast);
+        if (fm == 0u) continue;
+        const unsigned before = fm & ((1u << lane) - 1u);
+        int pcode = __shfl_sync(0xffffffffu, code, before ? 31 - __clz(before) : 0);
+        if (!before) pcode = ccode;
+        const unsigned heads = __ballot_sync(0xffffffffu, fast && code != pcode);
+        codes[lane] = code;
+        const int lastcode = __shfl_sync(0xffffffffu, code, 31 - __clz(fm));
+        double S0x[3], S0y[3], DSx[3], DSy[3];
+        {
+            double s1[3];
+            spline3(rX0 - X0, S0x[0], S0x[1], S0x[2]); spline3(rX0 - X1, s1[0], s1[1], s1[2]);
+#pragma unroll
+            for (int i = 0; i < 3; i++) DSx[i] = s1[i] - S0x[i];
+            spline3(rY0 - Y0, S0y[0], S0y[1], S0y[2]); spline3(rY0 - Y1, s1[0], s1[1], s1[2]);
+#pragma unroll
+            for (int i = 0; i < 3; i++) DSy[i] = s1[i] - S0y[i];
+        }
+        const double wq = fast ? w : 0.0;
+        // 2D prefactors: q/(dx dy), q/(dy dt), q/(dx dt) (DepositCoef2), passed in q_dV, q_dydzdt, q_dxdzdt
+        const double cd = a.q_dV * wq, fdx = a.q_dydzdt * wq, fdy = a.q_dxdzdt * wq, fvz = cd * vz;
+        const double one_twelfth = 1.0 / 12.0;
+        const double cumy0 = -fdy * DSy[0], cumy1 = cumy0 - fdy * DSy[1];
+        double cumx = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const double ai = S0x[i] + 0.5 * DSx[i], t12 = one_twelfth * DSx[i], rx = cd * (S0x[i] + DSx[i]);
+            cumx -= fdx * DSx[i];
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const double bj = S0y[j] + 0.5 * DSy[j];
+                red[(i * 3 + j) * 33 + lane] = rx * (S0y[j] + DSy[j]);
+                if (i < 2) red[(9 + i * 3 + j) * 33 + lane] = cumx * bj;
+                if (j < 2) red[(15 + i * 2 + j) * 33 + lane] = (j == 0 ? cumy0 : cumy1) * ai;
+                red[(21 + i * 3 + j) * 33 + lane] = fvz * (ai * bj + t12 * DSy[j]);
+            }
+        }
+        __syncwarp();
+        if (lane < 30) acc = row_sum<TY, 1>(acc, heads, row, codes, ccode, own);
+        __syncwarp();
+        ccode = lastcode;
+    }
+    if (lane < 30) flush_cell<TY, 1>(own, ccode, acc);
+}
+
+template <int TX, int TY, int NW>
+int launch_tiles2d(lpic_ctx *c, Species &sp, double dt, double q, double m, bool write_part) {
+    const Geom &g = c->g;
+    constexpr int TC = TX * TY;
+    const int ntx = (g.nx + TX - 1) / TX, nty = (g.ny + TY - 1) / TY;
+    const int ntile = ntx * nty;
+    const size_t perm_smem = sizeof(int) * (size_t)ntile * TC;
+    if (perm_smem > TILE_PERM_SMEM_LIMIT) return 1;
+    if (g.ng < 2) return 1;
+    if (int r = lpic_ensure_scratch(c, sp.total)) return r;
+    const size_t need = (size_t)g.npatch * (ntile + 1);
+    if (need > c->tile_start_cap) {
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_tile_start);
+        c->d_tile_start = nullptr; c->tile_start_cap = 0;
+        CUDA_TRY(cudaMalloc(&c->d_tile_start, sizeof(int) * need));
+        c->tile_start_cap = need;
+    }
+    int *d_nlist = (int *)(c->d_tmp64 + 64 + g.npatch);
+    TilePermArgs pa;
+    pa.x = sp.attr[LPIC_P_X]; pa.y = sp.attr[LPIC_P_Y]; pa.z = sp.attr[LPIC_P_Z];
+    pa.ux = sp.attr[LPIC_P_UX]; pa.uy = sp.attr[LPIC_P_UY]; pa.uz = sp.attr[LPIC_P_UZ]; pa.ig = sp.attr[LPIC_P_INV_GAMMA];
+    pa.dead = sp.dead; pa.off = sp.d_off; pa.npart = sp.d_npart; pa.x0 = c->d_x0; pa.y0 = c->d_y0; pa.z0 = c->d_z0;
+    pa.cdt = LPIC_C_LIGHT * 0.5 * dt; pa.inv_dx = 1.0 / g.dx; pa.inv_dy = 1.0 / g.dy; pa.inv_dz = 1.0;
+    pa.nx = g.nx; pa.ny = g.ny; pa.nz = 1; pa.nty = nty; pa.ntz = 1; pa.ntile = ntile;  // key = (tx * nty + ty) * TC + lx * TY + ly
+    pa.keys = (int *)c->scr_buf;
+    pa.perm = c->scr_b; pa.tile_start = c->d_tile_start; pa.list = c->scr_a; pa.nlist = d_nlist;
+    constexpr size_t push_smem = sizeof(double) * (6 * (TX + 3) * (TY + 4) + NW * 30 * 33) + sizeof(int) * NW * 32;
+    if (!c->tile2d_attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(k_tile_perm<TX, TY, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_PERM_SMEM_LIMIT));
+        CUDA_TRY(cudaFuncSetAttribute(k_push_tile2d<TX, TY, NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)push_smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_push_tile2d<TX, TY, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)push_smem));
+        c->tile2d_attr_set = true;
+    }
+    CUDA_TRY(cudaMemsetAsync(d_nlist, 0, sizeof(int) * g.npatch, c->stream));
+    k_tile_perm<TX, TY, 1, 2><<<g.npatch, PT, perm_smem, c->stream>>>(pa);
+    LAUNCHED(1);
+    TileArgs ta;
+    ta.g = g; ta.F = c->fields; ta.px0 = c->d_x0; ta.py0 = c->d_y0; ta.pz0 = c->d_z0; ta.s = make_slots(sp);
+    ta.perm = c->scr_b; ta.tile_start = c->d_tile_start; ta.list = c->scr_a; ta.nlist = d_nlist;
+    ta.nty = nty; ta.ntz = 1; ta.ntile = ntile;
+    ta.dt = dt; ta.cdt = pa.cdt; ta.efactor = q * dt / (2 * m * LPIC_C_LIGHT); ta.bfactor = q * dt / (2 * m);
+    ta.inv_dx = pa.inv_dx; ta.inv_dy = pa.inv_dy; ta.inv_dz = 1.0;
+    ta.q_dV = q / (g.dx * g.dy); ta.q_dydzdt = q / (g.dy * dt); ta.q_dxdzdt = q / (g.dx * dt); ta.q_dxdydt = 0.0;
+    const unsigned grid = (unsigned)((i64)g.npatch * ntile);
+    if (write_part) k_push_tile2d<TX, TY, NW, true><<<grid, NW * 32, push_smem, c->stream>>>(ta);
+    else k_push_tile2d<TX, TY, NW, false><<<grid, NW * 32, push_smem, c->stream>>>(ta);
+    LAUNCHED(1);
+    const unsigned lgrid = (unsigned)std::min<i64>(g.npatch, 148 * 8);
+    if (write_part) k_list_particles<true, 2><<<lgrid, 128, 0, c->stream>>>(g, c->fields, c->d_x0, c->d_y0, c->d_z0, ta.s, c->scr_a, d_nlist, dt, q, m);
+    else k_list_particles<false, 2><<<lgrid, 128, 0, c->stream>>>(g, c->fields, c->d_x0, c->d_y0, c->d_z0, ta.s, c->scr_a, d_nlist, dt, q, m);
+    LAUNCHED(1);
+    KERNEL_CHECK();
+    return 0;
 }
 
 template <int TX, int TY, int TZ, int NW>
@@ -505,13 +724,13 @@ int launch_tiles(lpic_ctx *c, Species &sp, double dt, double q, double m, bool w
     pa.perm = c->scr_b; pa.tile_start = c->d_tile_start; pa.list = c->scr_a; pa.nlist = d_nlist;
     constexpr size_t push_smem = sizeof(double) * (6 * (TX + 3) * (TY + 3) * (TZ + 4) + NW * 30 * 33) + sizeof(int) * NW * 32;
     if (!c->tile_attr_set) {  // per context: function attributes are per device, and a process may drive several
-        CUDA_TRY(cudaFuncSetAttribute(k_tile_perm<TX, TY, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_PERM_SMEM_LIMIT));
+        CUDA_TRY(cudaFuncSetAttribute(k_tile_perm<TX, TY, TZ, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_PERM_SMEM_LIMIT));
         CUDA_TRY(cudaFuncSetAttribute(k_push_tile<TX, TY, TZ, NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)push_smem));
         CUDA_TRY(cudaFuncSetAttribute(k_push_tile<TX, TY, TZ, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)push_smem));
         c->tile_attr_set = true;
     }
     CUDA_TRY(cudaMemsetAsync(d_nlist, 0, sizeof(int) * g.npatch, c->stream));
-    k_tile_perm<TX, TY, TZ><<<g.npatch, PT, perm_smem, c->stream>>>(pa);
+    k_tile_perm<TX, TY, TZ, 3><<<g.npatch, PT, perm_smem, c->stream>>>(pa);
     LAUNCHED(1);
     TileArgs ta;
     ta.g = g; ta.F = c->fields; ta.px0 = c->d_x0; ta.py0 = c->d_y0; ta.pz0 = c->d_z0; ta.s = make_slots(sp);
@@ -526,8 +745,8 @@ int launch_tiles(lpic_ctx *c, Species &sp, double dt, double q, double m, bool w
     else k_push_tile<TX, TY, TZ, NW, false><<<grid, NW * 32, push_smem, c->stream>>>(ta);
     LAUNCHED(1);
     const unsigned lgrid = (unsigned)std::min<i64>(g.npatch, 148 * 8);
-    if (write_part) k_list_particles<true><<<lgrid, 128, 0, c->stream>>>(g, c->fields, c->d_x0, c->d_y0, c->d_z0, ta.s, c->scr_a, d_nlist, dt, q, m);
-    else k_list_particles<false><<<lgrid, 128, 0, c->stream>>>(g, c->fields, c->d_x0, c->d_y0, c->d_z0, ta.s, c->scr_a, d_nlist, dt, q, m);
+    if (write_part) k_list_particles<true, 3><<<lgrid, 128, 0, c->stream>>>(g, c->fields, c->d_x0, c->d_y0, c->d_z0, ta.s, c->scr_a, d_nlist, dt, q, m);
+    else k_list_particles<false, 3><<<lgrid, 128, 0, c->stream>>>(g, c->fields, c->d_x0, c->d_y0, c->d_z0, ta.s, c->scr_a, d_nlist, dt, q, m);
     LAUNCHED(1);
     KERNEL_CHECK();
     return 0;
@@ -535,11 +754,11 @@ int launch_tiles(lpic_ctx *c, Species &sp, double dt, double q, double m, bool w
 
 }  // namespace
 
-// fused push + deposit, tile kernel (3D); returns 1 if this path does not apply (caller falls back)
+// fused push + deposit, tile kernels (3D and 2D); returns 1 if this path does not apply (caller falls back)
 int lpic_push_deposit_tiles(lpic_ctx *c, int ispec, double dt, double q, double m, bool write_part) {
     const Geom &g = c->g;
     Species &sp = c->spec[ispec];
-    if (g.dim != 3) return 1;
     if (sp.max_npart == 0) return 0;
+    if (g.dim == 2) return launch_tiles2d<8, 16, 4>(c, sp, dt, q, m, write_part);
     return launch_tiles<4, 4, 16, 8>(c, sp, dt, q, m, write_part);
 }
