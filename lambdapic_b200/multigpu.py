@@ -3,9 +3,9 @@ guard / current / particle exchange between ranks over NCCL point-to-point (NVLi
 
 Replaces core/mpi/mpi_manager.py + core/mpi/sync_{fields,particles}_{2d,3d}.c of the reference (MPI_Isend/Irecv per
 (patch, boundary[, attribute])).  Here every phase is: ONE pack kernel per peer -> one ncclSend/ncclRecv pair per peer
-(``torch.distributed.batch_isend_irecv`` on device staging buffers) -> ONE unpack kernel.  Order of exchanges inside a
-step is the reference's (simulation/simulation.py:937-1130): E guards, B guards, [particles pushed], local current
-reduce then remote current reduce, remote migration then local migration, B guards, E guards.
+on persistent device staging buffers -> ONE unpack kernel.  Order of exchanges inside a step is the reference's
+(simulation/simulation.py:937-1130): E guards, B guards, [particles pushed], local current reduce then remote current
+reduce, migration, B guards, E guards.
 
 Two transports share the exchange plan and the pack / unpack kernels:
 
