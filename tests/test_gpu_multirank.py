@@ -76,3 +76,52 @@ def test_exchange_plan_lines_up_between_ranks():
                 assert pb.grid.neighbor_index[q, bq] == pa.grid.index[p]
     for p in progs:
         p.eng.close()
+
+
+def test_emulated_ranks_stay_equal_to_one_rank_over_twenty_steps():
+    """Longer than the golden snapshots reach: a 4x4x2 grid of 8^3 patches, 20 keV, 20 steps on 4 emulated ranks against the
+    same 20 steps on ONE engine (no oracle involved: N ranks = 1 rank).  Particles cross rank boundaries every step, patches
+    grow, the sorters move slots; fields must stay <= 1e-10, particle sets per patch identical, their attributes <= 1e-10."""
+    import torch
+    from lambdapic_b200.multigpu import RankProgram, drive_in_process, torch_alloc
+    from lambdapic_b200.workloads import ThermalPlasma, build_engine
+    from lambdapic_b200._lib import FIELD_ATTRS
+    wl = ThermalPlasma(dim=3, cells=(32, 32, 16), patch=(8, 8, 8), ppc=(4, 2), temperature_eV=2.0e4)
+    nranks, nsteps, rev = 4, 20, [False, False]
+    one = build_engine(wl, rank=0, nranks=1)
+    engines = [build_engine(wl, rank=r, nranks=nranks) for r in range(nranks)]
+    progs = [RankProgram(e, e.grid, torch_alloc(torch.device("cuda", 0))) for e in engines]
+    sent = 0
+    for _ in range(nsteps):
+        one.step(wl.dt, wl.q, wl.m, rev)
+        res = drive_in_process([p.step(wl.dt, wl.q, wl.m, rev) for p in progs])
+        sent += sum(r[1][s]["sent"] for r in res for s in range(2))
+    assert sent > 0
+    one.download_all()
+    where = {int(gp): k for k, gp in enumerate(one.grid.index)}
+    low50 = np.uint64((1 << 50) - 1)  # the ids carry the rank in their top bits
+    worst = 0.0
+    for e in engines:
+        e.download_all()
+        for k, gp in enumerate(e.grid.index):
+            k1 = where[int(gp)]
+            for a in FIELD_ATTRS:
+                ref, got = one.field_view(a, k1), e.field_view(a, k)
+                scale = float(np.abs(ref).max())
+                err = float(np.abs(got - ref).max()) / scale if scale > 0 else 0.0
+                worst = max(worst, err)
+                assert err <= 1e-10, (a, int(gp), err)
+            for s in range(2):
+                m, m1 = e.species[s], one.species[s]
+                alive, alive1 = ~m.view("is_dead", k), ~m1.view("is_dead", k1)
+                ids, ids1 = m.view("_id", k).view(np.uint64)[alive] & low50, m1.view("_id", k1).view(np.uint64)[alive1] & low50
+                assert np.array_equal(np.sort(ids), np.sort(ids1)), ("particle set", int(gp), s)
+                o, o1 = np.argsort(ids), np.argsort(ids1)
+                for a in ("x", "y", "z", "ux", "uy", "uz"):
+                    ref, got = m1.view(a, k1)[alive1][o1], m.view(a, k)[alive][o]
+                    scale = float(np.abs(ref).max()) if ref.size else 0.0
+                    err = float(np.abs(got - ref).max()) / scale if scale > 0 else 0.0
+                    worst = max(worst, err)
+                    assert err <= 1e-10, (a, int(gp), s, err)
+    for e in engines + [one]:
+        e.close()
