@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--cells", type=int, nargs=3, default=None, help="weak: cells per GPU (default 256^3); strong: global cells (default 512^3)")
     ap.add_argument("--ppc", type=int, nargs=2, default=None, help="default 32 32 (weak) / 4 4 (strong)")
     ap.add_argument("--patch", type=int, default=16)
+    ap.add_argument("--temperature", type=float, default=1.0e3, help="eV (default 1 keV; 1e6 makes most particles change cell every step)")
     ap.add_argument("--slot-order", action="store_true", help="use the v1 particle kernel (memory order)")
     ap.add_argument("--breakdown", action="store_true", help="print per-operator CUDA-event times of one extra step to stderr")
     ap.add_argument("--no-e2e", action="store_true")
@@ -66,7 +67,8 @@ def parse():
 def workload(args, nranks):
     from lambdapic_b200.workloads import ThermalPlasma
     if args.scaling == "strong":  # fixed global box, block-partitioned over the ranks
-        return ThermalPlasma(dim=3, cells=tuple(args.cells) if args.cells else (512, 512, 512), patch=(args.patch,) * 3, ppc=tuple(args.ppc))
+        return ThermalPlasma(dim=3, cells=tuple(args.cells) if args.cells else (512, 512, 512), patch=(args.patch,) * 3, ppc=tuple(args.ppc),
+                             temperature_eV=args.temperature)
     per_gpu = tuple(args.cells) if args.cells else (256, 256, 256)
     # weak scaling: the global box doubles along z, then y, then x as ranks double (8 ranks: 2x2x2 blocks)
     mult = [1, 1, 1]
@@ -76,7 +78,7 @@ def workload(args, nranks):
         ax = (ax - 1) % 3
         r //= 2
     cells = tuple(c * m for c, m in zip(per_gpu, mult))
-    return ThermalPlasma(dim=3, cells=cells, patch=(args.patch,) * 3, ppc=tuple(args.ppc))
+    return ThermalPlasma(dim=3, cells=cells, patch=(args.patch,) * 3, ppc=tuple(args.ppc), temperature_eV=args.temperature)
 
 
 class ClockSampler:
@@ -201,7 +203,7 @@ def run_reference(args):
 def config_dict(args, wl, nranks):
     return {"workload": f"BASELINE.json configs[4]: 3D uniform thermal e-/p+ plasma, periodic, {args.scaling} scaling "
                         f"({wl.cells[0]}x{wl.cells[1]}x{wl.cells[2]} cells on {nranks} GPU(s), "
-                        f"{args.ppc[0]}+{args.ppc[1]} ppc, {args.patch}^3-cell patches, 1 keV, fp64)",
+                        f"{args.ppc[0]}+{args.ppc[1]} ppc, {args.patch}^3-cell patches, {args.temperature / 1e3:g} keV, fp64)",
             "cells_global": list(wl.cells), "particles_global": wl.n_particles(), "patch_cells": args.patch,
             "ppc": list(args.ppc), "n_guard": 3, "sorter": "one bucket per cell (--cell-sort experiment)" if args.cell_sort else "x-column buckets (reference default)", "parallelism": f"patch blocks over {nranks} GPU(s)",
             "l2_policy": "inputs larger than L2 (particle arenas are tens of GB; no flush needed)"}
