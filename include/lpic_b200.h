@@ -80,6 +80,13 @@ int lpic_species_layout(const lpic_ctx *ctx, int ispec, int64_t *off, int64_t *p
 /* host = base of an arena with the device's layout (total slots; fp64, or uint8 for LPIC_P_IS_DEAD) */
 int lpic_upload_particles(lpic_ctx *ctx, int ispec, int attr, const void *host);
 int lpic_download_particles(lpic_ctx *ctx, int ispec, int attr, void *host);
+/* The eight per-step attributes (LPIC_P_X .. LPIC_P_INV_GAMMA, bit a of mask = attribute a) in ONE pass: host[a] = base of
+ * the arena-layout array of attribute a (entries of attributes outside mask are not read).  On the device these eight form
+ * 64-byte records; the host side keeps the reference's one-numpy-array-per-attribute layout
+ * (core/particles.py:60-89), so the move is chunked through two staging buffers: the (un)packing kernel of one chunk runs
+ * under the PCIe copies of the other.  This is what Simulation.run's entry / exit copies use. */
+int lpic_upload_particle_records(lpic_ctx *ctx, int ispec, uint32_t mask, const double *const *host);
+int lpic_download_particle_records(lpic_ctx *ctx, int ispec, uint32_t mask, double *const *host);
 int lpic_upload_particle_ptrs(lpic_ctx *ctx, int ispec, int attr, const void *const *host_ptrs);
 int lpic_download_particle_ptrs(lpic_ctx *ctx, int ispec, int attr, void *const *host_ptrs);
 /* ParticlesBase.extend (core/particles.py:141-168) for every patch at once: appends ext[p] dead slots

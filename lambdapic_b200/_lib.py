@@ -43,6 +43,8 @@ SIGNATURES = {
     "lpic_species_layout": (_int, [_vp, _int, _vp, _vp, _vp, _vp]),
     "lpic_upload_particles": (_int, [_vp, _int, _int, _vp]),
     "lpic_download_particles": (_int, [_vp, _int, _int, _vp]),
+    "lpic_upload_particle_records": (_int, [_vp, _int, _u32, _vp]),
+    "lpic_download_particle_records": (_int, [_vp, _int, _u32, _vp]),
     "lpic_upload_particle_ptrs": (_int, [_vp, _int, _int, _vp]),
     "lpic_download_particle_ptrs": (_int, [_vp, _int, _int, _vp]),
     "lpic_species_extend": (_int, [_vp, _int, _vp, _vp, _vp]),

@@ -111,7 +111,12 @@ extern "C" lpic_ctx *lpic_create(int dim, int64_t npatch, int64_t nx, int64_t ny
 }
 
 static void free_species(Species &sp) {
-    for (int a = 0; a < LPIC_NPATTR; a++) { cudaFree(sp.attr[a]); sp.attr[a] = nullptr; }
+    for (int a = 0; a < LPIC_NPATTR; a++) {
+        if (!(sp.rec && a < LPIC_NREC)) cudaFree(sp.attr[a]);  // attr[0..7] point into the record arena when there is one
+        sp.attr[a] = nullptr;
+    }
+    cudaFree(sp.rec); sp.rec = nullptr;
+    sp.pstride = 1;
     cudaFree(sp.dead); sp.dead = nullptr;
     cudaFree(sp.d_off); cudaFree(sp.d_npart); sp.d_off = sp.d_npart = nullptr;
     cudaFree(sp.sort.bucket_count); cudaFree(sp.sort.bound_min); cudaFree(sp.sort.bound_max); cudaFree(sp.sort.pidx);
@@ -125,6 +130,7 @@ static void free_species(Species &sp) {
 
 void lpic_free_peers(lpic_ctx *c);
 void lpic_free_pml(lpic_ctx *c);
+static void free_xfer(lpic_ctx *c);
 int lpic_pml_zero_psi_of(lpic_ctx *c, i64 n, const int64_t *patches);  // fields.cu
 
 extern "C" void lpic_destroy(lpic_ctx *c) {
@@ -135,6 +141,7 @@ extern "C" void lpic_destroy(lpic_ctx *c) {
     delete[] c->spec;
     lpic_free_peers(c);
     lpic_free_pml(c);
+    free_xfer(c);
     cudaFree(c->fields); cudaFree(c->d_x0); cudaFree(c->d_y0); cudaFree(c->d_z0); cudaFree(c->d_nbr); cudaFree(c->d_box);
     cudaFree(c->scr_a); cudaFree(c->scr_b); cudaFree(c->scr_buf); cudaFree(c->d_sort_org); cudaFree(c->d_tmp64); cudaFree(c->d_tmpf); cudaFree(c->d_tile_start); cudaFree(c->d_slice); cudaFree(c->d_slice_k); cudaFree(c->d_laser_i); cudaFree(c->d_laser_s); cudaFree(c->d_sort_hist); cudaFree(c->d_ext_tab); cudaFree(c->d_ext_attrs);
     delete[] c->h_x0; delete[] c->h_y0; delete[] c->h_z0; delete[] c->h_nbr; delete[] c->h_patch_index;
@@ -305,7 +312,14 @@ extern "C" int lpic_species_alloc(lpic_ctx *c, int ispec, const int64_t *npart, 
     }
     sp.total = total;
     const size_t slots = (size_t)std::max<i64>(total, 1);
-    for (int a = 0; a < LPIC_NPATTR; a++)
+    const char *layout = getenv("LPIC_PARTICLE_LAYOUT");  // "soa": eight separate arrays (A/B runs); default: 64-byte records
+    if (!(layout && strcmp(layout, "soa") == 0)) {
+        CUDA_TRY(cudaMalloc(&sp.rec, sizeof(double) * LPIC_NREC * slots));
+        CUDA_TRY(cudaMemsetAsync(sp.rec, 0, sizeof(double) * LPIC_NREC * slots, c->stream));
+        sp.pstride = LPIC_NREC;
+        for (int a = 0; a < LPIC_NREC; a++) sp.attr[a] = sp.rec + a;
+    }
+    for (int a = sp.rec ? LPIC_NREC : 0; a < LPIC_NPATTR; a++)
         if (attr_resident(sp, a)) {
             CUDA_TRY(cudaMalloc(&sp.attr[a], sizeof(double) * slots));
             CUDA_TRY(cudaMemsetAsync(sp.attr[a], 0, sizeof(double) * slots, c->stream));  // no stale bit patterns in unused slots
@@ -348,13 +362,150 @@ static int particle_array(lpic_ctx *c, int ispec, int attr, void **dev, size_t *
     return 0;
 }
 
+// ---- host <-> device moves of the record attributes ------------------------------------------------------------------
+// The host mirrors keep the reference's one-array-per-attribute layout; the device keeps 64-byte records.  Chunks of slots
+// go through two staging buffers [8][chunk] on two auxiliary streams: the (un)packing kernel of one chunk runs under the
+// PCIe copies of the other, and every copy is one contiguous cudaMemcpyAsync per attribute and chunk.
+struct XferState {
+    double *buf[2] = {nullptr, nullptr};
+    i64 chunk = 0;
+    cudaStream_t st[2] = {nullptr, nullptr};
+    cudaEvent_t ev_begin = nullptr, ev_end[2] = {nullptr, nullptr};
+};
+static const i64 kXferChunkMax = 1ll << 21;  // slots per chunk: 2 x 128 MB of staging at most
+
+__global__ void __launch_bounds__(256) k_rec_unpack(const double *__restrict__ rec, i64 first, i64 n, double *__restrict__ stage,
+                                                    i64 chunk, unsigned mask) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double2 *r = reinterpret_cast<const double2 *>(rec + (first + i) * LPIC_NREC);
+    const double2 a = r[0], b = r[1], cc = r[2], d = r[3];
+    const double v[LPIC_NREC] = {a.x, a.y, b.x, b.y, cc.x, cc.y, d.x, d.y};
+#pragma unroll
+    for (int t = 0; t < LPIC_NREC; t++)
+        if (mask >> t & 1u) stage[t * chunk + i] = v[t];
+}
+__global__ void __launch_bounds__(256) k_rec_pack(double *__restrict__ rec, i64 first, i64 n, const double *__restrict__ stage,
+                                                  i64 chunk, unsigned mask) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double *r = rec + (first + i) * LPIC_NREC;
+    if (mask == 0xffu) {
+        double2 *r2 = reinterpret_cast<double2 *>(r);
+        r2[0] = make_double2(stage[i], stage[chunk + i]);
+        r2[1] = make_double2(stage[2 * chunk + i], stage[3 * chunk + i]);
+        r2[2] = make_double2(stage[4 * chunk + i], stage[5 * chunk + i]);
+        r2[3] = make_double2(stage[6 * chunk + i], stage[7 * chunk + i]);
+        return;
+    }
+#pragma unroll
+    for (int t = 0; t < LPIC_NREC; t++)
+        if (mask >> t & 1u) r[t] = stage[t * chunk + i];
+}
+
+static void free_xfer(lpic_ctx *c) {
+    XferState *x = c->xfer;
+    if (!x) return;
+    for (int i = 0; i < 2; i++) {
+        cudaFree(x->buf[i]);
+        if (x->st[i]) cudaStreamDestroy(x->st[i]);
+        if (x->ev_end[i]) cudaEventDestroy(x->ev_end[i]);
+    }
+    if (x->ev_begin) cudaEventDestroy(x->ev_begin);
+    delete x;
+    c->xfer = nullptr;
+}
+
+// host[t] (t in mask) = base of an arena-layout array of attribute t; slots [first, first + nslots) move
+static int xfer_records(lpic_ctx *c, Species &sp, unsigned mask, double *const *host, i64 first, i64 nslots, bool to_device) {
+    if (nslots <= 0 || !(mask & 0xffu)) return 0;
+    if (!c->xfer) c->xfer = new XferState();
+    XferState *x = c->xfer;
+    const i64 want = std::min<i64>(kXferChunkMax, ((nslots + 255) / 256) * 256);
+    if (want > x->chunk) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        for (int i = 0; i < 2; i++) {
+            cudaFree(x->buf[i]);
+            x->buf[i] = nullptr;
+        }
+        x->chunk = 0;
+        for (int i = 0; i < 2; i++) CUDA_TRY(cudaMalloc(&x->buf[i], sizeof(double) * LPIC_NREC * want));
+        x->chunk = want;
+    }
+    if (!x->st[0]) {
+        for (int i = 0; i < 2; i++) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&x->st[i], cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&x->ev_end[i], cudaEventDisableTiming));
+        }
+        CUDA_TRY(cudaEventCreateWithFlags(&x->ev_begin, cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventRecord(x->ev_begin, c->stream));
+    for (int i = 0; i < 2; i++) CUDA_TRY(cudaStreamWaitEvent(x->st[i], x->ev_begin, 0));
+    const i64 ch = x->chunk;
+    int k = 0;
+    for (i64 done = 0; done < nslots; done += ch, k ^= 1) {
+        const i64 n = std::min<i64>(ch, nslots - done), f = first + done;
+        cudaStream_t st = x->st[k];
+        double *B = x->buf[k];
+        if (to_device) {
+            for (int t = 0; t < LPIC_NREC; t++)
+                if (mask >> t & 1u) CUDA_TRY(cudaMemcpyAsync(B + t * ch, host[t] + f, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+            k_rec_pack<<<div_up(n, 256), 256, 0, st>>>(sp.rec, f, n, B, ch, mask & 0xffu);
+        } else {
+            k_rec_unpack<<<div_up(n, 256), 256, 0, st>>>(sp.rec, f, n, B, ch, mask & 0xffu);
+            for (int t = 0; t < LPIC_NREC; t++)
+                if (mask >> t & 1u) CUDA_TRY(cudaMemcpyAsync(host[t] + f, B + t * ch, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+        }
+        LAUNCHED(1);
+    }
+    KERNEL_CHECK();
+    for (int i = 0; i < 2; i++) {
+        CUDA_TRY(cudaEventRecord(x->ev_end[i], x->st[i]));
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, x->ev_end[i], 0));
+    }
+    return 0;
+}
+static int xfer_one(lpic_ctx *c, Species &sp, int attr, void *host, i64 first, i64 nslots, bool to_device) {
+    double *tab[LPIC_NREC] = {nullptr};
+    tab[attr] = (double *)host;
+    return xfer_records(c, sp, 1u << attr, tab, first, nslots, to_device);
+}
+static bool in_record(const Species &sp, int attr) { return sp.rec && attr >= 0 && attr < LPIC_NREC; }
+
 extern "C" int lpic_upload_particles(lpic_ctx *c, int ispec, int attr, const void *host) {
     DeviceGuard dg(c);
     void *dev; size_t esz;
     if (int r = particle_array(c, ispec, attr, &dev, &esz)) return r;
-    CUDA_TRY(cudaMemcpyAsync(dev, host, esz * c->spec[ispec].total, cudaMemcpyHostToDevice, c->stream));
-    c->spec[ispec].sort.valid = false;
-    c->spec[ispec].lists_valid = false;
+    Species &sp = c->spec[ispec];
+    if (in_record(sp, attr)) { if (int r = xfer_one(c, sp, attr, (void *)host, 0, sp.total, true)) return r; }
+    else CUDA_TRY(cudaMemcpyAsync(dev, host, esz * sp.total, cudaMemcpyHostToDevice, c->stream));
+    sp.sort.valid = false;
+    sp.lists_valid = false;
+    return 0;
+}
+// The record attributes named by mask (bit a = attribute a < 8) in one pass: host[a] = base of the arena-layout array of
+// attribute a.  This is what Simulation.run's entry / exit copies use; the per-attribute calls above remain for the rest.
+extern "C" int lpic_upload_particle_records(lpic_ctx *c, int ispec, uint32_t mask, const double *const *host) {
+    DeviceGuard dg(c);
+    REQUIRE(ispec >= 0 && ispec < c->nspec && c->spec[ispec].allocated, "species %d not allocated", ispec);
+    Species &sp = c->spec[ispec];
+    if (sp.rec) { if (int r = xfer_records(c, sp, mask, (double *const *)host, 0, sp.total, true)) return r; }
+    else
+        for (int t = 0; t < LPIC_NREC; t++)
+            if (mask >> t & 1u) CUDA_TRY(cudaMemcpyAsync(sp.attr[t], host[t], sizeof(double) * sp.total, cudaMemcpyHostToDevice, c->stream));
+    sp.sort.valid = false;
+    sp.lists_valid = false;
+    return 0;
+}
+extern "C" int lpic_download_particle_records(lpic_ctx *c, int ispec, uint32_t mask, double *const *host) {
+    DeviceGuard dg(c);
+    REQUIRE(ispec >= 0 && ispec < c->nspec && c->spec[ispec].allocated, "species %d not allocated", ispec);
+    Species &sp = c->spec[ispec];
+    if (sp.rec) { if (int r = xfer_records(c, sp, mask, host, 0, sp.total, false)) return r; }
+    else
+        for (int t = 0; t < LPIC_NREC; t++)
+            if (mask >> t & 1u) CUDA_TRY(cudaMemcpyAsync(host[t], sp.attr[t], sizeof(double) * sp.total, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
     return 0;
 }
 // One patch's slots [off[p], off[p] + npart[p]) of one attribute, from an arena with the device's layout (MovingWindow:
@@ -366,7 +517,8 @@ extern "C" int lpic_upload_particles_patch(lpic_ctx *c, int ispec, int attr, int
     Species &sp = c->spec[ispec];
     REQUIRE(patch >= 0 && patch < c->g.npatch, "bad patch %lld", (long long)patch);
     const size_t first = (size_t)sp.h_off[patch] * esz, bytes = (size_t)sp.h_npart[patch] * esz;
-    if (bytes) CUDA_TRY(cudaMemcpyAsync((char *)dev + first, (const char *)host_arena + first, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (in_record(sp, attr)) { if (int r = xfer_one(c, sp, attr, (void *)host_arena, sp.h_off[patch], sp.h_npart[patch], true)) return r; }
+    else if (bytes) CUDA_TRY(cudaMemcpyAsync((char *)dev + first, (const char *)host_arena + first, bytes, cudaMemcpyHostToDevice, c->stream));
     sp.sort.valid = false;
     sp.lists_valid = false;
     return 0;
@@ -386,18 +538,26 @@ extern "C" int lpic_download_particles(lpic_ctx *c, int ispec, int attr, void *h
     DeviceGuard dg(c);
     void *dev; size_t esz;
     if (int r = particle_array(c, ispec, attr, &dev, &esz)) return r;
-    CUDA_TRY(cudaMemcpyAsync(host, dev, esz * c->spec[ispec].total, cudaMemcpyDeviceToHost, c->stream));
+    Species &sp = c->spec[ispec];
+    if (in_record(sp, attr)) { if (int r = xfer_one(c, sp, attr, host, 0, sp.total, false)) return r; }
+    else CUDA_TRY(cudaMemcpyAsync(host, dev, esz * sp.total, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return 0;
 }
+// per-patch host pointers (ptrs[p] = the patch's own array): a record attribute is staged patch by patch
 extern "C" int lpic_upload_particle_ptrs(lpic_ctx *c, int ispec, int attr, const void *const *ptrs) {
     DeviceGuard dg(c);
     void *dev; size_t esz;
     if (int r = particle_array(c, ispec, attr, &dev, &esz)) return r;
     Species &sp = c->spec[ispec];
-    for (int p = 0; p < c->g.npatch; p++)
-        if (sp.h_npart[p] > 0)
+    for (int p = 0; p < c->g.npatch; p++) {
+        if (sp.h_npart[p] <= 0) continue;
+        if (in_record(sp, attr)) {  // xfer_one indexes host + first: hand it the base such an arena would have
+            if (int r = xfer_one(c, sp, attr, (double *)ptrs[p] - sp.h_off[p], sp.h_off[p], sp.h_npart[p], true)) return r;
+        } else {
             CUDA_TRY(cudaMemcpyAsync((char *)dev + esz * sp.h_off[p], ptrs[p], esz * sp.h_npart[p], cudaMemcpyHostToDevice, c->stream));
+        }
+    }
     sp.sort.valid = false;
     sp.lists_valid = false;
     return 0;
@@ -407,9 +567,14 @@ extern "C" int lpic_download_particle_ptrs(lpic_ctx *c, int ispec, int attr, voi
     void *dev; size_t esz;
     if (int r = particle_array(c, ispec, attr, &dev, &esz)) return r;
     Species &sp = c->spec[ispec];
-    for (int p = 0; p < c->g.npatch; p++)
-        if (sp.h_npart[p] > 0)
+    for (int p = 0; p < c->g.npatch; p++) {
+        if (sp.h_npart[p] <= 0) continue;
+        if (in_record(sp, attr)) {
+            if (int r = xfer_one(c, sp, attr, (double *)ptrs[p] - sp.h_off[p], sp.h_off[p], sp.h_npart[p], false)) return r;
+        } else {
             CUDA_TRY(cudaMemcpyAsync(ptrs[p], (char *)dev + esz * sp.h_off[p], esz * sp.h_npart[p], cudaMemcpyDeviceToHost, c->stream));
+        }
+    }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -417,8 +582,8 @@ extern "C" int lpic_download_particle_ptrs(lpic_ctx *c, int ispec, int attr, voi
 // ParticlesBase.extend (core/particles.py:141-168): new slots are NaN, w = 0, dead, with fresh ids.
 __global__ void __launch_bounds__(256) k_extend_init(int npatch, const i64 *__restrict__ off, const i64 *__restrict__ old_npart,
                                                      const i64 *__restrict__ ext, const u64 *__restrict__ id_first,
-                                                     double *const *attrs, int nattr, int ia_w, int ia_id, u8 *dead,
-                                                     int blocks_per_patch) {
+                                                     double *const *attrs, int nattr, int nrec, int ia_w, int ia_id, u8 *dead,
+                                                     int blocks_per_patch) {  // attrs[a], a < nrec, are indexed with the record stride
     const int p = blockIdx.x / blocks_per_patch;
     const i64 t = (i64)(blockIdx.x - p * blocks_per_patch) * blockDim.x + threadIdx.x;
     if (t >= ext[p]) return;
@@ -428,7 +593,7 @@ __global__ void __launch_bounds__(256) k_extend_init(int npatch, const i64 *__re
         double v = nan;
         if (a == ia_w) v = 0.0;
         if (a == ia_id) v = __longlong_as_double((long long)(id_first[p] + (u64)t));
-        attrs[a][ip] = v;
+        attrs[a][a < nrec ? ip * LPIC_NREC : ip] = v;
     }
     dead[ip] = 1;
 }
@@ -441,6 +606,7 @@ __global__ void __launch_bounds__(256) k_pidx_reset(const i64 *__restrict__ off,
     pidx[off[p] + t] = -1;
 }
 
+struct __align__(16) Rec64 { double2 v[4]; };
 // move every patch segment from the old arena offsets to the new ones (one attribute at a time)
 template <typename T>
 __global__ void __launch_bounds__(256) k_relayout(const T *__restrict__ src, T *__restrict__ dst, const i64 *__restrict__ old_off,
@@ -490,7 +656,19 @@ extern "C" int lpic_species_extend(lpic_ctx *c, int ispec, const int64_t *ext, c
         }
         CUDA_TRY(cudaMemcpyAsync(d_newoff, new_off.data(), sizeof(i64) * n, cudaMemcpyHostToDevice, c->stream));
         const int bpp = (int)div_up(std::max<i64>(sp.max_npart, 1), 256);
-        for (int a = 0; a < LPIC_NPATTR; a++) {
+        if (sp.rec) {  // the record arena moves as 64-byte elements
+            double *fresh = nullptr;
+            CUDA_TRY(cudaMalloc(&fresh, sizeof(Rec64) * total));
+            CUDA_TRY(cudaMemsetAsync(fresh, 0, sizeof(Rec64) * total, c->stream));
+            k_relayout<Rec64><<<(unsigned)((i64)bpp * n), 256, 0, c->stream>>>((const Rec64 *)sp.rec, (Rec64 *)fresh, sp.d_off, d_newoff, sp.d_npart, bpp);
+            LAUNCHED(1);
+            KERNEL_CHECK();
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            cudaFree(sp.rec);
+            sp.rec = fresh;
+            for (int a = 0; a < LPIC_NREC; a++) sp.attr[a] = sp.rec + a;
+        }
+        for (int a = sp.rec ? LPIC_NREC : 0; a < LPIC_NPATTR; a++) {
             if (!attr_resident(sp, a)) continue;
             double *fresh = nullptr;
             CUDA_TRY(cudaMalloc(&fresh, sizeof(double) * total));
@@ -539,7 +717,7 @@ extern "C" int lpic_species_extend(lpic_ctx *c, int ispec, const int64_t *ext, c
     CUDA_TRY(cudaMemcpyAsync(d_attrs, h_attrs, sizeof(double *) * na, cudaMemcpyHostToDevice, c->stream));
     const int bpp = (int)div_up(max_ext, 256);
     k_extend_init<<<(unsigned)((i64)bpp * n), 256, 0, c->stream>>>((int)n, sp.d_off, sp.d_npart, d_ext, d_idf, d_attrs, na,
-                                                                 ia_w, ia_id, sp.dead, bpp);
+                                                                 sp.rec ? LPIC_NREC : 0, ia_w, ia_id, sp.dead, bpp);
     LAUNCHED(1);
     KERNEL_CHECK();
     for (i64 p = 0; p < n; p++) sp.h_npart[p] += ext[p];

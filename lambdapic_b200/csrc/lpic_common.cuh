@@ -45,7 +45,15 @@ struct Species {
     unsigned long long remote_epoch = ~0ull;  // host-driven inter-rank path: scratch epoch at which prepare / relist built the lists
     unsigned long long lists_epoch = 0;  // ... and nobody else used the shared scratch lists since (lpic_ctx::scratch_epoch)
     i64 max_incoming = -1;  // largest per-patch newcomer count of the last lpic_migrate_count (-1: unknown)
+    // Particle layout.  The eight attributes every particle kernel reads or writes (x y z w | ux uy uz inv_gamma, enum order)
+    // live in ONE arena of 64-byte records: a particle is two full 32-byte sectors wherever its slot is, so the fused kernel
+    // costs the same whether the reference's slot order is still cell order or has decayed (SoA: 15 sectors per particle
+    // then).  attr[a] of those eight points INTO the record arena (rec + a) and is indexed with stride pstride = 8; _id and
+    // the optional *_part arrays are plain arrays (stride 1).  LPIC_PARTICLE_LAYOUT=soa at allocation keeps eight separate
+    // arrays (pstride = 1) for A/B runs: every kernel indexes through the stride.
     double *attr[LPIC_NPATTR] = {nullptr};
+    double *rec = nullptr;  // record arena (pstride == 8), owner of attr[0..7]
+    int pstride = 1;
     u8 *dead = nullptr;
     SortState sort;
     // migration bookkeeping (device): per (patch, boundary) leaver counts, per patch dead counts
@@ -130,6 +138,7 @@ struct lpic_ctx {
     const i64 *comm_remote_in = nullptr;  // comm.cu: per-patch remote arrival counts of the exchange in flight
     struct CommState *comm = nullptr;  // NCCL communicator, comm stream, staging buffers (comm.cu), null until lpic_comm_init
     cudaEvent_t *events = nullptr;  // lazily created, 4096 slots
+    struct XferState *xfer = nullptr;  // staging of the host <-> record moves (api.cu), null until first used
 };
 
 // Every entry point runs on its context's device whatever device is current in the calling thread (a process may hold
@@ -146,6 +155,9 @@ struct DeviceGuard {
     DeviceGuard(const DeviceGuard &) = delete;
     DeviceGuard &operator=(const DeviceGuard &) = delete;
 };
+
+#define LPIC_NREC 8  // attributes 0..7 form the record
+inline int attr_stride(const Species &sp, int a) { return a < LPIC_NREC ? sp.pstride : 1; }
 
 inline double *field_ptr(const lpic_ctx *c, int attr) { return c->fields + (size_t)attr * c->g.npatch * c->g.ncell; }
 

@@ -30,17 +30,25 @@ struct MigArgs {
     int *la, *lb;                                  // arena-sized int lists
     int *dirstart;                                 // (npatch, nb)
     double *attrs[LPIC_NPATTR];
+    int astride[LPIC_NPATTR];  // 8 for the attributes inside the record arena, else 1
+    int ps;                    // stride of x, y, z
     int ia_x, ia_y, ia_z;
     double glob[6], cell[3];
 };
 
 __device__ __forceinline__ int classify(const MigArgs &a, const double *bx, i64 ip) {
-    const double x = a.x[ip], y = a.y[ip];
+    double x, y;
+    if (a.ps == LPIC_NREC) {
+        const double2 xy = *reinterpret_cast<const double2 *>(a.x + ip * LPIC_NREC);
+        x = xy.x; y = xy.y;
+    } else {
+        x = a.x[ip]; y = a.y[ip];
+    }
     const int sx = x < bx[0] ? -1 : (x > bx[1] ? 1 : 0);
     const int sy = y < bx[2] ? -1 : (y > bx[3] ? 1 : 0);
     int sz = 0;
     if (a.dim == 3) {
-        const double z = a.z[ip];
+        const double z = a.z[ip * a.ps];
         sz = z < bx[4] ? -1 : (z > bx[5] ? 1 : 0);
     }
     return dir_lookup(a.dim, sx, sy, sz);  // -1 when inside
@@ -92,6 +100,7 @@ __global__ void __launch_bounds__(T) k_lists(MigArgs a) {
     __shared__ int sw[T / 32];
     __shared__ int s_cur[32];
     __shared__ int s_cnt[32];
+    __shared__ signed char s_code[T * 4];
     const int p = blockIdx.x, tid = threadIdx.x;
     const i64 off = a.off[p];
     const int np = (int)a.npart[p];
@@ -104,20 +113,33 @@ __global__ void __launch_bounds__(T) k_lists(MigArgs a) {
         const int ip0 = base + tid * IT;
         bool isdead[IT], leaves[IT];
         int cl = 0, cd = 0;
+        // classified with adjacent lanes on adjacent slots (coalesced for arrays and for 64-byte records alike), handed to the
+        // thread that owns IT consecutive slots through shared memory: 0 = stays (or past the end), 1 = dead, 2 = leaves
+        {
+            const int wbase = base + (tid >> 5) * (32 * IT), lane = tid & 31;
 #pragma unroll
-        for (int j = 0; j < IT; j++) {
-            const int ip = ip0 + j;
-            isdead[j] = leaves[j] = false;
-            if (ip < np) {
-                isdead[j] = a.dead[off + ip] != 0;
-                if (!isdead[j]) {
-                    const int b = classify(a, bx, off + ip);
-                    leaves[j] = b >= 0;
-                    if (b >= 0) atomicAdd(&s_cnt[b], 1);
+            for (int m = 0; m < IT; m++) {
+                const int ip = wbase + 32 * m + lane;
+                signed char code = 0;
+                if (ip < np) {
+                    if (a.dead[off + ip] != 0) code = 1;
+                    else {
+                        const int b = classify(a, bx, off + ip);
+                        if (b >= 0) { code = 2; atomicAdd(&s_cnt[b], 1); }
+                    }
                 }
+                s_code[(tid >> 5) * (32 * IT) + 32 * m + lane] = code;
             }
-            cl += leaves[j];
-            cd += isdead[j];
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < IT; j++) {
+                const signed char code = s_code[tid * IT + j];
+                isdead[j] = code == 1;
+                leaves[j] = code == 2;
+                cl += leaves[j];
+                cd += isdead[j];
+            }
+            __syncwarp();
         }
         int tot;
         int pl = nl + block_incl_sum(cl, sw, tot) - cl;
@@ -193,14 +215,14 @@ __global__ void __launch_bounds__(T) k_fill(MigArgs a, int blocks_per_patch) {
     const i64 dst = a.off[p] + a.la[a.off[p] + np - 1 - (k + skip)];
     const double *bx = a.box + 6 * (size_t)p;
     for (int t = 0; t < a.nattr; t++) {
-        double v = a.attrs[t][src];
+        double v = a.attrs[t][src * a.astride[t]];
         const int d = t == a.ia_x ? 0 : (t == a.ia_y ? 1 : (t == a.ia_z ? 2 : -1));
         if (d >= 0) {  // handle_periodic, :349-363
             const double lo = a.glob[2 * d], hi = a.glob[2 * d + 1], L = hi - lo, c0 = v;
             if (c0 > hi && fabs(bx[2 * d] - lo) < a.cell[d]) v -= L;
             if (c0 < lo && fabs(bx[2 * d + 1] - hi) < a.cell[d]) v += L;
         }
-        a.attrs[t][dst] = v;
+        a.attrs[t][dst * a.astride[t]] = v;
     }
     a.dead[dst] = 0;
 }
@@ -219,9 +241,9 @@ __global__ void __launch_bounds__(T) k_mark(MigArgs a) {
     for (int i = threadIdx.x; i < nl; i += T) {
         const i64 ip = off + a.lb[off + i];
         a.dead[ip] = 1;
-        a.x[ip] = nan;
-        a.y[ip] = nan;
-        if (a.dim == 3) a.z[ip] = nan;
+        if (a.ps == LPIC_NREC) *reinterpret_cast<double2 *>(a.x + ip * LPIC_NREC) = make_double2(nan, nan);
+        else { a.x[ip] = nan; a.y[ip] = nan; }
+        if (a.dim == 3) a.z[ip * a.ps] = nan;
     }
     if (a.dim != 3) return;
     const int nd = (int)a.ndead[p];
@@ -229,9 +251,19 @@ __global__ void __launch_bounds__(T) k_mark(MigArgs a) {
     const int filled = (int)(arrivals < nd ? arrivals : nd);
     for (int k = filled + threadIdx.x; k < nd; k += T) {
         const i64 ip = off + a.la[off + np - 1 - k];
-        a.x[ip] = nan;
-        a.y[ip] = nan;
-        a.z[ip] = nan;
+        if (a.ps == LPIC_NREC) {
+            // almost all of these slots have been dead (and NaN) for many steps: a 24-byte write into a 32-byte sector costs a
+            // read-modify-write in L2 / DRAM, so look first (x y z share the sector) and write only what is not NaN yet
+            double2 *r = reinterpret_cast<double2 *>(a.x + ip * LPIC_NREC);
+            const double2 xy = r[0];
+            const long long nb = 0x7ff8000000000000ll;  // (bit patterns, so that the result is the one an unconditional write gives)
+            if (__double_as_longlong(xy.x) != nb || __double_as_longlong(xy.y) != nb) r[0] = make_double2(nan, nan);
+            if (__double_as_longlong(a.z[ip * LPIC_NREC]) != nb) a.z[ip * LPIC_NREC] = nan;
+        } else {
+            a.x[ip] = nan;
+            a.y[ip] = nan;
+            a.z[ip] = nan;
+        }
     }
 }
 
@@ -253,8 +285,10 @@ int make_args(lpic_ctx *c, int ispec, MigArgs &a) {
         if (t == LPIC_P_X) a.ia_x = a.nattr;
         if (t == LPIC_P_Y) a.ia_y = a.nattr;
         if (t == LPIC_P_Z && g.dim == 3) a.ia_z = a.nattr;
+        a.astride[a.nattr] = attr_stride(sp, t);
         a.attrs[a.nattr++] = sp.attr[t];
     }
+    a.ps = sp.pstride;
     for (int i = 0; i < 6; i++) a.glob[i] = c->glob[i];
     a.cell[0] = g.dx; a.cell[1] = g.dy; a.cell[2] = g.dz;
     return 0;
@@ -275,7 +309,7 @@ __global__ void __launch_bounds__(T) k_remote_pack(MigArgs a, const int *__restr
     const int p = ent_patch[e], b = ent_b[e];
     const i64 src = a.off[p] + a.lb[a.off[p] + a.dirstart[(size_t)p * a.nb + b] + r];
     double *rec = buf + (size_t)(poff[e] + r) * a.nattr;
-    for (int t = 0; t < a.nattr; t++) rec[t] = a.attrs[t][src];
+    for (int t = 0; t < a.nattr; t++) rec[t] = a.attrs[t][src * a.astride[t]];
     a.dead[src] = 1;  // the sender gives the slot up at once (core/mpi/sync_particles_3d.c:573-577)
 }
 
@@ -308,7 +342,7 @@ __global__ void __launch_bounds__(T) k_remote_unpack(MigArgs a, const int *__res
             if (c0 > hi && fabs(bx[2 * d] - lo) < a.cell[d]) v -= L;
             if (c0 < lo && fabs(bx[2 * d + 1] - hi) < a.cell[d]) v += L;
         }
-        a.attrs[t][dst] = v;
+        a.attrs[t][dst * a.astride[t]] = v;
     }
     a.dead[dst] = 0;
 }

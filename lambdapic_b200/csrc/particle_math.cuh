@@ -24,8 +24,9 @@ __device__ __forceinline__ PatchView patch_view(const Geom &g, double *F, const 
     return v;
 }
 
-struct Slots {  // SoA attribute arenas of one species
+struct Slots {  // attribute arenas of one species; x..ig are indexed [slot * ps] (ps = 8: 64-byte records, 1: separate arrays)
     double *x, *y, *z, *w, *ux, *uy, *uz, *ig;
+    int ps;
     double *part[6];
     const u8 *dead;
     const i64 *off, *npart;
@@ -253,6 +254,6 @@ inline Slots make_slots(const Species &sp) {
     s.x = sp.attr[LPIC_P_X]; s.y = sp.attr[LPIC_P_Y]; s.z = sp.attr[LPIC_P_Z]; s.w = sp.attr[LPIC_P_W];
     s.ux = sp.attr[LPIC_P_UX]; s.uy = sp.attr[LPIC_P_UY]; s.uz = sp.attr[LPIC_P_UZ]; s.ig = sp.attr[LPIC_P_INV_GAMMA];
     for (int a = 0; a < 6; a++) s.part[a] = sp.attr[LPIC_P_EX_PART + a];
-    s.dead = sp.dead; s.off = sp.d_off; s.npart = sp.d_npart;
+    s.dead = sp.dead; s.off = sp.d_off; s.npart = sp.d_npart; s.ps = sp.pstride;
     return s;
 }

@@ -38,10 +38,10 @@ __global__ void __launch_bounds__(128) k_particles(Geom g, double *__restrict__ 
     i64 ip;
     if (!my_slot(s, blocks_per_patch, p, ip)) return;
     if (s.dead[ip]) return;
-    double x = s.x[ip], y = s.y[ip], z = DIM == 3 ? s.z[ip] : 0.0;
+    double x = s.x[ip * s.ps], y = s.y[ip * s.ps], z = DIM == 3 ? s.z[ip * s.ps] : 0.0;
     if (MODE != MODE_BORIS && (isnan(x) || isnan(y) || (DIM == 3 && isnan(z)))) return;
     const PatchView v = patch_view(g, F, px0, py0, pz0, p);
-    double ux = s.ux[ip], uy = s.uy[ip], uz = s.uz[ip], ig = s.ig[ip];
+    double ux = s.ux[ip * s.ps], uy = s.uy[ip * s.ps], uz = s.uz[ip * s.ps], ig = s.ig[ip * s.ps];
     const double cdt = LPIC_C_LIGHT * 0.5 * dt;
     if (MODE == MODE_FUSED || MODE == MODE_GATHER || MODE == MODE_BORIS) {
         double eb[6];
@@ -63,20 +63,20 @@ __global__ void __launch_bounds__(128) k_particles(Geom g, double *__restrict__ 
         if (MODE == MODE_GATHER) return;
         const double efactor = q * dt / (2 * m * LPIC_C_LIGHT), bfactor = q * dt / (2 * m);
         boris_kick(ux, uy, uz, ig, eb, efactor, bfactor);
-        s.ux[ip] = ux; s.uy[ip] = uy; s.uz[ip] = uz; s.ig[ip] = ig;
+        s.ux[ip * s.ps] = ux; s.uy[ip * s.ps] = uy; s.uz[ip * s.ps] = uz; s.ig[ip * s.ps] = ig;
         if (MODE == MODE_BORIS) return;
         x += cdt * ig * ux;
         y += cdt * ig * uy;
-        s.x[ip] = x; s.y[ip] = y;
-        if (DIM == 3) { z += cdt * ig * uz; s.z[ip] = z; }
+        s.x[ip * s.ps] = x; s.y[ip * s.ps] = y;
+        if (DIM == 3) { z += cdt * ig * uz; s.z[ip * s.ps] = z; }
     }
     if (MODE == MODE_POSITION) {  // push_position_2d (core/pusher/cpu.py:58-70): x += c*dt*inv_gamma*u
-        s.x[ip] = x + LPIC_C_LIGHT * dt * ig * ux;
-        s.y[ip] = y + LPIC_C_LIGHT * dt * ig * uy;
-        if (DIM == 3) s.z[ip] = z + LPIC_C_LIGHT * dt * ig * uz;
+        s.x[ip * s.ps] = x + LPIC_C_LIGHT * dt * ig * ux;
+        s.y[ip * s.ps] = y + LPIC_C_LIGHT * dt * ig * uy;
+        if (DIM == 3) s.z[ip * s.ps] = z + LPIC_C_LIGHT * dt * ig * uz;
         return;
     }
-    const double w = s.w[ip];
+    const double w = s.w[ip * s.ps];
     if (DIM == 3) {
         DepositCoef3 k;
         k.q_dV = q / (g.dx * g.dy * g.dz); k.q_dydzdt = q / (g.dy * g.dz * dt);
@@ -103,10 +103,10 @@ __global__ void __launch_bounds__(256) k_reduce(Slots s, int blocks_per_patch, i
     unsigned n = 0;
     if (my_slot(s, blocks_per_patch, p, ip) && !s.dead[ip]) {
         n = 1;
-        if (which == 0) { a = s.w[ip]; b = a * s.ux[ip]; }
+        if (which == 0) { a = s.w[ip * s.ps]; b = a * s.ux[ip * s.ps]; }
         if (which == 1) {
-            const double u2 = s.ux[ip] * s.ux[ip] + s.uy[ip] * s.uy[ip] + s.uz[ip] * s.uz[ip];
-            a = s.w[ip] * (u2 / (1.0 + sqrt(1.0 + u2)));  // gamma - 1 without cancellation
+            const double u2 = s.ux[ip * s.ps] * s.ux[ip * s.ps] + s.uy[ip * s.ps] * s.uy[ip * s.ps] + s.uz[ip * s.ps] * s.uz[ip * s.ps];
+            a = s.w[ip * s.ps] * (u2 / (1.0 + sqrt(1.0 + u2)));  // gamma - 1 without cancellation
         }
     }
     a = warp_sum(a);
@@ -142,8 +142,8 @@ __global__ void __launch_bounds__(256) k_init_uniform(Geom g, const double *px0,
     id[ip] = __longlong_as_double((long long)bits);
     if (local >= ncell * ppc) {  // spare capacity: dead slot as ParticlesBase.extend leaves it
         const double nan = __longlong_as_double(0x7ff8000000000000ll);
-        s.x[ip] = nan; s.y[ip] = nan; s.z[ip] = g.dim == 3 ? nan : 0.0;
-        s.ux[ip] = nan; s.uy[ip] = nan; s.uz[ip] = nan; s.ig[ip] = nan; s.w[ip] = 0.0;
+        s.x[ip * s.ps] = nan; s.y[ip * s.ps] = nan; s.z[ip * s.ps] = g.dim == 3 ? nan : 0.0;
+        s.ux[ip * s.ps] = nan; s.uy[ip * s.ps] = nan; s.uz[ip * s.ps] = nan; s.ig[ip * s.ps] = nan; s.w[ip * s.ps] = 0.0;
         dead[ip] = 1;
         return;
     }
@@ -153,18 +153,18 @@ __global__ void __launch_bounds__(256) k_init_uniform(Geom g, const double *px0,
     const double r0 = u01(h); h = mix64(h);
     const double r1 = u01(h); h = mix64(h);
     const double r2 = u01(h); h = mix64(h);
-    s.x[ip] = px0[p] + (i + r0 - 0.5) * g.dx;
-    s.y[ip] = py0[p] + (j + r1 - 0.5) * g.dy;
-    s.z[ip] = g.dim == 3 ? pz0[p] + (k + r2 - 0.5) * g.dz : 0.0;
+    s.x[ip * s.ps] = px0[p] + (i + r0 - 0.5) * g.dx;
+    s.y[ip * s.ps] = py0[p] + (j + r1 - 0.5) * g.dy;
+    s.z[ip * s.ps] = g.dim == 3 ? pz0[p] + (k + r2 - 0.5) * g.dz : 0.0;
     const double a0 = u01(h); h = mix64(h);
     const double a1 = u01(h); h = mix64(h);
     const double a2 = u01(h); h = mix64(h);
     const double a3 = u01(h);
     const double m0 = sqrt(-2.0 * log(a0)), m1 = sqrt(-2.0 * log(a2));
     const double ux = uth * m0 * cospi(2.0 * a1), uy = uth * m0 * sinpi(2.0 * a1), uz = uth * m1 * cospi(2.0 * a3);
-    s.ux[ip] = ux; s.uy[ip] = uy; s.uz[ip] = uz;
-    s.ig[ip] = 1.0 / sqrt(1.0 + ux * ux + uy * uy + uz * uz);
-    s.w[ip] = weight;
+    s.ux[ip * s.ps] = ux; s.uy[ip * s.ps] = uy; s.uz[ip * s.ps] = uz;
+    s.ig[ip * s.ps] = 1.0 / sqrt(1.0 + ux * ux + uy * uy + uz * uz);
+    s.w[ip * s.ps] = weight;
     dead[ip] = 0;
 }
 

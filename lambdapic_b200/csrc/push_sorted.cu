@@ -45,6 +45,7 @@ struct PushConst {
 };
 
 struct PermArgs {
+    int ps;  // stride of the attribute pointers below (8: records, 1: separate arrays)
     const double *x, *y, *z;
     const double *ux, *uy, *uz, *ig;  // predict != 0: order by the cell of x + v dt/2 (where the particle gathers AND where
     double cdt;                       // its deposit starts: x_end - v_new dt/2 == x + v_old dt/2), padded by one cell per side
@@ -82,12 +83,13 @@ __global__ void __launch_bounds__(PT) k_cell_perm(PermArgs a) {
     const double x0 = a.x0[p], y0 = a.y0[p], z0 = a.z0[p];
     auto key_of = [&](int ip) -> int {
         if (a.dead[off + ip]) return -1;
-        const double x = a.x[off + ip], y = a.y[off + ip], z = a.dim == 3 ? a.z[off + ip] : 0.0;
+        const i64 ir = (off + ip) * a.ps;
+        const double x = a.x[ir], y = a.y[ir], z = a.dim == 3 ? a.z[ir] : 0.0;
         if (isnan(x) || isnan(y) || isnan(z)) return -1;
         if (a.predict) {
-            const double h = a.cdt * a.ig[off + ip];
-            const int ix = node_pad(x + h * a.ux[off + ip], x0, a.dx, a.nx), iy = node_pad(y + h * a.uy[off + ip], y0, a.dy, a.ny),
-                      iz = a.dim == 3 ? node_pad(z + h * a.uz[off + ip], z0, a.dz, a.nz) : 0;
+            const double h = a.cdt * a.ig[ir];
+            const int ix = node_pad(x + h * a.ux[ir], x0, a.dx, a.nx), iy = node_pad(y + h * a.uy[ir], y0, a.dy, a.ny),
+                      iz = a.dim == 3 ? node_pad(z + h * a.uz[ir], z0, a.dz, a.nz) : 0;
             return iz + a.kz * (iy + a.ky * ix);
         }
         const int ix = node_of(x, x0, a.dx, a.nx), iy = a.ky > 1 ? node_of(y, y0, a.dy, a.ny) : 0,
@@ -210,9 +212,9 @@ __device__ __forceinline__ void push_body(const Geom &g, double *__restrict__ F,
     if (active) {
         local = perm[off + t];
         ip = off + local;
-        x = s.x[ip]; y = s.y[ip]; z = s.z[ip];
-        ux = s.ux[ip]; uy = s.uy[ip]; uz = s.uz[ip]; ig = s.ig[ip];
-        w = s.w[ip];
+        x = s.x[ip * s.ps]; y = s.y[ip * s.ps]; z = s.z[ip * s.ps];
+        ux = s.ux[ip * s.ps]; uy = s.uy[ip * s.ps]; uz = s.uz[ip * s.ps]; ig = s.ig[ip * s.ps];
+        w = s.w[ip * s.ps];
         x += cdt * ig * ux; y += cdt * ig * uy; z += cdt * ig * uz;
         double eb[6] = {0, 0, 0, 0, 0, 0};
         gather_eb_loop<COMPACT>(g, v, x, y, z, eb, k);
@@ -221,9 +223,9 @@ __device__ __forceinline__ void push_body(const Geom &g, double *__restrict__ F,
             for (int a = 0; a < 6; a++) s.part[a][ip] = eb[a];
         }
         boris_kick(ux, uy, uz, ig, eb, k.efactor, k.bfactor);
-        s.ux[ip] = ux; s.uy[ip] = uy; s.uz[ip] = uz; s.ig[ip] = ig;
+        s.ux[ip * s.ps] = ux; s.uy[ip * s.ps] = uy; s.uz[ip * s.ps] = uz; s.ig[ip * s.ps] = ig;
         x += cdt * ig * ux; y += cdt * ig * uy; z += cdt * ig * uz;
-        s.x[ip] = x; s.y[ip] = y; s.z[ip] = z;
+        s.x[ip * s.ps] = x; s.y[ip * s.ps] = y; s.z[ip * s.ps] = z;
     }
     // ---- deposit set-up (current_deposit.h:341-373) ------------------------------------------------------------
     const double vx = ux * LPIC_C_LIGHT * ig, vy = uy * LPIC_C_LIGHT * ig, vz = uz * LPIC_C_LIGHT * ig;
@@ -380,7 +382,7 @@ __global__ void __launch_bounds__(128) k_deposit_list(Geom g, double *__restrict
         const PatchView v = patch_view(g, F, px0, py0, pz0, p);
         for (int t = threadIdx.x; t < n; t += blockDim.x) {
             const i64 ip = s.off[p] + cross[s.off[p] + t];
-            deposit3(g, v, k, s.x[ip], s.y[ip], s.z[ip], s.ux[ip], s.uy[ip], s.uz[ip], s.ig[ip], s.w[ip]);
+            deposit3(g, v, k, s.x[ip * s.ps], s.y[ip * s.ps], s.z[ip * s.ps], s.ux[ip * s.ps], s.uy[ip * s.ps], s.uz[ip * s.ps], s.ig[ip * s.ps], s.w[ip * s.ps]);
         }
     }
 }
@@ -412,9 +414,9 @@ __global__ void __launch_bounds__(128, 6) k_push_sorted2d(Geom g, double *__rest
     if (active) {
         local = perm[off + t];
         ip = off + local;
-        x = s.x[ip]; y = s.y[ip];
-        ux = s.ux[ip]; uy = s.uy[ip]; uz = s.uz[ip]; ig = s.ig[ip];
-        w = s.w[ip];
+        x = s.x[ip * s.ps]; y = s.y[ip * s.ps];
+        ux = s.ux[ip * s.ps]; uy = s.uy[ip * s.ps]; uz = s.uz[ip * s.ps]; ig = s.ig[ip * s.ps];
+        w = s.w[ip * s.ps];
         x += cdt * ig * ux; y += cdt * ig * uy;
         double eb[6];
         gather_eb<2>(g, v, x, y, 0.0, eb);
@@ -423,9 +425,9 @@ __global__ void __launch_bounds__(128, 6) k_push_sorted2d(Geom g, double *__rest
             for (int a = 0; a < 6; a++) s.part[a][ip] = eb[a];
         }
         boris_kick(ux, uy, uz, ig, eb, k.efactor, k.bfactor);
-        s.ux[ip] = ux; s.uy[ip] = uy; s.uz[ip] = uz; s.ig[ip] = ig;
+        s.ux[ip * s.ps] = ux; s.uy[ip * s.ps] = uy; s.uz[ip * s.ps] = uz; s.ig[ip * s.ps] = ig;
         x += cdt * ig * ux; y += cdt * ig * uy;
-        s.x[ip] = x; s.y[ip] = y;
+        s.x[ip * s.ps] = x; s.y[ip * s.ps] = y;
     }
     // ---- deposit set-up (current_deposit.h:196-222) ----------------------------------------------------------------
     const double vx = ux * LPIC_C_LIGHT * ig, vy = uy * LPIC_C_LIGHT * ig, vz = uz * LPIC_C_LIGHT * ig;
@@ -524,7 +526,7 @@ __global__ void __launch_bounds__(128) k_deposit_list2d(Geom g, double *__restri
         const PatchView v = patch_view(g, F, px0, py0, pz0, p);
         for (int t = threadIdx.x; t < n; t += blockDim.x) {
             const i64 ip = s.off[p] + cross[s.off[p] + t];
-            deposit2(g, v, k, s.x[ip], s.y[ip], s.ux[ip], s.uy[ip], s.uz[ip], s.ig[ip], s.w[ip]);
+            deposit2(g, v, k, s.x[ip * s.ps], s.y[ip * s.ps], s.ux[ip * s.ps], s.uy[ip * s.ps], s.uz[ip * s.ps], s.ig[ip * s.ps], s.w[ip * s.ps]);
         }
     }
 }
@@ -539,7 +541,7 @@ int lpic_push_deposit_sorted(lpic_ctx *c, int ispec, double dt, double q, double
     const bool three = g.dim == 3;
     if (int r = lpic_ensure_scratch(c, sp.total)) return r;
     PermArgs a;
-    a.x = sp.attr[LPIC_P_X]; a.y = sp.attr[LPIC_P_Y]; a.z = sp.attr[LPIC_P_Z]; a.dead = sp.dead;
+    a.x = sp.attr[LPIC_P_X]; a.y = sp.attr[LPIC_P_Y]; a.z = sp.attr[LPIC_P_Z]; a.dead = sp.dead; a.ps = sp.pstride;
     a.off = sp.d_off; a.npart = sp.d_npart; a.x0 = c->d_x0; a.y0 = c->d_y0; a.z0 = c->d_z0;
     a.ux = sp.attr[LPIC_P_UX]; a.uy = sp.attr[LPIC_P_UY]; a.uz = sp.attr[LPIC_P_UZ]; a.ig = sp.attr[LPIC_P_INV_GAMMA];
     a.cdt = LPIC_C_LIGHT * 0.5 * dt;

@@ -58,6 +58,7 @@ __device__ __forceinline__ double div_rn(double n, double d, double r) {
 }
 
 struct TilePermArgs {
+    int ps;  // stride of the attribute pointers (8: 64-byte records, 1: separate arrays)
     const double *x, *y, *z, *ux, *uy, *uz, *ig;
     const u8 *dead;
     const i64 *off, *npart;
@@ -85,12 +86,19 @@ __global__ void __launch_bounds__(PT) k_tile_perm(TilePermArgs a) {
     const double x0 = a.x0[p], y0 = a.y0[p], z0 = a.z0[p];
     auto key_of = [&](int ip) -> int {
         if (a.dead[off + ip]) return -1;
-        const double x = a.x[off + ip], y = a.y[off + ip], z = DIM == 3 ? a.z[off + ip] : 0.0;
+        double x, y, z, ux, uy, uz, ig;
+        if (a.ps == LPIC_NREC) {  // one 64-byte record: four 16-byte loads from one or two lines
+            const double2 *r = reinterpret_cast<const double2 *>(a.x + (off + ip) * LPIC_NREC);
+            const double2 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3);
+            x = r0.x; y = r0.y; z = DIM == 3 ? r1.x : 0.0; ux = r2.x; uy = r2.y; uz = r3.x; ig = r3.y;
+        } else {
+            const i64 ir = (off + ip) * a.ps;
+            x = a.x[ir]; y = a.y[ir]; z = DIM == 3 ? a.z[ir] : 0.0; ux = a.ux[ir]; uy = a.uy[ir]; uz = DIM == 3 ? a.uz[ir] : 0.0; ig = a.ig[ir];
+        }
         if (isnan(x) || isnan(y) || isnan(z)) return -1;
-        const double ig = a.ig[off + ip];
-        const int ix = (int)nearest(grid_coord(half_push(x, a.cdt, ig, a.ux[off + ip]), x0, a.inv_dx));
-        const int iy = (int)nearest(grid_coord(half_push(y, a.cdt, ig, a.uy[off + ip]), y0, a.inv_dy));
-        const int iz = DIM == 3 ? (int)nearest(grid_coord(half_push(z, a.cdt, ig, a.uz[off + ip]), z0, a.inv_dz)) : 0;
+        const int ix = (int)nearest(grid_coord(half_push(x, a.cdt, ig, ux), x0, a.inv_dx));
+        const int iy = (int)nearest(grid_coord(half_push(y, a.cdt, ig, uy), y0, a.inv_dy));
+        const int iz = DIM == 3 ? (int)nearest(grid_coord(half_push(z, a.cdt, ig, uz), z0, a.inv_dz)) : 0;
         if ((unsigned)ix >= (unsigned)a.nx || (unsigned)iy >= (unsigned)a.ny || (unsigned)iz >= (unsigned)a.nz) return -2;
         const int tx = ix / TX, ty = iy / TY, tz = iz / TZ;
         return ((tx * a.nty + ty) * a.ntz + tz) * TC + ((ix - tx * TX) * TY + (iy - ty * TY)) * TZ + (iz - tz * TZ);
@@ -150,6 +158,7 @@ __global__ void __launch_bounds__(PT) k_tile_perm(TilePermArgs a) {
 struct TileArgs {
     Geom g;
     double *F;
+    double *rec;  // records (x y z w | ux uy uz inv_gamma) of 64 bytes per slot, REC kernels only
     const double *px0, *py0, *pz0;
     Slots s;
     const int *perm, *tile_start;
@@ -259,7 +268,7 @@ __device__ __noinline__ double row_sum(double acc, unsigned heads, const double 
     return acc;
 }
 
-template <int TX, int TY, int TZ, int NW, bool WRITE_PART>
+template <int TX, int TY, int TZ, int NW, bool WRITE_PART, bool REC>
 __global__ void __launch_bounds__(NW * 32, TILE_MIN_CTAS) k_push_tile(const TileArgs a) {
     constexpr int EX = TX + 3, EY = TY + 3, EZ = TZ + 4, EN = EX * EY * EZ;  // EZ: TZ + 3 nodes, padded to an even row length
     constexpr int SX = EY * EZ, SY = EZ;  // strides (in doubles) of the staged tile
@@ -310,12 +319,32 @@ __global__ void __launch_bounds__(NW * 32, TILE_MIN_CTAS) k_push_tile(const Tile
         const bool active = t0 + lane < wlast;
         double x = 0, y = 0, z = 0, ux = 0, uy = 0, uz = 0, ig = 1, w = 0;
         int local = 0, cx = 0, cy = 0, cz = 0;
+        if (active) local = a.perm[off + t0 + lane];
+        if (REC) {
+            // A quad of lanes fetches one 64-byte record per load instruction (lane q of quad Q: piece q of particle 4Q + j), so
+            // a warp-level load touches 8 records = 16 full sectors however the slots are ordered.  The pieces go through the
+            // warp's (idle) reduction tile, 80 bytes per particle: conflict-free for the quad stores and for the owners' loads.
+            const int q = lane & 3, qb = lane & ~3;
+            double2 *stg = reinterpret_cast<double2 *>(red);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int P = qb + j;
+                if (t0 + P < wlast) stg[P * 5 + q] = __ldg(reinterpret_cast<const double2 *>(a.rec + (off + a.perm[off + t0 + P]) * LPIC_NREC) + q);
+            }
+            __syncwarp();
+            if (active) {
+                const double2 r0 = stg[lane * 5], r1 = stg[lane * 5 + 1], r2 = stg[lane * 5 + 2], r3 = stg[lane * 5 + 3];
+                x = r0.x; y = r0.y; z = r1.x; w = r1.y; ux = r2.x; uy = r2.y; uz = r3.x; ig = r3.y;
+            }
+            __syncwarp();
+        }
         if (active) {
-            local = a.perm[off + t0 + lane];
             const i64 ip = off + local;
-            x = a.s.x[ip]; y = a.s.y[ip]; z = a.s.z[ip];
-            ux = a.s.ux[ip]; uy = a.s.uy[ip]; uz = a.s.uz[ip]; ig = a.s.ig[ip];
-            w = a.s.w[ip];
+            if (!REC) {
+                x = a.s.x[ip * a.s.ps]; y = a.s.y[ip * a.s.ps]; z = a.s.z[ip * a.s.ps];
+                ux = a.s.ux[ip * a.s.ps]; uy = a.s.uy[ip * a.s.ps]; uz = a.s.uz[ip * a.s.ps]; ig = a.s.ig[ip * a.s.ps];
+                w = a.s.w[ip * a.s.ps];
+            }
             x = half_push(x, a.cdt, ig, ux); y = half_push(y, a.cdt, ig, uy); z = half_push(z, a.cdt, ig, uz);
             const double X = grid_coord(x, x0, a.inv_dx), Y = grid_coord(y, y0, a.inv_dy), Z = grid_coord(z, z0, a.inv_dz);
             const double rX = nearest(X), rY = nearest(Y), rZ = nearest(Z), fX = floor(X), fY = floor(Y), fZ = floor(Z);
@@ -342,9 +371,26 @@ __global__ void __launch_bounds__(NW * 32, TILE_MIN_CTAS) k_push_tile(const Tile
                 for (int c = 0; c < 6; c++) a.s.part[c][ip] = f[c];
             }
             boris_kick(ux, uy, uz, ig, f, a.efactor, a.bfactor);
-            a.s.ux[ip] = ux; a.s.uy[ip] = uy; a.s.uz[ip] = uz; a.s.ig[ip] = ig;
             x += a.cdt * ig * ux; y += a.cdt * ig * uy; z += a.cdt * ig * uz;
-            a.s.x[ip] = x; a.s.y[ip] = y; a.s.z[ip] = z;
+            if (!REC) {
+                a.s.ux[ip * a.s.ps] = ux; a.s.uy[ip * a.s.ps] = uy; a.s.uz[ip * a.s.ps] = uz; a.s.ig[ip * a.s.ps] = ig;
+                a.s.x[ip * a.s.ps] = x; a.s.y[ip * a.s.ps] = y; a.s.z[ip * a.s.ps] = z;
+            }
+        }
+        if (REC) {  // whole records back (w unchanged): every store instruction writes full 32-byte sectors
+            const int q = lane & 3, qb = lane & ~3;
+            double2 *stg = reinterpret_cast<double2 *>(red);
+            if (active) {
+                stg[lane * 5] = make_double2(x, y); stg[lane * 5 + 1] = make_double2(z, w);
+                stg[lane * 5 + 2] = make_double2(ux, uy); stg[lane * 5 + 3] = make_double2(uz, ig);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int P = qb + j;
+                if (t0 + P < wlast) reinterpret_cast<double2 *>(a.rec + (off + a.perm[off + t0 + P]) * LPIC_NREC)[q] = stg[P * 5 + q];
+            }
+            __syncwarp();  // the deposit below reuses the tile
         }
         // ---- deposit set-up (current_deposit.h:341-373): the path from x - v dt/2 to x + v dt/2 ------------------------
         // Same expressions as the reference (and k_particles): a slow particle's current is proportional to X1 - X0, the
@@ -459,7 +505,14 @@ __global__ void __launch_bounds__(128) k_list_particles(Geom g, double *__restri
         for (int t = threadIdx.x; t < n; t += blockDim.x) {
             const int e = list[s.off[p] + t];
             const i64 ip = s.off[p] + (e & ~LIST_WHOLE_STEP);
-            double x = s.x[ip], y = s.y[ip], z = DIM == 3 ? s.z[ip] : 0.0, ux = s.ux[ip], uy = s.uy[ip], uz = s.uz[ip], ig = s.ig[ip];
+            double x, y, z, ux, uy, uz, ig, w;
+            double2 *r = reinterpret_cast<double2 *>(s.x + ip * LPIC_NREC);  // (records only)
+            if (s.ps == LPIC_NREC) {
+                const double2 r0 = r[0], r1 = r[1], r2 = r[2], r3 = r[3];
+                x = r0.x; y = r0.y; z = DIM == 3 ? r1.x : 0.0; w = r1.y; ux = r2.x; uy = r2.y; uz = r3.x; ig = r3.y;
+            } else {
+                x = s.x[ip]; y = s.y[ip]; z = DIM == 3 ? s.z[ip] : 0.0; ux = s.ux[ip]; uy = s.uy[ip]; uz = s.uz[ip]; ig = s.ig[ip]; w = s.w[ip];
+            }
             if (e & LIST_WHOLE_STEP) {
                 x = half_push(x, cdt, ig, ux); y = half_push(y, cdt, ig, uy);
                 if (DIM == 3) z = half_push(z, cdt, ig, uz);
@@ -470,13 +523,20 @@ __global__ void __launch_bounds__(128) k_list_particles(Geom g, double *__restri
                     for (int c = 0; c < 6; c++) s.part[c][ip] = eb[c];
                 }
                 boris_kick(ux, uy, uz, ig, eb, efactor, bfactor);
-                s.ux[ip] = ux; s.uy[ip] = uy; s.uz[ip] = uz; s.ig[ip] = ig;
                 x += cdt * ig * ux; y += cdt * ig * uy;
-                s.x[ip] = x; s.y[ip] = y;
-                if (DIM == 3) { z += cdt * ig * uz; s.z[ip] = z; }
+                if (DIM == 3) z += cdt * ig * uz;
+                if (s.ps == LPIC_NREC) {
+                    r[0] = make_double2(x, y);
+                    if (DIM == 3) r[1] = make_double2(z, w);
+                    r[2] = make_double2(ux, uy); r[3] = make_double2(uz, ig);
+                } else {
+                    s.ux[ip] = ux; s.uy[ip] = uy; s.uz[ip] = uz; s.ig[ip] = ig;
+                    s.x[ip] = x; s.y[ip] = y;
+                    if (DIM == 3) s.z[ip] = z;
+                }
             }
-            if (DIM == 3) deposit3(g, v, k, x, y, z, ux, uy, uz, ig, s.w[ip]);
-            else deposit2(g, v, k2, x, y, ux, uy, uz, ig, s.w[ip]);
+            if (DIM == 3) deposit3(g, v, k, x, y, z, ux, uy, uz, ig, w);
+            else deposit2(g, v, k2, x, y, ux, uy, uz, ig, w);
         }
     }
 }
@@ -540,9 +600,9 @@ __global__ void __launch_bounds__(NW * 32, 4) k_push_tile2d(const TileArgs a) {
         if (active) {
             local = a.perm[off + t0 + lane];
             const i64 ip = off + local;
-            x = a.s.x[ip]; y = a.s.y[ip];
-            ux = a.s.ux[ip]; uy = a.s.uy[ip]; uz = a.s.uz[ip]; ig = a.s.ig[ip];
-            w = a.s.w[ip];
+            x = a.s.x[ip * a.s.ps]; y = a.s.y[ip * a.s.ps];
+            ux = a.s.ux[ip * a.s.ps]; uy = a.s.uy[ip * a.s.ps]; uz = a.s.uz[ip * a.s.ps]; ig = a.s.ig[ip * a.s.ps];
+            w = a.s.w[ip * a.s.ps];
             x = half_push(x, a.cdt, ig, ux); y = half_push(y, a.cdt, ig, uy);
             const double X = grid_coord(x, x0, a.inv_dx), Y = grid_coord(y, y0, a.inv_dy);
             const double rX = nearest(X), rY = nearest(Y), fX = floor(X), fY = floor(Y);
@@ -574,9 +634,9 @@ __global__ void __launch_bounds__(NW * 32, 4) k_push_tile2d(const TileArgs a) {
                 for (int c = 0; c < 6; c++) a.s.part[c][ip] = f[c];
             }
             boris_kick(ux, uy, uz, ig, f, a.efactor, a.bfactor);
-            a.s.ux[ip] = ux; a.s.uy[ip] = uy; a.s.uz[ip] = uz; a.s.ig[ip] = ig;
+            a.s.ux[ip * a.s.ps] = ux; a.s.uy[ip * a.s.ps] = uy; a.s.uz[ip * a.s.ps] = uz; a.s.ig[ip * a.s.ps] = ig;
             x += a.cdt * ig * ux; y += a.cdt * ig * uy;
-            a.s.x[ip] = x; a.s.y[ip] = y;
+            a.s.x[ip * a.s.ps] = x; a.s.y[ip * a.s.ps] = y;
         }
         // ---- deposit set-up (current_deposit.h:196-222) ----------------------------------------------------------------
         const double vx = ux * LPIC_C_LIGHT * ig, vy = uy * LPIC_C_LIGHT * ig, vz = uz * LPIC_C_LIGHT * ig;
@@ -661,7 +721,7 @@ int launch_tiles2d(lpic_ctx *c, Species &sp, double dt, double q, double m, bool
     TilePermArgs pa;
     pa.x = sp.attr[LPIC_P_X]; pa.y = sp.attr[LPIC_P_Y]; pa.z = sp.attr[LPIC_P_Z];
     pa.ux = sp.attr[LPIC_P_UX]; pa.uy = sp.attr[LPIC_P_UY]; pa.uz = sp.attr[LPIC_P_UZ]; pa.ig = sp.attr[LPIC_P_INV_GAMMA];
-    pa.dead = sp.dead; pa.off = sp.d_off; pa.npart = sp.d_npart; pa.x0 = c->d_x0; pa.y0 = c->d_y0; pa.z0 = c->d_z0;
+    pa.ps = sp.pstride; pa.dead = sp.dead; pa.off = sp.d_off; pa.npart = sp.d_npart; pa.x0 = c->d_x0; pa.y0 = c->d_y0; pa.z0 = c->d_z0;
     pa.cdt = LPIC_C_LIGHT * 0.5 * dt; pa.inv_dx = 1.0 / g.dx; pa.inv_dy = 1.0 / g.dy; pa.inv_dz = 1.0;
     pa.nx = g.nx; pa.ny = g.ny; pa.nz = 1; pa.nty = nty; pa.ntz = 1; pa.ntile = ntile;  // key = (tx * nty + ty) * TC + lx * TY + ly
     pa.keys = (int *)c->scr_buf;
@@ -677,7 +737,7 @@ int launch_tiles2d(lpic_ctx *c, Species &sp, double dt, double q, double m, bool
     k_tile_perm<TX, TY, 1, 2><<<g.npatch, PT, perm_smem, c->stream>>>(pa);
     LAUNCHED(1);
     TileArgs ta;
-    ta.g = g; ta.F = c->fields; ta.px0 = c->d_x0; ta.py0 = c->d_y0; ta.pz0 = c->d_z0; ta.s = make_slots(sp);
+    ta.g = g; ta.F = c->fields; ta.rec = nullptr; ta.px0 = c->d_x0; ta.py0 = c->d_y0; ta.pz0 = c->d_z0; ta.s = make_slots(sp);
     ta.perm = c->scr_b; ta.tile_start = c->d_tile_start; ta.list = c->scr_a; ta.nlist = d_nlist;
     ta.nty = nty; ta.ntz = 1; ta.ntile = ntile;
     ta.dt = dt; ta.cdt = pa.cdt; ta.efactor = q * dt / (2 * m * LPIC_C_LIGHT); ta.bfactor = q * dt / (2 * m);
@@ -717,7 +777,7 @@ int launch_tiles(lpic_ctx *c, Species &sp, double dt, double q, double m, bool w
     TilePermArgs pa;
     pa.x = sp.attr[LPIC_P_X]; pa.y = sp.attr[LPIC_P_Y]; pa.z = sp.attr[LPIC_P_Z];
     pa.ux = sp.attr[LPIC_P_UX]; pa.uy = sp.attr[LPIC_P_UY]; pa.uz = sp.attr[LPIC_P_UZ]; pa.ig = sp.attr[LPIC_P_INV_GAMMA];
-    pa.dead = sp.dead; pa.off = sp.d_off; pa.npart = sp.d_npart; pa.x0 = c->d_x0; pa.y0 = c->d_y0; pa.z0 = c->d_z0;
+    pa.ps = sp.pstride; pa.dead = sp.dead; pa.off = sp.d_off; pa.npart = sp.d_npart; pa.x0 = c->d_x0; pa.y0 = c->d_y0; pa.z0 = c->d_z0;
     pa.cdt = LPIC_C_LIGHT * 0.5 * dt; pa.inv_dx = 1.0 / g.dx; pa.inv_dy = 1.0 / g.dy; pa.inv_dz = 1.0 / g.dz;
     pa.nx = g.nx; pa.ny = g.ny; pa.nz = g.nz; pa.nty = nty; pa.ntz = ntz; pa.ntile = ntile;
     pa.keys = (int *)c->scr_buf;  // the sort's staging buffer is idle during the push
@@ -725,15 +785,17 @@ int launch_tiles(lpic_ctx *c, Species &sp, double dt, double q, double m, bool w
     constexpr size_t push_smem = sizeof(double) * (6 * (TX + 3) * (TY + 3) * (TZ + 4) + NW * 30 * 33) + sizeof(int) * NW * 32;
     if (!c->tile_attr_set) {  // per context: function attributes are per device, and a process may drive several
         CUDA_TRY(cudaFuncSetAttribute(k_tile_perm<TX, TY, TZ, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_PERM_SMEM_LIMIT));
-        CUDA_TRY(cudaFuncSetAttribute(k_push_tile<TX, TY, TZ, NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)push_smem));
-        CUDA_TRY(cudaFuncSetAttribute(k_push_tile<TX, TY, TZ, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)push_smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_push_tile<TX, TY, TZ, NW, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)push_smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_push_tile<TX, TY, TZ, NW, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)push_smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_push_tile<TX, TY, TZ, NW, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)push_smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_push_tile<TX, TY, TZ, NW, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)push_smem));
         c->tile_attr_set = true;
     }
     CUDA_TRY(cudaMemsetAsync(d_nlist, 0, sizeof(int) * g.npatch, c->stream));
     k_tile_perm<TX, TY, TZ, 3><<<g.npatch, PT, perm_smem, c->stream>>>(pa);
     LAUNCHED(1);
     TileArgs ta;
-    ta.g = g; ta.F = c->fields; ta.px0 = c->d_x0; ta.py0 = c->d_y0; ta.pz0 = c->d_z0; ta.s = make_slots(sp);
+    ta.g = g; ta.F = c->fields; ta.rec = nullptr; ta.px0 = c->d_x0; ta.py0 = c->d_y0; ta.pz0 = c->d_z0; ta.s = make_slots(sp);
     ta.perm = c->scr_b; ta.tile_start = c->d_tile_start; ta.list = c->scr_a; ta.nlist = d_nlist;
     ta.nty = nty; ta.ntz = ntz; ta.ntile = ntile;
     ta.dt = dt; ta.cdt = pa.cdt; ta.efactor = q * dt / (2 * m * LPIC_C_LIGHT); ta.bfactor = q * dt / (2 * m);
@@ -741,8 +803,14 @@ int launch_tiles(lpic_ctx *c, Species &sp, double dt, double q, double m, bool w
     ta.q_dV = q / (g.dx * g.dy * g.dz); ta.q_dydzdt = q / (g.dy * g.dz * dt);
     ta.q_dxdzdt = q / (g.dx * g.dz * dt); ta.q_dxdydt = q / (g.dx * g.dy * dt);
     const unsigned grid = (unsigned)((i64)g.npatch * ntile);
-    if (write_part) k_push_tile<TX, TY, TZ, NW, true><<<grid, NW * 32, push_smem, c->stream>>>(ta);
-    else k_push_tile<TX, TY, TZ, NW, false><<<grid, NW * 32, push_smem, c->stream>>>(ta);
+    ta.rec = sp.rec;
+    if (sp.rec) {
+        if (write_part) k_push_tile<TX, TY, TZ, NW, true, true><<<grid, NW * 32, push_smem, c->stream>>>(ta);
+        else k_push_tile<TX, TY, TZ, NW, false, true><<<grid, NW * 32, push_smem, c->stream>>>(ta);
+    } else {
+        if (write_part) k_push_tile<TX, TY, TZ, NW, true, false><<<grid, NW * 32, push_smem, c->stream>>>(ta);
+        else k_push_tile<TX, TY, TZ, NW, false, false><<<grid, NW * 32, push_smem, c->stream>>>(ta);
+    }
     LAUNCHED(1);
     const unsigned lgrid = (unsigned)std::min<i64>(g.npatch, 148 * 8);
     if (write_part) k_list_particles<true, 3><<<lgrid, 128, 0, c->stream>>>(g, c->fields, c->d_x0, c->d_y0, c->d_z0, ta.s, c->scr_a, d_nlist, dt, q, m);

@@ -81,6 +81,7 @@ __device__ __forceinline__ int grouped_fetch_add(int *ctr, int key, bool active)
 }
 
 struct SortArgs {
+    int ps;  // stride of x, y, z (8: records, 1: separate arrays)
     const double *x, *y, *z;
     const u8 *dead;
     const i64 *off, *npart;
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(T) k_sort_index(SortArgs a) {
     __shared__ int sinc[T];
     __shared__ int sw[T / 32];
     __shared__ int s_hist[SMEM_BINS];
+    __shared__ int s_keys[T * IT];
     __shared__ int s_carry;
     const int p = blockIdx.x, tid = threadIdx.x;
     const i64 off = a.off[p];
@@ -122,33 +124,52 @@ __global__ void __launch_bounds__(T) k_sort_index(SortArgs a) {
         int keys[IT];
         bool valid[IT];
         int lastv = -1;
+        // Keys are computed with adjacent lanes on adjacent slots (a warp covers its 32 * IT consecutive slots in IT strips:
+        // coalesced whether the positions sit in separate arrays or in 64-byte records) and handed to the thread that owns
+        // IT consecutive slots through shared memory.  -1: dead or past the end.
+        {
+            const int wbase = base + (tid >> 5) * (32 * IT), lane = tid & 31;
 #pragma unroll
-        for (int j = 0; j < IT; j++) {
-            const int ip = ip0 + j;
-            valid[j] = false;
-            keys[j] = 0;
-            if (ip < np && !a.dead[off + ip]) {
-                valid[j] = true;
-                lastv = j;
-                // bucket coordinates as doubles (floor of the reference's quotient); NaN compares false everywhere and
-                // ends up out of range / clamped to 0, like (npy_intp)floor(NaN) = INT64_MIN does on the host
-                const double fx = floor((a.x[off + ip] - x0) / a.dxb);
-                const double vy = a.y[off + ip] - y0, vz = a.dim == 3 ? a.z[off + ip] - z0 : 0.0;
-                const double fy = a.nyb == 1 ? (vy >= 0.0 ? (vy < a.dyb ? 0.0 : 1.0) : -1.0) : floor(vy / a.dyb);
-                const double fz = a.dim != 3 ? 0.0 : (a.nzb == 1 ? (vz >= 0.0 ? (vz < a.dzb ? 0.0 : 1.0) : -1.0) : floor(vz / a.dzb));
-                const bool inx = fx >= 0.0 && fx < (double)a.nxb, iny = fy >= 0.0 && fy < (double)a.nyb,
-                           inz = fz >= 0.0 && fz < (double)a.nzb;
-                if (a.reverse_x) {
-                    const int ix = inx ? (int)fx : (fx >= (double)a.nxb ? a.nxb - 1 : 0);
-                    const int iy = iny ? (int)fy : (fy >= (double)a.nyb ? a.nyb - 1 : 0);
-                    const int iz = inz ? (int)fz : (fz >= (double)a.nzb ? a.nzb - 1 : 0);
-                    keys[j] = iz + iy * a.nzb + (a.nxb - 1 - ix) * a.nyb * a.nzb;
-                } else if (inx && iny && inz) {
-                    keys[j] = (int)fz + (int)fy * a.nzb + (int)fx * a.nyb * a.nzb;
-                } else {
-                    keys[j] = nbin - 1;
+            for (int m = 0; m < IT; m++) {
+                const int ip = wbase + 32 * m + lane;
+                int key = -1;
+                if (ip < np && !a.dead[off + ip]) {
+                    // bucket coordinates as doubles (floor of the reference's quotient); NaN compares false everywhere and
+                    // ends up out of range / clamped to 0, like (npy_intp)floor(NaN) = INT64_MIN does on the host
+                    double px, py, pz;
+                    if (a.ps == LPIC_NREC) {
+                        const double2 xy = *reinterpret_cast<const double2 *>(a.x + (off + ip) * LPIC_NREC);
+                        px = xy.x; py = xy.y; pz = a.dim == 3 ? a.z[(off + ip) * LPIC_NREC] : 0.0;
+                    } else {
+                        px = a.x[off + ip]; py = a.y[off + ip]; pz = a.dim == 3 ? a.z[off + ip] : 0.0;
+                    }
+                    const double fx = floor((px - x0) / a.dxb);
+                    const double vy = py - y0, vz = a.dim == 3 ? pz - z0 : 0.0;
+                    const double fy = a.nyb == 1 ? (vy >= 0.0 ? (vy < a.dyb ? 0.0 : 1.0) : -1.0) : floor(vy / a.dyb);
+                    const double fz = a.dim != 3 ? 0.0 : (a.nzb == 1 ? (vz >= 0.0 ? (vz < a.dzb ? 0.0 : 1.0) : -1.0) : floor(vz / a.dzb));
+                    const bool inx = fx >= 0.0 && fx < (double)a.nxb, iny = fy >= 0.0 && fy < (double)a.nyb,
+                               inz = fz >= 0.0 && fz < (double)a.nzb;
+                    if (a.reverse_x) {
+                        const int ix = inx ? (int)fx : (fx >= (double)a.nxb ? a.nxb - 1 : 0);
+                        const int iy = iny ? (int)fy : (fy >= (double)a.nyb ? a.nyb - 1 : 0);
+                        const int iz = inz ? (int)fz : (fz >= (double)a.nzb ? a.nzb - 1 : 0);
+                        key = iz + iy * a.nzb + (a.nxb - 1 - ix) * a.nyb * a.nzb;
+                    } else if (inx && iny && inz) {
+                        key = (int)fz + (int)fy * a.nzb + (int)fx * a.nyb * a.nzb;
+                    } else {
+                        key = nbin - 1;
+                    }
                 }
+                s_keys[(tid >> 5) * (32 * IT) + 32 * m + lane] = key;
             }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < IT; j++) {
+                keys[j] = s_keys[tid * IT + j];
+                valid[j] = keys[j] >= 0;
+                if (valid[j]) lastv = j; else keys[j] = 0;
+            }
+            __syncwarp();
         }
         int mylast = 0;
 #pragma unroll
@@ -288,13 +309,17 @@ __global__ void __launch_bounds__(T) k_sort_index(SortArgs a) {
 
 struct MoveArgs {
     double *a[LPIC_NPATTR];
-    int n;       // number of double attributes in this group
-    u8 *dead;    // moved with the group if not null
+    int stride[LPIC_NPATTR];  // 1, or 8 for a word of the record arena moved on its own
+    int n;                    // number of 8-byte attributes in this group
+    double *rec;              // record arena: 16-byte pieces [piece0, piece0 + npiece) of every moved record ride with the group
+    int piece0, npiece;
+    u8 *dead;                 // moved with the group if not null
 };
 
 // Value move of the misplaced slots, all attributes of a group in one thread: thread i of the compact list
 // [0, sum nbuf) finds its patch by bisection of the prefix poff, then issues one independent load per attribute.
-// gather: staging[attr][i] = attr[src_of[i]]; scatter: attr[tgt[i]] = staging[attr][i] (staging is [attr][total]).
+// gather: staging[attr][i] = attr[src_of[i]]; scatter: attr[tgt[i]] = staging[attr][i].  Staging: [npiece][total] 16-byte
+// record pieces, then [n][total] words, then the is_dead bytes.
 __device__ __forceinline__ int patch_of(const i64 *__restrict__ poff, int npatch, i64 i) {
     int lo = 0, hi = npatch - 1;  // last patch with poff[p] <= i
     while (lo < hi) {
@@ -310,13 +335,22 @@ __global__ void __launch_bounds__(256) k_sort_gather_all(MoveArgs A, double *__r
     const int p = patch_of(poff, npatch, i);
     const i64 src = off[p] + src_of[off[p] + (i - poff[p])];
     double v[LPIC_NPATTR];
+    double2 r[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (k < A.npiece) r[k] = reinterpret_cast<const double2 *>(A.rec + src * LPIC_NREC)[A.piece0 + k];
 #pragma unroll
     for (int y = 0; y < LPIC_NPATTR; y++)
-        if (y < A.n) v[y] = A.a[y][src];
+        if (y < A.n) v[y] = A.a[y][src * A.stride[y]];
+    double2 *pieces = reinterpret_cast<double2 *>(buf);
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (k < A.npiece) pieces[(size_t)k * total + i] = r[k];
+    double *words = buf + (size_t)2 * A.npiece * total;
 #pragma unroll
     for (int y = 0; y < LPIC_NPATTR; y++)
-        if (y < A.n) buf[(size_t)y * total + i] = v[y];
-    if (A.dead) ((u8 *)(buf + (size_t)A.n * total))[i] = A.dead[src];
+        if (y < A.n) words[(size_t)y * total + i] = v[y];
+    if (A.dead) ((u8 *)(words + (size_t)A.n * total))[i] = A.dead[src];
 }
 __global__ void __launch_bounds__(256) k_sort_scatter_all(MoveArgs A, const double *__restrict__ buf, i64 total, const int *__restrict__ tgt,
                                                           const i64 *__restrict__ off, const i64 *__restrict__ poff, int npatch) {
@@ -324,10 +358,15 @@ __global__ void __launch_bounds__(256) k_sort_scatter_all(MoveArgs A, const doub
     if (i >= total) return;
     const int p = patch_of(poff, npatch, i);
     const i64 dst = off[p] + tgt[off[p] + (i - poff[p])];
+    const double2 *pieces = reinterpret_cast<const double2 *>(buf);
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (k < A.npiece) reinterpret_cast<double2 *>(A.rec + dst * LPIC_NREC)[A.piece0 + k] = pieces[(size_t)k * total + i];
+    const double *words = buf + (size_t)2 * A.npiece * total;
 #pragma unroll
     for (int y = 0; y < LPIC_NPATTR; y++)
-        if (y < A.n) A.a[y][dst] = buf[(size_t)y * total + i];
-    if (A.dead) A.dead[dst] = ((const u8 *)(buf + (size_t)A.n * total))[i];
+        if (y < A.n) A.a[y][dst * A.stride[y]] = words[(size_t)y * total + i];
+    if (A.dead) A.dead[dst] = ((const u8 *)(words + (size_t)A.n * total))[i];
 }
 
 __global__ void k_widen(const int *__restrict__ src, i64 *__restrict__ dst, i64 n) {
@@ -380,7 +419,7 @@ extern "C" int lpic_sort(lpic_ctx *c, int ispec, int reverse_x, int64_t nxb, int
     }
     i64 *d_nbuf = c->d_tmp64 + 64;
     SortArgs a;
-    a.x = sp.attr[LPIC_P_X]; a.y = sp.attr[LPIC_P_Y]; a.z = sp.attr[LPIC_P_Z]; a.dead = sp.dead;
+    a.x = sp.attr[LPIC_P_X]; a.y = sp.attr[LPIC_P_Y]; a.z = sp.attr[LPIC_P_Z]; a.dead = sp.dead; a.ps = sp.pstride;
     a.off = sp.d_off; a.npart = sp.d_npart; a.org = c->d_sort_org;
     a.npatch = (int)n; a.nxb = (int)nxb; a.nyb = (int)nyb; a.nzb = (int)nzb; a.nbin = (int)nbin;
     a.reverse_x = reverse_x; a.dim = g.dim; a.dxb = dxb; a.dyb = dyb; a.dzb = dzb;
@@ -401,21 +440,32 @@ extern "C" int lpic_sort(lpic_ctx *c, int ispec, int reverse_x, int64_t nxb, int
         for (i64 p = 0; p < n; p++) { poff[p] = run; run += h_nbuf[p]; }
         i64 *d_poff = d_nbuf + n;
         CUDA_TRY(cudaMemcpyAsync(d_poff, poff.data(), sizeof(i64) * n, cudaMemcpyHostToDevice, c->stream));
-        std::vector<double *> attrs;
-        for (int at = 0; at < LPIC_NPATTR; at++)
-            if (sp.attr[at]) attrs.push_back(sp.attr[at]);
-        // attribute groups sized to the staging buffer (scr_cap doubles): all at once while <= ~10 % of the slots move;
-        // the is_dead bytes ride with the last group if a row is left, else alone
+        // What has to move, in rows of the staging buffer (one row = one 8-byte word per moved slot): the record arena as
+        // four 16-byte pieces of two rows each -- or, when more than half of all slots move and not even one piece fits, as
+        // eight strided words -- then the plain arrays, then the is_dead bytes (less than a row; alone if no row is left).
+        // Every group is gathered completely before it is scattered: sources and targets are the same set of slots.
         const i64 room = std::max<i64>(1, c->scr_cap / total);
+        struct Item { double *ptr; int stride; };
+        std::vector<Item> words;
+        int pieces_left = 0;
+        if (sp.rec) {
+            if (room >= 2) pieces_left = 4;
+            else for (int at = 0; at < LPIC_NREC; at++) words.push_back({sp.rec + at, LPIC_NREC});
+        }
+        for (int at = sp.rec ? LPIC_NREC : 0; at < LPIC_NPATTR; at++)
+            if (sp.attr[at]) words.push_back({sp.attr[at], 1});
         const unsigned grid = (unsigned)div_up(total, 256);
         size_t a0 = 0;
         bool dead_done = false;
-        while (a0 < attrs.size() || !dead_done) {
+        while (a0 < words.size() || pieces_left > 0 || !dead_done) {
             MoveArgs A;
-            A.n = 0;
-            A.dead = nullptr;
-            while (a0 < attrs.size() && A.n < room && A.n < LPIC_NPATTR) A.a[A.n++] = attrs[a0++];
-            if (a0 == attrs.size() && (A.n < room || A.n == 0)) { A.dead = sp.dead; dead_done = true; }
+            A.n = 0; A.dead = nullptr; A.rec = sp.rec; A.piece0 = 4 - pieces_left; A.npiece = 0;
+            i64 rows = 0;
+            while (pieces_left > 0 && rows + 2 <= room) { A.npiece++; pieces_left--; rows += 2; }
+            while (pieces_left == 0 && a0 < words.size() && rows + 1 <= room && A.n < LPIC_NPATTR) {
+                A.a[A.n] = words[a0].ptr; A.stride[A.n] = words[a0].stride; A.n++; a0++; rows++;
+            }
+            if (pieces_left == 0 && a0 == words.size() && (rows + 1 <= room || rows == 0)) { A.dead = sp.dead; dead_done = true; }
             k_sort_gather_all<<<grid, 256, 0, c->stream>>>(A, c->scr_buf, total, c->scr_b, sp.d_off, d_poff, (int)n);
             k_sort_scatter_all<<<grid, 256, 0, c->stream>>>(A, c->scr_buf, total, c->scr_a, sp.d_off, d_poff, (int)n);
             LAUNCHED(2);

@@ -250,17 +250,39 @@ class DeviceEngine:
         self.npart_created[ispec] = (np.array(npart_created, dtype=np.int64) if npart_created is not None else npart.copy())
         return self.species[ispec]
 
+    def _record_table(self, m, names):
+        """(mask, pointer table) of the attributes among `names` that live in the device's 64-byte records (ids 0..7)."""
+        import ctypes as C
+        tab = (C.c_void_p * 8)()
+        mask = 0
+        for a in names:
+            aid = PART_ATTRS.index(a) if a != "is_dead" else -1
+            if 0 <= aid < 8:
+                tab[aid] = m.host[a].ctypes.data
+                mask |= 1 << aid
+        return mask, tab
+
     def upload_particles(self, ispec, attrs=None):
         m = self.species[ispec]
-        for a in (attrs or m.attrs + ["is_dead"]):
+        names = list(attrs or m.attrs + ["is_dead"])
+        mask, tab = self._record_table(m, names)
+        if mask:  # x y z w ux uy uz inv_gamma in one chunked, double-buffered pass (lpic_upload_particle_records)
+            check(self.L.lpic_upload_particle_records(self.ctx, ispec, mask, tab))
+        for a in names:
             aid = P_IS_DEAD if a == "is_dead" else PART_ATTRS.index(a)
-            check(self.L.lpic_upload_particles(self.ctx, ispec, aid, _ptr(m.host[a])))
+            if not (0 <= aid < 8):
+                check(self.L.lpic_upload_particles(self.ctx, ispec, aid, _ptr(m.host[a])))
 
     def download_particles(self, ispec, attrs=None):
         m = self.species[ispec]
-        for a in (attrs or m.attrs + ["is_dead"]):
+        names = list(attrs or m.attrs + ["is_dead"])
+        mask, tab = self._record_table(m, names)
+        if mask:
+            check(self.L.lpic_download_particle_records(self.ctx, ispec, mask, tab))
+        for a in names:
             aid = P_IS_DEAD if a == "is_dead" else PART_ATTRS.index(a)
-            check(self.L.lpic_download_particles(self.ctx, ispec, aid, _ptr(m.host[a])))
+            if not (0 <= aid < 8):
+                check(self.L.lpic_download_particles(self.ctx, ispec, aid, _ptr(m.host[a])))
 
     def upload_all(self):
         self.upload_fields()
