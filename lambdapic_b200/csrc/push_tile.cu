@@ -216,6 +216,8 @@ __device__ __forceinline__ ZSplit zsplit(int bz, double w0, double w1, double w2
 struct RowOwner {
     double *dst;     // this patch's jx / jy / jz / rho block
     int ax, ay, az;  // tile origin + the owner's stencil offset - 1 (ax is advanced by one per x-plane)
+};
+struct PadDims {  // padded patch sizes: passed along from the kernel parameters (constant bank) instead of living in registers
     int NX, NY, NZ;
 };
 
@@ -227,10 +229,10 @@ __device__ __forceinline__ void red_add(double *p, double v) {
 
 // one RED for a finished cell (code = cell inside the tile; -1: nothing carried yet)
 template <int TY, int TZ>
-__device__ __forceinline__ void flush_cell(const RowOwner &o, int code, double sum) {
+__device__ __forceinline__ void flush_cell(const RowOwner &o, const PadDims &d, int code, double sum) {
     if (code < 0) return;
     const int lz = code % TZ, ly = (code / TZ) % TY, lx = code / (TZ * TY);
-    const int id = (wrapneg(o.ax + lx, o.NX) * o.NY + wrapneg(o.ay + ly, o.NY)) * o.NZ + wrapneg(o.az + lz, o.NZ);
+    const int id = (wrapneg(o.ax + lx, d.NX) * d.NY + wrapneg(o.ay + ly, d.NY)) * d.NZ + wrapneg(o.az + lz, d.NZ);
     red_add(o.dst + id, sum);
 }
 
@@ -239,8 +241,11 @@ __device__ __forceinline__ void flush_cell(const RowOwner &o, int code, double s
 // this in the instruction stream serves the three x-planes.  Straight-line per group of four source lanes; a group
 // that contains a head splits its four values around it.
 template <int TY, int TZ>
-__device__ __noinline__ double row_sum(double acc, unsigned heads, const double *__restrict__ row, const int *__restrict__ codes,
-                                       int cur, RowOwner o) {
+__device__ __noinline__ double row_sum(double acc, unsigned heads, const double *__restrict__ tile, int cur, RowOwner o, PadDims d) {
+    // tile = the warp's [30][33] reduction tile followed by its 32 cell codes; this lane's row and the codes are derived here
+    // rather than handed in: four registers fewer to keep alive around the call
+    const double *__restrict__ row = tile + (threadIdx.x & 31) * 33;
+    const int *__restrict__ codes = reinterpret_cast<const int *>(tile + 30 * 33);
 #pragma unroll
     for (int g4 = 0; g4 < 32; g4 += 4) {
         const unsigned mm = (heads >> g4) & 0xFu;
@@ -250,14 +255,14 @@ __device__ __noinline__ double row_sum(double acc, unsigned heads, const double 
         } else if ((mm & (mm - 1u)) == 0u) {  // one head, at position t: sources before it close the current cell
             const int t = __ffs(mm) - 1;
             const double lo = (t > 0 ? v0 : 0.0) + (t > 1 ? v1 : 0.0) + (t > 2 ? v2 : 0.0);
-            flush_cell<TY, TZ>(o, cur, acc + lo);
+            flush_cell<TY, TZ>(o, d, cur, acc + lo);
             cur = codes[g4 + t];
             acc = ((t > 0 ? 0.0 : v0) + (t > 1 ? 0.0 : v1)) + ((t > 2 ? 0.0 : v2) + v3);
         } else {  // several cells start inside the group (fewer than 4 particles per cell): rolled, re-reads the row
 #pragma unroll 1
             for (int t = 0; t < 4; t++) {
                 if ((mm >> t) & 1u) {
-                    flush_cell<TY, TZ>(o, cur, acc);
+                    flush_cell<TY, TZ>(o, d, cur, acc);
                     acc = 0.0;
                     cur = codes[g4 + t];
                 }
@@ -274,8 +279,8 @@ __global__ void __launch_bounds__(NW * 32, TILE_MIN_CTAS) k_push_tile(const Tile
     constexpr int SX = EY * EZ, SY = EZ;  // strides (in doubles) of the staged tile
     extern __shared__ __align__(16) double smem[];
     double *eb = smem;                                            // [6][EX][EY][EZ]
-    double *red = smem + 6 * EN + (threadIdx.x >> 5) * (30 * 33);  // this warp's [30][33] reduction tile
-    int *codes = (int *)(smem + 6 * EN + NW * 30 * 33) + (threadIdx.x >> 5) * 32;
+    double *red = smem + 6 * EN + (threadIdx.x >> 5) * (30 * 33 + 16);  // this warp's [30][33] reduction tile + its 32 cell codes
+    int *codes = (int *)(red + 30 * 33);
     const Geom &g = a.g;
     const int p = blockIdx.x / a.ntile, tile = blockIdx.x - p * a.ntile;
     const int *ts = a.tile_start + (size_t)p * (a.ntile + 1) + tile;
@@ -285,6 +290,8 @@ __global__ void __launch_bounds__(NW * 32, TILE_MIN_CTAS) k_push_tile(const Tile
     const int ox = tx * TX, oy = ty * TY, oz = tz * TZ;
     const size_t stride = (size_t)g.npatch * g.ncell;
     double *Fp = a.F + (size_t)p * g.ncell;
+    __shared__ double s_org[3];
+    if (threadIdx.x == 0) { s_org[0] = a.px0[p]; s_org[1] = a.py0[p]; s_org[2] = a.pz0[p]; }
     // ---- stage E/B of the tile and its halo: nodes [o-2, o+T] per axis, logical order --------------------------------
     for (int idx = threadIdx.x; idx < EN; idx += NW * 32) {
         const int lz = idx % EZ, ly = (idx / EZ) % EY, lx = idx / (EZ * EY);  // (the pad column lz = TZ + 3 is loaded too: one more guard node)
@@ -301,7 +308,9 @@ __global__ void __launch_bounds__(NW * 32, TILE_MIN_CTAS) k_push_tile(const Tile
     const int wfirst = first + warp * per, wlast = min(last, wfirst + per);
     if (wfirst >= wlast) return;
     const i64 off = a.s.off[p];
-    const double x0 = a.px0[p], y0 = a.py0[p], z0 = a.pz0[p];
+    // (the patch origin is read from shared memory where it is used: three doubles fewer to keep in registers across the
+    // iteration -- whatever this kernel spills misses the small L1 and costs an L2 round trip)
+    const volatile double *org = s_org;
     // which row of the reduction tile does this lane own?  [0,9) rho(j,k)  [9,15) jy(j<2,k)  [15,21) jz(j,k<2)  [21,30) jx(j,k)
     int comp, sj, sk;
     if (lane < 9) { comp = LPIC_RHO; sj = lane / 3; sk = lane - 3 * sj; }
@@ -311,32 +320,38 @@ __global__ void __launch_bounds__(NW * 32, TILE_MIN_CTAS) k_push_tile(const Tile
     RowOwner own;
     own.dst = Fp + comp * stride;
     own.ax = ox - 1; own.ay = oy + sj - 1; own.az = oz + sk - 1;
-    own.NX = g.NX; own.NY = g.NY; own.NZ = g.NZ;
-    const double *row = red + lane * 33;
+    PadDims pd;
+    pd.NX = g.NX; pd.NY = g.NY; pd.NZ = g.NZ;
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;  // the owner's running sums of the current cell, one per x-plane
     int ccode = -1;                             // that cell (-1: none yet)
     for (int t0 = wfirst; t0 < wlast; t0 += 32) {
         const bool active = t0 + lane < wlast;
         double x = 0, y = 0, z = 0, ux = 0, uy = 0, uz = 0, ig = 1, w = 0;
         int local = 0, cx = 0, cy = 0, cz = 0;
-        if (active) local = a.perm[off + t0 + lane];
+        if (active && (!REC || WRITE_PART)) local = a.perm[off + t0 + lane];
         if (REC) {
             // A quad of lanes fetches one 64-byte record per load instruction (lane q of quad Q: piece q of particle 4Q + j), so
             // a warp-level load touches 8 records = 16 full sectors however the slots are ordered.  The pieces go through the
             // warp's (idle) reduction tile, 80 bytes per particle: conflict-free for the quad stores and for the owners' loads.
+            // The quad's four slot numbers are parked behind them for the store phase (registers are what this kernel is short
+            // of: its spills do not fit the 28 KB of L1 left beside the shared memory and cost an L2 round trip each).
             const int q = lane & 3, qb = lane & ~3;
             double2 *stg = reinterpret_cast<double2 *>(red);
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int P = qb + j;
-                if (t0 + P < wlast) stg[P * 5 + q] = __ldg(reinterpret_cast<const double2 *>(a.rec + (off + a.perm[off + t0 + P]) * LPIC_NREC) + q);
-            }
+            int4 lq = make_int4(0, 0, 0, 0);
+            if (t0 + qb < wlast) lq.x = a.perm[off + t0 + qb];
+            if (t0 + qb + 1 < wlast) lq.y = a.perm[off + t0 + qb + 1];
+            if (t0 + qb + 2 < wlast) lq.z = a.perm[off + t0 + qb + 2];
+            if (t0 + qb + 3 < wlast) lq.w = a.perm[off + t0 + qb + 3];
+            if (t0 + qb < wlast) stg[qb * 5 + q] = __ldg(reinterpret_cast<const double2 *>(a.rec + (off + lq.x) * LPIC_NREC) + q);
+            if (t0 + qb + 1 < wlast) stg[(qb + 1) * 5 + q] = __ldg(reinterpret_cast<const double2 *>(a.rec + (off + lq.y) * LPIC_NREC) + q);
+            if (t0 + qb + 2 < wlast) stg[(qb + 2) * 5 + q] = __ldg(reinterpret_cast<const double2 *>(a.rec + (off + lq.z) * LPIC_NREC) + q);
+            if (t0 + qb + 3 < wlast) stg[(qb + 3) * 5 + q] = __ldg(reinterpret_cast<const double2 *>(a.rec + (off + lq.w) * LPIC_NREC) + q);
+            reinterpret_cast<int4 *>(red + 32 * 10)[lane] = lq;
             __syncwarp();
             if (active) {
                 const double2 r0 = stg[lane * 5], r1 = stg[lane * 5 + 1], r2 = stg[lane * 5 + 2], r3 = stg[lane * 5 + 3];
-                x = r0.x; y = r0.y; z = r1.x; w = r1.y; ux = r2.x; uy = r2.y; uz = r3.x; ig = r3.y;
+                x = r0.x; y = r0.y; z = r1.x; ux = r2.x; uy = r2.y; uz = r3.x; ig = r3.y;  // (w stays in the tile until the deposit)
             }
-            __syncwarp();
         }
         if (active) {
             const i64 ip = off + local;
@@ -346,7 +361,7 @@ __global__ void __launch_bounds__(NW * 32, TILE_MIN_CTAS) k_push_tile(const Tile
                 w = a.s.w[ip * a.s.ps];
             }
             x = half_push(x, a.cdt, ig, ux); y = half_push(y, a.cdt, ig, uy); z = half_push(z, a.cdt, ig, uz);
-            const double X = grid_coord(x, x0, a.inv_dx), Y = grid_coord(y, y0, a.inv_dy), Z = grid_coord(z, z0, a.inv_dz);
+            const double X = grid_coord(x, org[0], a.inv_dx), Y = grid_coord(y, org[1], a.inv_dy), Z = grid_coord(z, org[2], a.inv_dz);
             const double rX = nearest(X), rY = nearest(Y), rZ = nearest(Z), fX = floor(X), fY = floor(Y), fZ = floor(Z);
             cx = (int)rX; cy = (int)rY; cz = (int)rZ;
             double gx0, gx1, gx2, gy0, gy1, gy2, gz0, gz1, gz2, hx0, hx1, hx2, hy0, hy1, hy2, hz0, hz1, hz2;
@@ -381,21 +396,22 @@ __global__ void __launch_bounds__(NW * 32, TILE_MIN_CTAS) k_push_tile(const Tile
             const int q = lane & 3, qb = lane & ~3;
             double2 *stg = reinterpret_cast<double2 *>(red);
             if (active) {
-                stg[lane * 5] = make_double2(x, y); stg[lane * 5 + 1] = make_double2(z, w);
+                stg[lane * 5] = make_double2(x, y); red[lane * 10 + 2] = z;
                 stg[lane * 5 + 2] = make_double2(ux, uy); stg[lane * 5 + 3] = make_double2(uz, ig);
+                w = red[lane * 10 + 3];
             }
             __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int P = qb + j;
-                if (t0 + P < wlast) reinterpret_cast<double2 *>(a.rec + (off + a.perm[off + t0 + P]) * LPIC_NREC)[q] = stg[P * 5 + q];
-            }
+            const int *lq = reinterpret_cast<const int *>(red + 32 * 10) + lane * 4;
+#pragma unroll 1  // one record at a time: stores need no memory-level parallelism, and four in flight cost 28 registers
+            for (int j = 0; j < 4; j++)
+                if (t0 + qb + j < wlast) reinterpret_cast<double2 *>(a.rec + (off + lq[j]) * LPIC_NREC)[q] = stg[(qb + j) * 5 + q];
             __syncwarp();  // the deposit below reuses the tile
         }
         // ---- deposit set-up (current_deposit.h:341-373): the path from x - v dt/2 to x + v dt/2 ------------------------
         // Same expressions as the reference (and k_particles): a slow particle's current is proportional to X1 - X0, the
         // difference of two separately rounded coordinates, so the quotients have to round the way a division does.
         const double vx = ux * LPIC_C_LIGHT * ig, vy = uy * LPIC_C_LIGHT * ig, vz = uz * LPIC_C_LIGHT * ig;
+        const double x0 = org[0], y0 = org[1], z0 = org[2];
         const double X0 = div_rn(x - vx * 0.5 * a.dt - x0, g.dx, a.inv_dx), X1 = div_rn(x + vx * 0.5 * a.dt - x0, g.dx, a.inv_dx);
         const double Y0 = div_rn(y - vy * 0.5 * a.dt - y0, g.dy, a.inv_dy), Y1 = div_rn(y + vy * 0.5 * a.dt - y0, g.dy, a.inv_dy);
         const double Z0 = div_rn(z - vz * 0.5 * a.dt - z0, g.dz, a.inv_dz), Z1 = div_rn(z + vz * 0.5 * a.dt - z0, g.dz, a.inv_dz);
@@ -410,7 +426,7 @@ __global__ void __launch_bounds__(NW * 32, TILE_MIN_CTAS) k_push_tile(const Tile
                 int basepos = 0;
                 if (lane == __ffs(cm) - 1) basepos = atomicAdd(&a.nlist[p], __popc(cm));
                 basepos = __shfl_sync(0xffffffffu, basepos, __ffs(cm) - 1);
-                if (active && !fast) a.list[off + basepos + __popc(cm & ((1u << lane) - 1u))] = local;
+                if (active && !fast) a.list[off + basepos + __popc(cm & ((1u << lane) - 1u))] = REC ? a.perm[off + t0 + lane] : local;
             }
         }
         // cells = runs of consecutive fast lanes with the same code; lanes outside the fast path add zeros and never
@@ -470,18 +486,18 @@ __global__ void __launch_bounds__(NW * 32, TILE_MIN_CTAS) k_push_tile(const Tile
             if (lane < (i < 2 ? 30 : 21)) {
                 RowOwner o = own;
                 o.ax += i;
-                const double acc = row_sum<TY, TZ>(i == 0 ? acc0 : (i == 1 ? acc1 : acc2), heads, row, codes, ccode, o);
+                const double acc = row_sum<TY, TZ>(i == 0 ? acc0 : (i == 1 ? acc1 : acc2), heads, red, ccode, o, pd);
                 if (i == 0) acc0 = acc; else if (i == 1) acc1 = acc; else acc2 = acc;
             }
             __syncwarp();
         }
         ccode = lastcode;
     }
-    flush_cell<TY, TZ>(own, ccode, acc0);
+    flush_cell<TY, TZ>(own, pd, ccode, acc0);
     own.ax++;
-    flush_cell<TY, TZ>(own, ccode, acc1);
+    flush_cell<TY, TZ>(own, pd, ccode, acc1);
     own.ax++;
-    if (lane < 21) flush_cell<TY, TZ>(own, ccode, acc2);
+    if (lane < 21) flush_cell<TY, TZ>(own, pd, ccode, acc2);
 }
 
 // The listed particles of every patch: entries tagged LIST_WHOLE_STEP get the whole step with gathers from global memory
@@ -553,8 +569,8 @@ __global__ void __launch_bounds__(NW * 32, 4) k_push_tile2d(const TileArgs a) {
     constexpr int SX = EY;
     extern __shared__ __align__(16) double smem[];
     double *eb = smem;                                            // [6][EX][EY]
-    double *red = smem + 6 * EN + (threadIdx.x >> 5) * (30 * 33);  // this warp's [30][33] reduction tile
-    int *codes = (int *)(smem + 6 * EN + NW * 30 * 33) + (threadIdx.x >> 5) * 32;
+    double *red = smem + 6 * EN + (threadIdx.x >> 5) * (30 * 33 + 16);  // this warp's [30][33] reduction tile + its 32 cell codes
+    int *codes = (int *)(red + 30 * 33);
     const Geom &g = a.g;
     const int p = blockIdx.x / a.ntile, tile = blockIdx.x - p * a.ntile;
     const int *ts = a.tile_start + (size_t)p * (a.ntile + 1) + tile;
@@ -589,8 +605,8 @@ __global__ void __launch_bounds__(NW * 32, 4) k_push_tile2d(const TileArgs a) {
     RowOwner own;
     own.dst = Fp + comp * stride;
     own.ax = ox + si - 1; own.ay = oy + sj - 1; own.az = 0;
-    own.NX = g.NX; own.NY = g.NY; own.NZ = 1;
-    const double *row = red + lane * 33;
+    PadDims pd;
+    pd.NX = g.NX; pd.NY = g.NY; pd.NZ = 1;
     double acc = 0.0;
     int ccode = -1;
     for (int t0 = wfirst; t0 < wlast; t0 += 32) {
@@ -692,11 +708,11 @@ __global__ void __launch_bounds__(NW * 32, 4) k_push_tile2d(const TileArgs a) {
             }
         }
         __syncwarp();
-        if (lane < 30) acc = row_sum<TY, 1>(acc, heads, row, codes, ccode, own);
+        if (lane < 30) acc = row_sum<TY, 1>(acc, heads, red, ccode, own, pd);
         __syncwarp();
         ccode = lastcode;
     }
-    if (lane < 30) flush_cell<TY, 1>(own, ccode, acc);
+    if (lane < 30) flush_cell<TY, 1>(own, pd, ccode, acc);
 }
 
 template <int TX, int TY, int NW>
