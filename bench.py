@@ -507,11 +507,12 @@ def e2e_public_api(args, wl, rank=0, world=1):
     for sp in sim.species:
         lp.SetTemperature(sp, wl.temperature_eV)(sim)
     t_setup = time.perf_counter() - t_setup
-    hist = []
+    hist, stamps = [], []
 
     @lp.callback("end", needs_host=False)
     def diag(sim):
-        hist.append(sim.energies())
+        hist.append(sim.energies())   # (a D2H read: the step's device work is complete when it returns)
+        stamps.append(time.perf_counter())
     steps = max(1, args.steps)
     before = dict(sim.bridge.stats)
     n0 = sum(int((~pt.is_dead).sum()) for p in sim.patches for pt in p.particles)
@@ -538,6 +539,9 @@ def e2e_public_api(args, wl, rank=0, world=1):
            "h2d_seconds": st.get("h2d_seconds", 0.0) - before.get("h2d_seconds", 0.0),
            "d2h_seconds": st.get("d2h_seconds", 0.0) - before.get("d2h_seconds", 0.0),
            "energy_drift_rel": abs(tot[-1] - tot[0]) / tot[0],
+           # wall time of every step inside run() (the first ones carry the reference's start-up transient: the first
+           # migration appends 25 % dead slots to every patch and the following sorts drag up to half of all slots along)
+           "step_ms": [round(1e3 * (b - a), 1) for a, b in zip([t0 + (st.get("h2d_seconds", 0.0) - before.get("h2d_seconds", 0.0))] + stamps[:-1], stamps)],
            "workload": f"{wl.cells[0]}x{wl.cells[1]}x{wl.cells[2]} cells, {wl.ppc[0]}+{wl.ppc[1]} ppc ({wl.n_particles()} particles)",
            "mode": "Simulation3D.run(nsteps=K): H2D of all state from pinned host mirrors at entry, K steps with a per-step "
                    "D2H energy diagnostic, D2H of all state at exit"}

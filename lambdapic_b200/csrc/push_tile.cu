@@ -155,6 +155,41 @@ __global__ void __launch_bounds__(PT) k_tile_perm(TilePermArgs a) {
     }
 }
 
+// ---- record access of one warp iteration (particles t0 .. t0+31 of the processing order) ------------------------------
+// A quad of lanes fetches one 64-byte record per load instruction (lane q of quad Q: piece q of particle 4Q + j), so a
+// warp-level load touches 8 records = 16 full sectors however the slots are ordered.  The pieces go through the warp's
+// (idle) reduction tile, 80 bytes per particle: conflict-free for the quad stores and for the owners' loads.  The quad's
+// four slot numbers are parked behind them for the store phase, and w stays in the tile until the deposit: registers are
+// what these kernels are short of (their spills miss the 28 KB of L1 left beside the shared memory: an L2 round trip each).
+__device__ __forceinline__ void rec_load_warp(const double *__restrict__ rec, const int *__restrict__ perm, i64 off, int t0,
+                                              int wlast, int lane, double *red) {
+    const int q = lane & 3, qb = lane & ~3;
+    double2 *stg = reinterpret_cast<double2 *>(red);
+    int4 lq = make_int4(0, 0, 0, 0);
+    if (t0 + qb < wlast) lq.x = perm[off + t0 + qb];
+    if (t0 + qb + 1 < wlast) lq.y = perm[off + t0 + qb + 1];
+    if (t0 + qb + 2 < wlast) lq.z = perm[off + t0 + qb + 2];
+    if (t0 + qb + 3 < wlast) lq.w = perm[off + t0 + qb + 3];
+    if (t0 + qb < wlast) stg[qb * 5 + q] = __ldg(reinterpret_cast<const double2 *>(rec + (off + lq.x) * LPIC_NREC) + q);
+    if (t0 + qb + 1 < wlast) stg[(qb + 1) * 5 + q] = __ldg(reinterpret_cast<const double2 *>(rec + (off + lq.y) * LPIC_NREC) + q);
+    if (t0 + qb + 2 < wlast) stg[(qb + 2) * 5 + q] = __ldg(reinterpret_cast<const double2 *>(rec + (off + lq.z) * LPIC_NREC) + q);
+    if (t0 + qb + 3 < wlast) stg[(qb + 3) * 5 + q] = __ldg(reinterpret_cast<const double2 *>(rec + (off + lq.w) * LPIC_NREC) + q);
+    reinterpret_cast<int4 *>(red + 32 * 10)[lane] = lq;
+    __syncwarp();
+}
+// whole records back (z and w as they are in the tile): every store instruction writes full 32-byte sectors.  The caller
+// has put this lane's new values into red[lane * 10 + ...] before.
+__device__ __forceinline__ void rec_store_warp(double *__restrict__ rec, i64 off, int t0, int wlast, int lane, double *red) {
+    const int q = lane & 3, qb = lane & ~3;
+    const double2 *stg = reinterpret_cast<const double2 *>(red);
+    __syncwarp();
+    const int *lq = reinterpret_cast<const int *>(red + 32 * 10) + lane * 4;
+#pragma unroll 1  // one record at a time: stores need no memory-level parallelism, and four in flight cost 28 registers
+    for (int j = 0; j < 4; j++)
+        if (t0 + qb + j < wlast) reinterpret_cast<double2 *>(rec + (off + lq[j]) * LPIC_NREC)[q] = stg[(qb + j) * 5 + q];
+    __syncwarp();  // the deposit reuses the tile
+}
+
 struct TileArgs {
     Geom g;
     double *F;
@@ -330,27 +365,11 @@ __global__ void __launch_bounds__(NW * 32, TILE_MIN_CTAS) k_push_tile(const Tile
         int local = 0, cx = 0, cy = 0, cz = 0;
         if (active && (!REC || WRITE_PART)) local = a.perm[off + t0 + lane];
         if (REC) {
-            // A quad of lanes fetches one 64-byte record per load instruction (lane q of quad Q: piece q of particle 4Q + j), so
-            // a warp-level load touches 8 records = 16 full sectors however the slots are ordered.  The pieces go through the
-            // warp's (idle) reduction tile, 80 bytes per particle: conflict-free for the quad stores and for the owners' loads.
-            // The quad's four slot numbers are parked behind them for the store phase (registers are what this kernel is short
-            // of: its spills do not fit the 28 KB of L1 left beside the shared memory and cost an L2 round trip each).
-            const int q = lane & 3, qb = lane & ~3;
-            double2 *stg = reinterpret_cast<double2 *>(red);
-            int4 lq = make_int4(0, 0, 0, 0);
-            if (t0 + qb < wlast) lq.x = a.perm[off + t0 + qb];
-            if (t0 + qb + 1 < wlast) lq.y = a.perm[off + t0 + qb + 1];
-            if (t0 + qb + 2 < wlast) lq.z = a.perm[off + t0 + qb + 2];
-            if (t0 + qb + 3 < wlast) lq.w = a.perm[off + t0 + qb + 3];
-            if (t0 + qb < wlast) stg[qb * 5 + q] = __ldg(reinterpret_cast<const double2 *>(a.rec + (off + lq.x) * LPIC_NREC) + q);
-            if (t0 + qb + 1 < wlast) stg[(qb + 1) * 5 + q] = __ldg(reinterpret_cast<const double2 *>(a.rec + (off + lq.y) * LPIC_NREC) + q);
-            if (t0 + qb + 2 < wlast) stg[(qb + 2) * 5 + q] = __ldg(reinterpret_cast<const double2 *>(a.rec + (off + lq.z) * LPIC_NREC) + q);
-            if (t0 + qb + 3 < wlast) stg[(qb + 3) * 5 + q] = __ldg(reinterpret_cast<const double2 *>(a.rec + (off + lq.w) * LPIC_NREC) + q);
-            reinterpret_cast<int4 *>(red + 32 * 10)[lane] = lq;
-            __syncwarp();
+            rec_load_warp(a.rec, a.perm, off, t0, wlast, lane, red);
             if (active) {
-                const double2 r0 = stg[lane * 5], r1 = stg[lane * 5 + 1], r2 = stg[lane * 5 + 2], r3 = stg[lane * 5 + 3];
-                x = r0.x; y = r0.y; z = r1.x; ux = r2.x; uy = r2.y; uz = r3.x; ig = r3.y;  // (w stays in the tile until the deposit)
+                const double2 *stg = reinterpret_cast<const double2 *>(red);
+                const double2 r0 = stg[lane * 5], r2 = stg[lane * 5 + 2], r3 = stg[lane * 5 + 3];
+                x = r0.x; y = r0.y; z = red[lane * 10 + 2]; ux = r2.x; uy = r2.y; uz = r3.x; ig = r3.y;
             }
         }
         if (active) {
@@ -392,20 +411,14 @@ __global__ void __launch_bounds__(NW * 32, TILE_MIN_CTAS) k_push_tile(const Tile
                 a.s.x[ip * a.s.ps] = x; a.s.y[ip * a.s.ps] = y; a.s.z[ip * a.s.ps] = z;
             }
         }
-        if (REC) {  // whole records back (w unchanged): every store instruction writes full 32-byte sectors
-            const int q = lane & 3, qb = lane & ~3;
-            double2 *stg = reinterpret_cast<double2 *>(red);
+        if (REC) {
             if (active) {
+                double2 *stg = reinterpret_cast<double2 *>(red);
                 stg[lane * 5] = make_double2(x, y); red[lane * 10 + 2] = z;
                 stg[lane * 5 + 2] = make_double2(ux, uy); stg[lane * 5 + 3] = make_double2(uz, ig);
                 w = red[lane * 10 + 3];
             }
-            __syncwarp();
-            const int *lq = reinterpret_cast<const int *>(red + 32 * 10) + lane * 4;
-#pragma unroll 1  // one record at a time: stores need no memory-level parallelism, and four in flight cost 28 registers
-            for (int j = 0; j < 4; j++)
-                if (t0 + qb + j < wlast) reinterpret_cast<double2 *>(a.rec + (off + lq[j]) * LPIC_NREC)[q] = stg[(qb + j) * 5 + q];
-            __syncwarp();  // the deposit below reuses the tile
+            rec_store_warp(a.rec, off, t0, wlast, lane, red);
         }
         // ---- deposit set-up (current_deposit.h:341-373): the path from x - v dt/2 to x + v dt/2 ------------------------
         // Same expressions as the reference (and k_particles): a slow particle's current is proportional to X1 - X0, the
@@ -563,7 +576,7 @@ __global__ void __launch_bounds__(128) k_list_particles(Geom g, double *__restri
 // (the three y-neighbours of a stencil row as an aligned LDS.128 + LDS.64), and the whole 3x3 stencil of a particle that
 // stays in its cell is ONE round of the [30][33] reduction tile -- rho 9 rows, jx 6 (the last x row is sum(DSx) = 0 up to
 // rounding), jy 6 (last y column likewise), jz 9 -- with one carried sum per owner lane.
-template <int TX, int TY, int NW, bool WRITE_PART>
+template <int TX, int TY, int NW, bool WRITE_PART, bool REC>
 __global__ void __launch_bounds__(NW * 32, 4) k_push_tile2d(const TileArgs a) {
     constexpr int EX = TX + 3, EY = TY + 4, EN = EX * EY;  // EY: TY + 3 nodes, padded to an even row length
     constexpr int SX = EY;
@@ -613,12 +626,22 @@ __global__ void __launch_bounds__(NW * 32, 4) k_push_tile2d(const TileArgs a) {
         const bool active = t0 + lane < wlast;
         double x = 0, y = 0, ux = 0, uy = 0, uz = 0, ig = 1, w = 0;
         int local = 0, cx = 0, cy = 0;
+        if (REC) {
+            rec_load_warp(a.rec, a.perm, off, t0, wlast, lane, red);
+            if (active) {
+                const double2 *stg = reinterpret_cast<const double2 *>(red);
+                const double2 r0 = stg[lane * 5], r2 = stg[lane * 5 + 2], r3 = stg[lane * 5 + 3];
+                x = r0.x; y = r0.y; ux = r2.x; uy = r2.y; uz = r3.x; ig = r3.y;
+            }
+        }
         if (active) {
             local = a.perm[off + t0 + lane];
             const i64 ip = off + local;
-            x = a.s.x[ip * a.s.ps]; y = a.s.y[ip * a.s.ps];
-            ux = a.s.ux[ip * a.s.ps]; uy = a.s.uy[ip * a.s.ps]; uz = a.s.uz[ip * a.s.ps]; ig = a.s.ig[ip * a.s.ps];
-            w = a.s.w[ip * a.s.ps];
+            if (!REC) {
+                x = a.s.x[ip * a.s.ps]; y = a.s.y[ip * a.s.ps];
+                ux = a.s.ux[ip * a.s.ps]; uy = a.s.uy[ip * a.s.ps]; uz = a.s.uz[ip * a.s.ps]; ig = a.s.ig[ip * a.s.ps];
+                w = a.s.w[ip * a.s.ps];
+            }
             x = half_push(x, a.cdt, ig, ux); y = half_push(y, a.cdt, ig, uy);
             const double X = grid_coord(x, x0, a.inv_dx), Y = grid_coord(y, y0, a.inv_dy);
             const double rX = nearest(X), rY = nearest(Y), fX = floor(X), fY = floor(Y);
@@ -650,9 +673,20 @@ __global__ void __launch_bounds__(NW * 32, 4) k_push_tile2d(const TileArgs a) {
                 for (int c = 0; c < 6; c++) a.s.part[c][ip] = f[c];
             }
             boris_kick(ux, uy, uz, ig, f, a.efactor, a.bfactor);
-            a.s.ux[ip * a.s.ps] = ux; a.s.uy[ip * a.s.ps] = uy; a.s.uz[ip * a.s.ps] = uz; a.s.ig[ip * a.s.ps] = ig;
             x += a.cdt * ig * ux; y += a.cdt * ig * uy;
-            a.s.x[ip * a.s.ps] = x; a.s.y[ip * a.s.ps] = y;
+            if (!REC) {
+                a.s.ux[ip * a.s.ps] = ux; a.s.uy[ip * a.s.ps] = uy; a.s.uz[ip * a.s.ps] = uz; a.s.ig[ip * a.s.ps] = ig;
+                a.s.x[ip * a.s.ps] = x; a.s.y[ip * a.s.ps] = y;
+            }
+        }
+        if (REC) {
+            if (active) {
+                double2 *stg = reinterpret_cast<double2 *>(red);
+                stg[lane * 5] = make_double2(x, y);
+                stg[lane * 5 + 2] = make_double2(ux, uy); stg[lane * 5 + 3] = make_double2(uz, ig);
+                w = red[lane * 10 + 3];
+            }
+            rec_store_warp(a.rec, off, t0, wlast, lane, red);
         }
         // ---- deposit set-up (current_deposit.h:196-222) ----------------------------------------------------------------
         const double vx = ux * LPIC_C_LIGHT * ig, vy = uy * LPIC_C_LIGHT * ig, vz = uz * LPIC_C_LIGHT * ig;
@@ -745,8 +779,10 @@ int launch_tiles2d(lpic_ctx *c, Species &sp, double dt, double q, double m, bool
     constexpr size_t push_smem = sizeof(double) * (6 * (TX + 3) * (TY + 4) + NW * 30 * 33) + sizeof(int) * NW * 32;
     if (!c->tile2d_attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(k_tile_perm<TX, TY, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_PERM_SMEM_LIMIT));
-        CUDA_TRY(cudaFuncSetAttribute(k_push_tile2d<TX, TY, NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)push_smem));
-        CUDA_TRY(cudaFuncSetAttribute(k_push_tile2d<TX, TY, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)push_smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_push_tile2d<TX, TY, NW, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)push_smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_push_tile2d<TX, TY, NW, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)push_smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_push_tile2d<TX, TY, NW, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)push_smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_push_tile2d<TX, TY, NW, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)push_smem));
         c->tile2d_attr_set = true;
     }
     CUDA_TRY(cudaMemsetAsync(d_nlist, 0, sizeof(int) * g.npatch, c->stream));
@@ -760,8 +796,14 @@ int launch_tiles2d(lpic_ctx *c, Species &sp, double dt, double q, double m, bool
     ta.inv_dx = pa.inv_dx; ta.inv_dy = pa.inv_dy; ta.inv_dz = 1.0;
     ta.q_dV = q / (g.dx * g.dy); ta.q_dydzdt = q / (g.dy * dt); ta.q_dxdzdt = q / (g.dx * dt); ta.q_dxdydt = 0.0;
     const unsigned grid = (unsigned)((i64)g.npatch * ntile);
-    if (write_part) k_push_tile2d<TX, TY, NW, true><<<grid, NW * 32, push_smem, c->stream>>>(ta);
-    else k_push_tile2d<TX, TY, NW, false><<<grid, NW * 32, push_smem, c->stream>>>(ta);
+    ta.rec = sp.rec;
+    if (sp.rec) {
+        if (write_part) k_push_tile2d<TX, TY, NW, true, true><<<grid, NW * 32, push_smem, c->stream>>>(ta);
+        else k_push_tile2d<TX, TY, NW, false, true><<<grid, NW * 32, push_smem, c->stream>>>(ta);
+    } else {
+        if (write_part) k_push_tile2d<TX, TY, NW, true, false><<<grid, NW * 32, push_smem, c->stream>>>(ta);
+        else k_push_tile2d<TX, TY, NW, false, false><<<grid, NW * 32, push_smem, c->stream>>>(ta);
+    }
     LAUNCHED(1);
     const unsigned lgrid = (unsigned)std::min<i64>(g.npatch, 148 * 8);
     if (write_part) k_list_particles<true, 2><<<lgrid, 128, 0, c->stream>>>(g, c->fields, c->d_x0, c->d_y0, c->d_z0, ta.s, c->scr_a, d_nlist, dt, q, m);

@@ -328,12 +328,14 @@ __device__ __forceinline__ int patch_of(const i64 *__restrict__ poff, int npatch
     }
     return lo;
 }
+// (the launch covers the patches [p0, p0 + npatch) whose moved slots are [base, base + total) of the compact list)
 __global__ void __launch_bounds__(256) k_sort_gather_all(MoveArgs A, double *__restrict__ buf, i64 total, const int *__restrict__ src_of,
-                                                         const i64 *__restrict__ off, const i64 *__restrict__ poff, int npatch) {
+                                                         const i64 *__restrict__ off, const i64 *__restrict__ poff, int p0, int npatch,
+                                                         i64 base) {
     const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    const int p = patch_of(poff, npatch, i);
-    const i64 src = off[p] + src_of[off[p] + (i - poff[p])];
+    const int p = p0 + patch_of(poff + p0, npatch, i + base);
+    const i64 src = off[p] + src_of[off[p] + (i + base - poff[p])];
     double v[LPIC_NPATTR];
     double2 r[4];
 #pragma unroll
@@ -353,11 +355,12 @@ __global__ void __launch_bounds__(256) k_sort_gather_all(MoveArgs A, double *__r
     if (A.dead) ((u8 *)(words + (size_t)A.n * total))[i] = A.dead[src];
 }
 __global__ void __launch_bounds__(256) k_sort_scatter_all(MoveArgs A, const double *__restrict__ buf, i64 total, const int *__restrict__ tgt,
-                                                          const i64 *__restrict__ off, const i64 *__restrict__ poff, int npatch) {
+                                                          const i64 *__restrict__ off, const i64 *__restrict__ poff, int p0, int npatch,
+                                                          i64 base) {
     const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    const int p = patch_of(poff, npatch, i);
-    const i64 dst = off[p] + tgt[off[p] + (i - poff[p])];
+    const int p = p0 + patch_of(poff + p0, npatch, i + base);
+    const i64 dst = off[p] + tgt[off[p] + (i + base - poff[p])];
     const double2 *pieces = reinterpret_cast<const double2 *>(buf);
 #pragma unroll
     for (int k = 0; k < 4; k++)
@@ -440,35 +443,52 @@ extern "C" int lpic_sort(lpic_ctx *c, int ispec, int reverse_x, int64_t nxb, int
         for (i64 p = 0; p < n; p++) { poff[p] = run; run += h_nbuf[p]; }
         i64 *d_poff = d_nbuf + n;
         CUDA_TRY(cudaMemcpyAsync(d_poff, poff.data(), sizeof(i64) * n, cudaMemcpyHostToDevice, c->stream));
-        // What has to move, in rows of the staging buffer (one row = one 8-byte word per moved slot): the record arena as
-        // four 16-byte pieces of two rows each -- or, when more than half of all slots move and not even one piece fits, as
-        // eight strided words -- then the plain arrays, then the is_dead bytes (less than a row; alone if no row is left).
-        // Every group is gathered completely before it is scattered: sources and targets are the same set of slots.
-        const i64 room = std::max<i64>(1, c->scr_cap / total);
+        // The permutation never leaves a patch, so the move is done for one group of consecutive patches at a time, each
+        // group small enough that ALL its attributes fit the staging buffer at once: whole 64-byte records (two full
+        // sectors per moved slot) instead of four passes over half-used sectors, and the slot lists are read once.  That is
+        // what the first steps of a run need, when the reference's growth rule makes up to half of all slots change
+        // bucket.  A single patch too large for that (few-patch runs) falls back to moving its attributes in turns.
         struct Item { double *ptr; int stride; };
-        std::vector<Item> words;
-        int pieces_left = 0;
-        if (sp.rec) {
-            if (room >= 2) pieces_left = 4;
-            else for (int at = 0; at < LPIC_NREC; at++) words.push_back({sp.rec + at, LPIC_NREC});
-        }
+        std::vector<Item> plain;
         for (int at = sp.rec ? LPIC_NREC : 0; at < LPIC_NPATTR; at++)
-            if (sp.attr[at]) words.push_back({sp.attr[at], 1});
-        const unsigned grid = (unsigned)div_up(total, 256);
-        size_t a0 = 0;
-        bool dead_done = false;
-        while (a0 < words.size() || pieces_left > 0 || !dead_done) {
-            MoveArgs A;
-            A.n = 0; A.dead = nullptr; A.rec = sp.rec; A.piece0 = 4 - pieces_left; A.npiece = 0;
-            i64 rows = 0;
-            while (pieces_left > 0 && rows + 2 <= room) { A.npiece++; pieces_left--; rows += 2; }
-            while (pieces_left == 0 && a0 < words.size() && rows + 1 <= room && A.n < LPIC_NPATTR) {
-                A.a[A.n] = words[a0].ptr; A.stride[A.n] = words[a0].stride; A.n++; a0++; rows++;
+            if (sp.attr[at]) plain.push_back({sp.attr[at], 1});
+        const i64 rows_all = (sp.rec ? LPIC_NREC : 0) + (i64)plain.size() + 1;  // 8-byte words per moved slot, is_dead included
+        i64 p0 = 0;
+        while (p0 < n) {
+            i64 p1 = p0, cnt = 0;
+            while (p1 < n && (cnt == 0 || (cnt + h_nbuf[p1]) * rows_all <= c->scr_cap)) cnt += h_nbuf[p1++];
+            const i64 base = poff[p0];
+            if (cnt > 0) {
+                // rows of the staging buffer (one row = one word per moved slot of the group): the record arena as four
+                // 16-byte pieces of two rows each -- or, if not even one piece fits, as eight strided words -- then the
+                // plain arrays, then the is_dead bytes (less than a row; alone if no row is left).  Every pass is gathered
+                // completely before it is scattered: sources and targets are the same set of slots.
+                const i64 room = std::max<i64>(1, c->scr_cap / cnt);
+                std::vector<Item> words;
+                int pieces_left = 0;
+                if (sp.rec) {
+                    if (room >= 2) pieces_left = 4;
+                    else for (int at = 0; at < LPIC_NREC; at++) words.push_back({sp.rec + at, LPIC_NREC});
+                }
+                words.insert(words.end(), plain.begin(), plain.end());
+                const unsigned grid = (unsigned)div_up(cnt, 256);
+                size_t a0 = 0;
+                bool dead_done = false;
+                while (a0 < words.size() || pieces_left > 0 || !dead_done) {
+                    MoveArgs A;
+                    A.n = 0; A.dead = nullptr; A.rec = sp.rec; A.piece0 = 4 - pieces_left; A.npiece = 0;
+                    i64 rows = 0;
+                    while (pieces_left > 0 && rows + 2 <= room) { A.npiece++; pieces_left--; rows += 2; }
+                    while (pieces_left == 0 && a0 < words.size() && rows + 1 <= room && A.n < LPIC_NPATTR) {
+                        A.a[A.n] = words[a0].ptr; A.stride[A.n] = words[a0].stride; A.n++; a0++; rows++;
+                    }
+                    if (pieces_left == 0 && a0 == words.size() && (rows + 1 <= room || rows == 0)) { A.dead = sp.dead; dead_done = true; }
+                    k_sort_gather_all<<<grid, 256, 0, c->stream>>>(A, c->scr_buf, cnt, c->scr_b, sp.d_off, d_poff, (int)p0, (int)(p1 - p0), base);
+                    k_sort_scatter_all<<<grid, 256, 0, c->stream>>>(A, c->scr_buf, cnt, c->scr_a, sp.d_off, d_poff, (int)p0, (int)(p1 - p0), base);
+                    LAUNCHED(2);
+                }
             }
-            if (pieces_left == 0 && a0 == words.size() && (rows + 1 <= room || rows == 0)) { A.dead = sp.dead; dead_done = true; }
-            k_sort_gather_all<<<grid, 256, 0, c->stream>>>(A, c->scr_buf, total, c->scr_b, sp.d_off, d_poff, (int)n);
-            k_sort_scatter_all<<<grid, 256, 0, c->stream>>>(A, c->scr_buf, total, c->scr_a, sp.d_off, d_poff, (int)n);
-            LAUNCHED(2);
+            p0 = p1;
         }
         KERNEL_CHECK();
     }

@@ -76,3 +76,57 @@ def test_tile_and_sorted_kernels_agree(monkeypatch):
     a, _ = _run(wl, 2)
     b, _ = _run(wl, 2, env={"LPIC_PUSH_SORTED": "1"}, monkeypatch=monkeypatch)
     assert max(a.values()) <= 1e-12 and max(b.values()) <= 1e-12, (a, b)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_record_layout_and_separate_arrays_agree(dim, monkeypatch):
+    """The device keeps x y z w ux uy uz inv_gamma as 64-byte records (default) or as eight arrays (LPIC_PARTICLE_LAYOUT=soa,
+    chosen when a species is allocated).  After three full steps from zero slack (sort, push, deposit, migration with growth
+    and an arena re-layout) both must sit on the oracle, their integer state (capacities, is_dead, _id = the slot permutation)
+    must be identical, and their floats must agree to the rounding noise of the deposit's atomic adds (whose order between
+    CTAs is not fixed: 1e-13 of each array's max-abs)."""
+    from oracle import oracle as orc
+    from tests import gpu_harness as h
+    from lambdapic_b200.workloads import ThermalPlasma
+    if dim == 3:
+        wl = ThermalPlasma(dim=3, cells=(32, 32, 32), patch=(16, 16, 16), ppc=(5, 3), temperature_eV=5.0e4)
+    else:
+        wl = ThermalPlasma(dim=2, cells=(64, 64), patch=(16, 32), ppc=(7, 5), temperature_eV=5.0e4)
+    views = []
+    for layout in ("rec", "soa"):
+        if layout == "soa":
+            monkeypatch.setenv("LPIC_PARTICLE_LAYOUT", "soa")
+        else:
+            monkeypatch.delenv("LPIC_PARTICLE_LAYOUT", raising=False)
+        g = h.synthetic_snapshot(wl)
+        eng, meta = h.engine_from_golden(g, "t0", with_part=True, slack=1.0, min_extra=0)  # zero slack: growth re-lays the arena out
+        ost = orc.OState.from_golden(g, "t0")
+        rev = [False] * eng.nspec
+        ost.set_reverse_x(rev)
+        for _ in range(3):
+            eng.step(meta["dt"], meta["q"], meta["m"], rev, write_part=True)
+            orc.step(ost, "ref" if orc.have_ref() else "port")
+        worst = h.compare_with_oracle(eng, ost, rtol=1e-12)
+        assert max(worst.values()) <= 1e-12, (layout, worst)
+        st = h.host_view(eng, with_sorter=False)
+        snap = {}
+        for ip, patch in enumerate(st.patches):  # copies: the mirrors go away with the engine
+            for name, arr in vars(patch.fields).items():
+                snap[(ip, name)] = np.array(arr, copy=True)
+            for isp, pt in enumerate(patch.particles):
+                for name, arr in vars(pt).items():
+                    if arr is not None:
+                        snap[(ip, isp, name)] = np.array(arr, copy=True)
+        views.append(snap)
+        eng.close()
+    a, b = views
+    assert set(a) == set(b)
+    for k in a:
+        assert a[k].shape == b[k].shape, k
+        if k[-1] in ("is_dead", "_id"):
+            assert a[k].tobytes() == b[k].tobytes(), k
+        else:
+            alive = np.isfinite(a[k]) & np.isfinite(b[k])
+            assert (np.isfinite(a[k]) == np.isfinite(b[k])).all(), k
+            scale = max(float(np.abs(a[k][alive]).max()) if alive.any() else 0.0, 1e-300)
+            assert float(np.abs(a[k][alive] - b[k][alive]).max() if alive.any() else 0.0) <= 1e-13 * scale, k
