@@ -281,6 +281,14 @@ class Simulation:
         self.pairproduction = [None] * len(self.species)
         self._init_sorter()
         self.load_balancer = None
+        if self.mpi.size > 1:
+            # The communicator belongs to set-up, as in the reference (MPIManager is built in initialize,
+            # simulation/simulation.py:700-720): create it here and run one guard exchange of the (consistent) initial fields
+            # so that NCCL's connection set-up -- seconds -- is not paid by the first step of run().
+            xch = self.mpi.xch  # (straight on the device copy: the host mirrors stay authoritative until run() uploads them)
+            xch.halo_start(self.mpi._mask(["ex", "ey", "ez"]), 0)
+            xch.halo_wait()
+            self.bridge.engine.sync()
         self.initialized = True
         comm.Barrier()
 
