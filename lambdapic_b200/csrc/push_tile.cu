@@ -194,6 +194,7 @@ struct TileArgs {
     Geom g;
     double *F;
     double *rec;  // records (x y z w | ux uy uz inv_gamma) of 64 bytes per slot, REC kernels only
+    bool prefetch;
     const double *px0, *py0, *pz0;
     Slots s;
     const int *perm, *tile_start;
@@ -310,6 +311,7 @@ __device__ __noinline__ double row_sum(double acc, unsigned heads, const double 
 
 template <int TX, int TY, int TZ, int NW, bool WRITE_PART, bool REC>
 __global__ void __launch_bounds__(NW * 32, TILE_MIN_CTAS) k_push_tile(const TileArgs a) {
+    const bool PREFETCH = a.prefetch;
     constexpr int EX = TX + 3, EY = TY + 3, EZ = TZ + 4, EN = EX * EY * EZ;  // EZ: TZ + 3 nodes, padded to an even row length
     constexpr int SX = EY * EZ, SY = EZ;  // strides (in doubles) of the staged tile
     extern __shared__ __align__(16) double smem[];
@@ -366,6 +368,8 @@ __global__ void __launch_bounds__(NW * 32, TILE_MIN_CTAS) k_push_tile(const Tile
         if (active && (!REC || WRITE_PART)) local = a.perm[off + t0 + lane];
         if (REC) {
             rec_load_warp(a.rec, a.perm, off, t0, wlast, lane, red);
+            if (PREFETCH && t0 + 32 + lane < wlast)  // the next iteration's record on its way into L2 while this one computes
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rec + (off + a.perm[off + t0 + 32 + lane]) * LPIC_NREC));
             if (active) {
                 const double2 *stg = reinterpret_cast<const double2 *>(red);
                 const double2 r0 = stg[lane * 5], r2 = stg[lane * 5 + 2], r3 = stg[lane * 5 + 3];
@@ -789,7 +793,7 @@ int launch_tiles2d(lpic_ctx *c, Species &sp, double dt, double q, double m, bool
     k_tile_perm<TX, TY, 1, 2><<<g.npatch, PT, perm_smem, c->stream>>>(pa);
     LAUNCHED(1);
     TileArgs ta;
-    ta.g = g; ta.F = c->fields; ta.rec = nullptr; ta.px0 = c->d_x0; ta.py0 = c->d_y0; ta.pz0 = c->d_z0; ta.s = make_slots(sp);
+    ta.g = g; ta.F = c->fields; ta.rec = nullptr; ta.prefetch = getenv("LPIC_REC_NO_PREFETCH") == nullptr; ta.px0 = c->d_x0; ta.py0 = c->d_y0; ta.pz0 = c->d_z0; ta.s = make_slots(sp);
     ta.perm = c->scr_b; ta.tile_start = c->d_tile_start; ta.list = c->scr_a; ta.nlist = d_nlist;
     ta.nty = nty; ta.ntz = 1; ta.ntile = ntile;
     ta.dt = dt; ta.cdt = pa.cdt; ta.efactor = q * dt / (2 * m * LPIC_C_LIGHT); ta.bfactor = q * dt / (2 * m);
@@ -853,7 +857,7 @@ int launch_tiles(lpic_ctx *c, Species &sp, double dt, double q, double m, bool w
     k_tile_perm<TX, TY, TZ, 3><<<g.npatch, PT, perm_smem, c->stream>>>(pa);
     LAUNCHED(1);
     TileArgs ta;
-    ta.g = g; ta.F = c->fields; ta.rec = nullptr; ta.px0 = c->d_x0; ta.py0 = c->d_y0; ta.pz0 = c->d_z0; ta.s = make_slots(sp);
+    ta.g = g; ta.F = c->fields; ta.rec = nullptr; ta.prefetch = getenv("LPIC_REC_NO_PREFETCH") == nullptr; ta.px0 = c->d_x0; ta.py0 = c->d_y0; ta.pz0 = c->d_z0; ta.s = make_slots(sp);
     ta.perm = c->scr_b; ta.tile_start = c->d_tile_start; ta.list = c->scr_a; ta.nlist = d_nlist;
     ta.nty = nty; ta.ntz = ntz; ta.ntile = ntile;
     ta.dt = dt; ta.cdt = pa.cdt; ta.efactor = q * dt / (2 * m * LPIC_C_LIGHT); ta.bfactor = q * dt / (2 * m);
