@@ -12,10 +12,13 @@
  *             N = n + 2*n_guard and the reference's WRAPPED guard layout (logical index -k lives at N-k).
  *             Device arena = [attr][patch][NX*NY*NZ]; the host mirror handed to upload/download has the
  *             same shape, so one copy moves one attribute of every patch.
- *   particles SoA fp64 x y z w ux uy uz inv_gamma ex_part..bz_part _id + uint8 is_dead per
- *             (species, patch).  Device arena per (species, attribute): patch p owns the slots
- *             [off[p], off[p] + npart[p]) of a segment of physical size pcap[p] >= npart[p]; `npart`
- *             is the reference's capacity (alive + dead slots).  The six *_part arrays are optional.
+ *   particles fp64 x y z w ux uy uz inv_gamma ex_part..bz_part _id + uint8 is_dead per (species, patch).
+ *             HOST side of every call: one array per attribute with the arena layout below (the reference's
+ *             numpy arrays, core/particles.py:60-89).  Patch p owns the slots [off[p], off[p] + npart[p]) of a
+ *             segment of physical size pcap[p] >= npart[p]; `npart` is the reference's capacity (alive + dead
+ *             slots).  The six *_part arrays are optional.  DEVICE side (internal): x y z w ux uy uz inv_gamma
+ *             are interleaved into one 64-byte record per slot, the others are plain arrays; the upload /
+ *             download entries convert.
  */
 #ifndef LPIC_B200_H
 #define LPIC_B200_H

@@ -6,7 +6,8 @@
 // core/pusher/boris.py:6-38, core/pusher/cpu.py:58-90.
 //
 // Kernel structure (round 1): one thread per particle slot, blocks never straddle a patch so the patch's
-// grid base pointers are block-uniform; SoA attribute streams are read/written coalesced; E/B are read
+// grid base pointers are block-uniform; the attribute streams (records or separate arrays, indexed through Slots::ps) are
+// read/written in slot order; E/B are read
 // through L1 (a patch tile + guards is 85 KB per component at 16^3); J/rho are accumulated with native
 // fp64 global reductions (REDG.E.ADD.F64) that resolve in L2 because consecutive blocks work on one patch.
 // Floating-point contract: the reference is itself built with FMA contraction, so results agree to

@@ -1,4 +1,4 @@
-// Per-patch in-place bucket sort of the particle SoA, reproducing the reference's slot permutation bit-for-bit.
+// Per-patch in-place bucket sort of the particle arenas (records + plain arrays), reproducing the reference's slot permutation bit-for-bit.
 //
 // Reference behaviour restated (not copied): core/sort/cpu3d.c:8-156 (calculate_cell_index, calculate_bucket_bound,
 // bucket_sort_3d), driver :214-299, 2D twin core/sort/cpu2d.c; facade core/sort/particle_sort.py.
