@@ -120,6 +120,7 @@ static void free_species(Species &sp) {
     cudaFree(sp.dead); sp.dead = nullptr;
     cudaFree(sp.d_off); cudaFree(sp.d_npart); sp.d_off = sp.d_npart = nullptr;
     cudaFree(sp.sort.bucket_count); cudaFree(sp.sort.bound_min); cudaFree(sp.sort.bound_max); cudaFree(sp.sort.pidx);
+    cudaFree(sp.sort.kcache); cudaFree(sp.sort.d_korg); delete[] sp.sort.h_korg;
     sp.sort = SortState();
     cudaFree(sp.d_out); cudaFree(sp.d_ndead); cudaFree(sp.d_incoming); cudaFree(sp.d_extend); cudaFree(sp.d_alive);
     sp.d_out = sp.d_ndead = sp.d_incoming = sp.d_extend = sp.d_alive = nullptr;
@@ -480,7 +481,7 @@ extern "C" int lpic_upload_particles(lpic_ctx *c, int ispec, int attr, const voi
     if (in_record(sp, attr)) { if (int r = xfer_one(c, sp, attr, (void *)host, 0, sp.total, true)) return r; }
     else CUDA_TRY(cudaMemcpyAsync(dev, host, esz * sp.total, cudaMemcpyHostToDevice, c->stream));
     sp.sort.valid = false;
-    sp.lists_valid = false;
+    sp.lists_valid = false; sp.sort.keys_valid = sp.sort.keys_written = false;
     return 0;
 }
 // The record attributes named by mask (bit a = attribute a < 8) in one pass: host[a] = base of the arena-layout array of
@@ -494,7 +495,7 @@ extern "C" int lpic_upload_particle_records(lpic_ctx *c, int ispec, uint32_t mas
         for (int t = 0; t < LPIC_NREC; t++)
             if (mask >> t & 1u) CUDA_TRY(cudaMemcpyAsync(sp.attr[t], host[t], sizeof(double) * sp.total, cudaMemcpyHostToDevice, c->stream));
     sp.sort.valid = false;
-    sp.lists_valid = false;
+    sp.lists_valid = false; sp.sort.keys_valid = sp.sort.keys_written = false;
     return 0;
 }
 extern "C" int lpic_download_particle_records(lpic_ctx *c, int ispec, uint32_t mask, double *const *host) {
@@ -520,7 +521,7 @@ extern "C" int lpic_upload_particles_patch(lpic_ctx *c, int ispec, int attr, int
     if (in_record(sp, attr)) { if (int r = xfer_one(c, sp, attr, (void *)host_arena, sp.h_off[patch], sp.h_npart[patch], true)) return r; }
     else if (bytes) CUDA_TRY(cudaMemcpyAsync((char *)dev + first, (const char *)host_arena + first, bytes, cudaMemcpyHostToDevice, c->stream));
     sp.sort.valid = false;
-    sp.lists_valid = false;
+    sp.lists_valid = false; sp.sort.keys_valid = sp.sort.keys_written = false;
     return 0;
 }
 // Vacuum fields (all ten attributes) and psi arrays of the listed patches, on the device (callback/utils.py:790-800)
@@ -559,7 +560,7 @@ extern "C" int lpic_upload_particle_ptrs(lpic_ctx *c, int ispec, int attr, const
         }
     }
     sp.sort.valid = false;
-    sp.lists_valid = false;
+    sp.lists_valid = false; sp.sort.keys_valid = sp.sort.keys_written = false;
     return 0;
 }
 extern "C" int lpic_download_particle_ptrs(lpic_ctx *c, int ispec, int attr, void *const *ptrs) {
@@ -731,7 +732,7 @@ extern "C" int lpic_species_extend(lpic_ctx *c, int ispec, const int64_t *ext, c
     }
     int r = upload_layout(c, sp);  // synchronises the stream: the host tables above may go out of scope
     sp.sort.valid = false;
-    sp.lists_valid = false;
+    sp.lists_valid = false; sp.sort.keys_valid = sp.sort.keys_written = false;
     return r;
 }
 
@@ -747,7 +748,7 @@ extern "C" int lpic_species_set_npart(lpic_ctx *c, int ispec, const int64_t *npa
                 (long long)npart[p], (long long)sp.h_pcap[p]);
     for (i64 p = 0; p < n; p++) sp.h_npart[p] = npart[p];
     sp.sort.valid = false;
-    sp.lists_valid = false;
+    sp.lists_valid = false; sp.sort.keys_valid = sp.sort.keys_written = false;
     return upload_layout(c, sp);
 }
 

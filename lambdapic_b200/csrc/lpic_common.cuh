@@ -26,7 +26,24 @@ struct Geom {
     double dx, dy, dz;
 };
 
+// Everything the bucket key of a position depends on (lpic_sort's arguments); org = (3, npatch) bucket origins on the device
+struct SortKeyParams {
+    const double *org = nullptr;
+    int npatch = 0, nxb = 0, nyb = 0, nzb = 0, nbin = 0, reverse_x = 0, dim = 0;
+    double dxb = 0, dyb = 0, dzb = 0;
+};
+
 struct SortState {
+    // Bucket keys left behind by the migration (migrate.cu): its classification pass reads every alive slot's position at
+    // the end of step n, which is the position the sorter of step n+1 keys by -- except for the slots the migration itself
+    // fills, and it keys those too.  With records a position-only pass pays for whole 64-byte DRAM accesses, so the sorter
+    // reading 4 + 1 bytes per slot instead is worth a 4-byte array.  keys_valid: every alive slot's key is current for the
+    // parameters in kp; anything else that moves particles or slots clears it.
+    int *kcache = nullptr;
+    i64 kcache_cap = 0;
+    bool keys_written = false, keys_valid = false, have_kp = false;
+    SortKeyParams kp;
+    double *d_korg = nullptr, *h_korg = nullptr;  // this species' bucket origins (3, npatch), device and host copies
     i64 nxb = 0, nyb = 0, nzb = 0, nbin = 0;
     i64 *bucket_count = nullptr, *bound_min = nullptr, *bound_max = nullptr;  // (npatch, nbin) device
     int *pidx = nullptr;                                                       // arena-sized, pre-sort bucket of every slot
@@ -222,6 +239,28 @@ __host__ __device__ inline int dir_opposite(int dim, int b) {
 }
 
 __host__ __device__ inline int wrapneg(int i, int N) { return i < 0 ? i + N : i; }
+
+// Bucket of a position (core/sort/cpu3d.c:8-60 calculate_cell_index, restated): bucket coordinates as doubles (floor of the
+// reference's quotient); NaN compares false everywhere and ends up out of range / clamped to 0, like
+// (npy_intp)floor(NaN) = INT64_MIN does on the host.  Single-bucket axes (ny_buckets = nz_buckets = 1, the default):
+// floor(v / d) is 0 exactly when 0 <= v < d -- for doubles v < d the rounded quotient is at most 1 - 2^-53 < 1 -- so the
+// reference's division is replaced by two comparisons there without changing any result.  ONE definition, used by the
+// sorter and by the migration kernels that leave keys behind for it.
+__device__ __forceinline__ int sort_bucket_key(const SortKeyParams &k, double x0, double y0, double z0, double px, double py, double pz) {
+    const double fx = floor((px - x0) / k.dxb);
+    const double vy = py - y0, vz = k.dim == 3 ? pz - z0 : 0.0;
+    const double fy = k.nyb == 1 ? (vy >= 0.0 ? (vy < k.dyb ? 0.0 : 1.0) : -1.0) : floor(vy / k.dyb);
+    const double fz = k.dim != 3 ? 0.0 : (k.nzb == 1 ? (vz >= 0.0 ? (vz < k.dzb ? 0.0 : 1.0) : -1.0) : floor(vz / k.dzb));
+    const bool inx = fx >= 0.0 && fx < (double)k.nxb, iny = fy >= 0.0 && fy < (double)k.nyb, inz = fz >= 0.0 && fz < (double)k.nzb;
+    if (k.reverse_x) {
+        const int ix = inx ? (int)fx : (fx >= (double)k.nxb ? k.nxb - 1 : 0);
+        const int iy = iny ? (int)fy : (fy >= (double)k.nyb ? k.nyb - 1 : 0);
+        const int iz = inz ? (int)fz : (fz >= (double)k.nzb ? k.nzb - 1 : 0);
+        return iz + iy * k.nzb + (k.nxb - 1 - ix) * k.nyb * k.nzb;
+    }
+    if (inx && iny && inz) return (int)fz + (int)fy * k.nzb + (int)fx * k.nyb * k.nzb;
+    return k.nbin - 1;
+}
 
 // kernels' launch helpers
 static inline unsigned div_up(i64 a, i64 b) { return (unsigned)((a + b - 1) / b); }

@@ -29,6 +29,8 @@ struct MigArgs {
     const i64 *remote_in;                          // per patch: arrivals from other ranks take the first dead slots (null: none)
     int *la, *lb;                                  // arena-sized int lists
     int *dirstart;                                 // (npatch, nb)
+    SortKeyParams kp;  // the sorter's parameters and ...
+    int *kcache;       // ... its key cache (SortState): every kernel that sees or sets a position leaves the bucket key (null: off)
     double *attrs[LPIC_NPATTR];
     int astride[LPIC_NPATTR];  // 8 for the attributes inside the record arena, else 1
     int ps;                    // stride of x, y, z
@@ -36,22 +38,25 @@ struct MigArgs {
     double glob[6], cell[3];
 };
 
-__device__ __forceinline__ int classify(const MigArgs &a, const double *bx, i64 ip) {
-    double x, y;
+__device__ __forceinline__ void load_position(const MigArgs &a, i64 ip, double &x, double &y, double &z) {
     if (a.ps == LPIC_NREC) {
         const double2 xy = *reinterpret_cast<const double2 *>(a.x + ip * LPIC_NREC);
         x = xy.x; y = xy.y;
     } else {
         x = a.x[ip]; y = a.y[ip];
     }
+    z = a.dim == 3 ? a.z[ip * a.ps] : 0.0;
+}
+__device__ __forceinline__ int classify_position(const MigArgs &a, const double *bx, double x, double y, double z) {
     const int sx = x < bx[0] ? -1 : (x > bx[1] ? 1 : 0);
     const int sy = y < bx[2] ? -1 : (y > bx[3] ? 1 : 0);
-    int sz = 0;
-    if (a.dim == 3) {
-        const double z = a.z[ip * a.ps];
-        sz = z < bx[4] ? -1 : (z > bx[5] ? 1 : 0);
-    }
+    const int sz = a.dim == 3 ? (z < bx[4] ? -1 : (z > bx[5] ? 1 : 0)) : 0;
     return dir_lookup(a.dim, sx, sy, sz);  // -1 when inside
+}
+__device__ __forceinline__ int classify(const MigArgs &a, const double *bx, i64 ip) {
+    double x, y, z;
+    load_position(a, ip, x, y, z);
+    return classify_position(a, bx, x, y, z);
 }
 
 __device__ __forceinline__ int warp_incl_sum(int v) {
@@ -105,6 +110,8 @@ __global__ void __launch_bounds__(T) k_lists(MigArgs a) {
     const i64 off = a.off[p];
     const int np = (int)a.npart[p];
     const double *bx = a.box + 6 * (size_t)p;
+    double kx0 = 0.0, ky0 = 0.0, kz0 = 0.0;
+    if (a.kcache) { kx0 = a.kp.org[p]; ky0 = a.kp.org[a.kp.npatch + p]; kz0 = a.kp.org[2 * a.kp.npatch + p]; }
     if (tid < 32) s_cnt[tid] = 0;
     __syncthreads();
     int nl = 0, nd = 0;
@@ -124,8 +131,12 @@ __global__ void __launch_bounds__(T) k_lists(MigArgs a) {
                 if (ip < np) {
                     if (a.dead[off + ip] != 0) code = 1;
                     else {
-                        const int b = classify(a, bx, off + ip);
+                        double x, y, z;
+                        load_position(a, off + ip, x, y, z);
+                        const int b = classify_position(a, bx, x, y, z);
                         if (b >= 0) { code = 2; atomicAdd(&s_cnt[b], 1); }
+                        // the position the next step's sorter keys by (the leavers' slots will be dead by then)
+                        if (a.kcache) a.kcache[off + ip] = sort_bucket_key(a.kp, kx0, ky0, kz0, x, y, z);
                     }
                 }
                 s_code[(tid >> 5) * (32 * IT) + 32 * m + lane] = code;
@@ -214,6 +225,7 @@ __global__ void __launch_bounds__(T) k_fill(MigArgs a, int blocks_per_patch) {
     const i64 np = a.npart[p];
     const i64 dst = a.off[p] + a.la[a.off[p] + np - 1 - (k + skip)];
     const double *bx = a.box + 6 * (size_t)p;
+    double kpx = 0.0, kpy = 0.0, kpz = 0.0;
     for (int t = 0; t < a.nattr; t++) {
         double v = a.attrs[t][src * a.astride[t]];
         const int d = t == a.ia_x ? 0 : (t == a.ia_y ? 1 : (t == a.ia_z ? 2 : -1));
@@ -221,10 +233,13 @@ __global__ void __launch_bounds__(T) k_fill(MigArgs a, int blocks_per_patch) {
             const double lo = a.glob[2 * d], hi = a.glob[2 * d + 1], L = hi - lo, c0 = v;
             if (c0 > hi && fabs(bx[2 * d] - lo) < a.cell[d]) v -= L;
             if (c0 < lo && fabs(bx[2 * d + 1] - hi) < a.cell[d]) v += L;
+            if (d == 0) kpx = v; else if (d == 1) kpy = v; else kpz = v;
         }
         a.attrs[t][dst * a.astride[t]] = v;
     }
     a.dead[dst] = 0;
+    if (a.kcache)  // the newcomer's bucket in its new patch, for the next step's sorter
+        a.kcache[dst] = sort_bucket_key(a.kp, a.kp.org[p], a.kp.org[a.kp.npatch + p], a.kp.org[2 * a.kp.npatch + p], kpx, kpy, kpz);
 }
 
 // mark_out_of_bound_as_dead (:326-346): alive outside the box -> dead with NaN position; in 3D every dead slot's
@@ -278,6 +293,11 @@ int make_args(lpic_ctx *c, int ispec, MigArgs &a) {
     a.out = sp.d_out; a.ndead = sp.d_ndead; a.incoming = sp.d_incoming; a.extend = sp.d_extend; a.alive = sp.d_alive;
     a.la = c->scr_a; a.lb = c->scr_b;
     a.remote_in = nullptr;
+    {   // the sorter's key cache: on when the sorter has run (parameters known) and its array covers the arena
+        SortState &st = sp.sort;
+        a.kp = st.kp;
+        a.kcache = (st.have_kp && st.kcache && st.kcache_cap >= sp.total) ? st.kcache : nullptr;
+    }
     a.dirstart = (int *)(c->d_tmp64 + 64);  // npatch*nb ints = 13 npatch i64 words at most; d_tmp64 holds 64 + 16 npatch (lpic_create)
     a.nattr = 0; a.ia_x = a.ia_y = a.ia_z = -1;
     for (int t = 0; t < LPIC_NPATTR; t++) {
@@ -334,6 +354,7 @@ __global__ void __launch_bounds__(T) k_remote_unpack(MigArgs a, const int *__res
     const i64 np = a.npart[p];
     const i64 dst = a.off[p] + a.la[a.off[p] + np - 1 - k];
     const double *bx = a.box + 6 * (size_t)p;
+    double kpx = 0.0, kpy = 0.0, kpz = 0.0;
     for (int t = 0; t < a.nattr; t++) {
         double v = rec[t];
         const int d = t == a.ia_x ? 0 : (t == a.ia_y ? 1 : (t == a.ia_z ? 2 : -1));
@@ -341,10 +362,13 @@ __global__ void __launch_bounds__(T) k_remote_unpack(MigArgs a, const int *__res
             const double lo = a.glob[2 * d], hi = a.glob[2 * d + 1], L = hi - lo, c0 = v;
             if (c0 > hi && fabs(bx[2 * d] - lo) < a.cell[d]) v -= L;
             if (c0 < lo && fabs(bx[2 * d + 1] - hi) < a.cell[d]) v += L;
+            if (d == 0) kpx = v; else if (d == 1) kpy = v; else kpz = v;
         }
         a.attrs[t][dst * a.astride[t]] = v;
     }
     a.dead[dst] = 0;
+    if (a.kcache)
+        a.kcache[dst] = sort_bucket_key(a.kp, a.kp.org[p], a.kp.org[a.kp.npatch + p], a.kp.org[2 * a.kp.npatch + p], kpx, kpy, kpz);
 }
 
 }  // namespace
@@ -367,6 +391,7 @@ extern "C" int lpic_remote_migrate_prepare(lpic_ctx *c, int ispec, int64_t *send
     const i64 n = c->g.npatch;
     const int nb = c->g.nb;
     k_lists<<<(unsigned)n, T, 0, c->stream>>>(a);  // counts + lists in one classification pass
+    c->spec[ispec].sort.keys_written = a.kcache != nullptr;
     LAUNCHED(1);
     KERNEL_CHECK();
     sp.remote_epoch = c->scratch_epoch;  // pack / unpack insist that nobody else used the shared scratch lists in between
@@ -396,6 +421,7 @@ extern "C" int lpic_remote_migrate_relist(lpic_ctx *c, int ispec) {
     MigArgs a;
     if (int r = make_args(c, ispec, a)) return r;
     k_lists<<<(unsigned)c->g.npatch, T, 0, c->stream>>>(a);
+    c->spec[ispec].sort.keys_written = a.kcache != nullptr;
     LAUNCHED(1);
     KERNEL_CHECK();
     c->spec[ispec].remote_epoch = c->scratch_epoch;
@@ -474,6 +500,7 @@ int lpic_mig_classify(lpic_ctx *c, int ispec, const i64 *) {
     if (int r = make_args(c, ispec, a)) return r;
     Species &sp = c->spec[ispec];
     k_lists<<<(unsigned)c->g.npatch, T, 0, c->stream>>>(a);
+    c->spec[ispec].sort.keys_written = a.kcache != nullptr;
     k_plan<<<div_up(c->g.npatch, 128), 128, 0, c->stream>>>(a);
     LAUNCHED(2);
     KERNEL_CHECK();
@@ -534,6 +561,7 @@ int lpic_mig_unpack_mark(lpic_ctx *c, int ispec, const double *const *dev_recv, 
     KERNEL_CHECK();
     sp.sort.valid = false;
     sp.lists_valid = false;
+    sp.sort.keys_valid = sp.sort.keys_written && a.kcache != nullptr;  // the migration is complete: every alive slot carries its bucket key
     return 0;
 }
 
@@ -545,6 +573,7 @@ extern "C" int lpic_migrate_count(lpic_ctx *c, int ispec, int64_t *to_extend, in
     Species &sp = c->spec[ispec];
     const i64 n = c->g.npatch;
     k_lists<<<(unsigned)n, T, 0, c->stream>>>(a);  // counts + leaver / dead-slot lists in one classification pass
+    c->spec[ispec].sort.keys_written = a.kcache != nullptr;
     LAUNCHED(1);
     sp.lists_valid = true;  // until the arrays grow (lpic_species_extend), anything else touches the slots ...
     sp.lists_epoch = c->scratch_epoch;  // ... or another operator uses the shared scratch lists
@@ -573,6 +602,7 @@ extern "C" int lpic_migrate_fill(lpic_ctx *c, int ispec) {
     if (sp.max_npart == 0) return 0;
     if (!sp.lists_valid || sp.lists_epoch != epoch) {  // e.g. the host grew some patches after the count: the new (dead) slots must enter the lists
         k_lists<<<(unsigned)n, T, 0, c->stream>>>(a);
+        c->spec[ispec].sort.keys_written = a.kcache != nullptr;
         LAUNCHED(1);
     }
     sp.lists_valid = false;
@@ -588,5 +618,6 @@ extern "C" int lpic_migrate_fill(lpic_ctx *c, int ispec) {
     KERNEL_CHECK();
     sp.sort.valid = false;
     sp.lists_valid = false;
+    sp.sort.keys_valid = sp.sort.keys_written && a.kcache != nullptr;  // the migration is complete: every alive slot carries its bucket key
     return 0;
 }

@@ -203,7 +203,7 @@ int launch_particles(lpic_ctx *c, int ispec, double dt, double q, double m, bool
         return -2;
     }
     if (sp.max_npart == 0) return 0;
-    sp.lists_valid = false;  // positions change: the migration lists no longer describe the slots
+    sp.lists_valid = false; sp.sort.keys_valid = sp.sort.keys_written = false;  // positions change: the migration lists no longer describe the slots
     const Geom &g = c->g;
     const int B = 128;
     const int bpp = (int)div_up(sp.max_npart, B);
@@ -231,7 +231,7 @@ extern "C" int lpic_push_deposit(lpic_ctx *c, int ispec, double dt, double q, do
         lpic_set_error("species %d was allocated without ex_part..bz_part", ispec);
         return -2;
     }
-    c->spec[ispec].lists_valid = false;
+    c->spec[ispec].lists_valid = false; c->spec[ispec].sort.keys_valid = c->spec[ispec].sort.keys_written = false;
     if (!(flags & LPIC_PUSH_SLOT_ORDER)) {
         // default in 3D: the tile kernel (push_tile.cu); 2D, patches too large for its histogram and LPIC_PUSH_SORTED=1
         // (A/B runs): the round-1 cell-ordered kernel (push_sorted.cu)
@@ -296,6 +296,6 @@ extern "C" int lpic_species_init_uniform(lpic_ctx *c, int ispec, int64_t ppc, do
     LAUNCHED(1);
     KERNEL_CHECK();
     sp.sort.valid = false;
-    sp.lists_valid = false;
+    sp.lists_valid = false; sp.sort.keys_valid = sp.sort.keys_written = false;
     return 0;
 }
