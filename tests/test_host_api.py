@@ -261,3 +261,36 @@ def test_timer_records_have_the_format_timer_stat_parses(tmp_path):
     assert len(lines) == 1
     m = re.search(r"Rank \d+ (.*?) took ([\d.]+)ms", lines[0].split("|")[-1].strip())
     assert m and m.group(1) == "unified pusher for electron" and float(m.group(2)) >= 2.0
+
+
+def test_particle_transfers_batch_the_record_attributes():
+    """Engine.upload_particles / download_particles move x y z w ux uy uz inv_gamma (the device's 64-byte records) through ONE
+    lpic_*_particle_records call with the right mask and pointer table, and everything else attribute by attribute."""
+    import ctypes as C
+    import types
+    from lambdapic_b200 import engine as E
+    calls = []
+
+    class FakeLib:
+        def __getattr__(self, name):
+            def f(*args):
+                calls.append((name, args))
+                return 0
+            return f
+
+    attrs = ["x", "y", "z", "w", "ux", "uy", "uz", "inv_gamma", "_id"]
+    host = {a: np.zeros(8) for a in attrs}
+    host["is_dead"] = np.zeros(8, dtype=np.uint8)
+    eng = types.SimpleNamespace(L=FakeLib(), ctx=None, species=[types.SimpleNamespace(attrs=attrs, host=host)])
+    eng._record_table = types.MethodType(E.DeviceEngine._record_table, eng)
+    E.DeviceEngine.upload_particles(eng, 0)
+    names = [c[0] for c in calls]
+    assert names == ["lpic_upload_particle_records", "lpic_upload_particles", "lpic_upload_particles"]
+    _, (_, ispec, mask, tab) = calls[0]
+    assert ispec == 0 and mask == 0xFF
+    assert [tab[i] for i in range(8)] == [host[a].ctypes.data for a in attrs[:8]]
+    assert sorted(c[1][2] for c in calls[1:]) == sorted([E.PART_ATTRS.index("_id"), E.P_IS_DEAD])
+    calls.clear()
+    E.DeviceEngine.download_particles(eng, 0, attrs=["ux", "is_dead"])
+    assert [c[0] for c in calls] == ["lpic_download_particle_records", "lpic_download_particles"]
+    assert calls[0][1][2] == 1 << E.PART_ATTRS.index("ux") and calls[1][1][2] == E.P_IS_DEAD
