@@ -416,33 +416,35 @@ extern "C" int lpic_sort(lpic_ctx *c, int ispec, int reverse_x, int64_t nxb, int
         // Off by default: measured at 128^3 x 32+32 ppc, the sorter gains 0.63 ms per step and the migration's passes lose
         // 0.36 ms computing the keys (net 0.9 % of the step); LPIC_SORT_KEY_CACHE=1 turns it on (all GPU tests pass with it).
         static const bool enabled = getenv("LPIC_SORT_KEY_CACHE") != nullptr;
-        if (!st.h_korg) {
-            st.h_korg = new double[3 * n];
-            CUDA_TRY(cudaMalloc(&st.d_korg, sizeof(double) * 3 * n));
-            st.have_kp = false;
-        }
         SortKeyParams kp;
-        kp.org = st.d_korg; kp.npatch = (int)n; kp.nxb = (int)nxb; kp.nyb = (int)nyb; kp.nzb = (int)nzb; kp.nbin = (int)nbin;
+        kp.org = nullptr; kp.npatch = (int)n; kp.nxb = (int)nxb; kp.nyb = (int)nyb; kp.nzb = (int)nzb; kp.nbin = (int)nbin;
         kp.reverse_x = reverse_x; kp.dim = g.dim; kp.dxb = dxb; kp.dyb = dyb; kp.dzb = dzb;
-        const bool same = st.have_kp && memcmp(st.h_korg, org.data(), sizeof(double) * 3 * n) == 0 && st.kp.nxb == kp.nxb &&
-                          st.kp.nyb == kp.nyb && st.kp.nzb == kp.nzb && st.kp.reverse_x == kp.reverse_x && st.kp.dim == kp.dim &&
-                          st.kp.dxb == kp.dxb && st.kp.dyb == kp.dyb && st.kp.dzb == kp.dzb;
-        use_cache = enabled && same && st.keys_valid && st.kcache && st.kcache_cap >= sp.total;
-        if (!same) {
-            memcpy(st.h_korg, org.data(), sizeof(double) * 3 * n);
-            CUDA_TRY(cudaMemcpyAsync(st.d_korg, st.h_korg, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
-            CUDA_TRY(cudaStreamSynchronize(c->stream));  // (org is a local vector)
+        if (enabled) {
+            if (!st.h_korg) {
+                st.h_korg = new double[3 * n];
+                CUDA_TRY(cudaMalloc(&st.d_korg, sizeof(double) * 3 * n));
+                st.have_kp = false;
+            }
+            kp.org = st.d_korg;
+            const bool same = st.have_kp && memcmp(st.h_korg, org.data(), sizeof(double) * 3 * n) == 0 && st.kp.nxb == kp.nxb &&
+                              st.kp.nyb == kp.nyb && st.kp.nzb == kp.nzb && st.kp.reverse_x == kp.reverse_x && st.kp.dim == kp.dim &&
+                              st.kp.dxb == kp.dxb && st.kp.dyb == kp.dyb && st.kp.dzb == kp.dzb;
+            use_cache = same && st.keys_valid && st.kcache && st.kcache_cap >= sp.total;
+            if (!same) {
+                memcpy(st.h_korg, org.data(), sizeof(double) * 3 * n);
+                CUDA_TRY(cudaMemcpyAsync(st.d_korg, st.h_korg, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+            }
+            if (st.kcache_cap < sp.total) {  // (re)allocated here, filled by the next migration
+                CUDA_TRY(cudaStreamSynchronize(c->stream));
+                cudaFree(st.kcache);
+                st.kcache = nullptr; st.kcache_cap = 0;
+                CUDA_TRY(cudaMalloc(&st.kcache, sizeof(int) * (size_t)sp.total));
+                st.kcache_cap = sp.total;
+                use_cache = false;
+            }
         }
-        st.kp = kp;
+        st.kp = kp;          // (the sorter's own key computation reads these too)
         st.have_kp = enabled;
-        if (enabled && st.kcache_cap < sp.total) {  // (re)allocated here, filled by the next migration
-            CUDA_TRY(cudaStreamSynchronize(c->stream));
-            cudaFree(st.kcache);
-            st.kcache = nullptr; st.kcache_cap = 0;
-            CUDA_TRY(cudaMalloc(&st.kcache, sizeof(int) * (size_t)sp.total));
-            st.kcache_cap = sp.total;
-            use_cache = false;
-        }
     }
     SortArgs a;
     a.kp = st.kp; a.kp.org = c->d_sort_org;
